@@ -1,0 +1,312 @@
+"""ctypes binding of the C ABI in include/catint_pnp.h and the cell-batch container.
+
+PyTorch is only used for device memory, streams and (elsewhere)
+torch.distributed; the solver itself is the hand-written CUDA library
+``libcatint_pnp.so`` built from catint_b200/csrc.  There is NO CPU fallback:
+every compute entry point raises if the library or a B200 is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+MAX_SPECIES = 14
+MAX_REACTIONS = 12
+MAX_REACTANTS = 4
+
+BC_DIRICHLET_WALL_NEUMANN_BULK = 0
+BC_STERN_ROBIN = 1
+MODE_TRANSIENT = 0
+MODE_STEADY = 1
+
+CELL_STATUS = {0: 'converged', 1: 'max_steps', 2: 'corrector_failed', 3: 'error_test_failed',
+               4: 'not_finite', 5: 'polish_failed'}
+
+_LIB_NAME = 'libcatint_pnp.so'
+_lib = None
+
+
+class CatintPnpShared(ctypes.Structure):
+    _fields_ = [
+        ('S', ctypes.c_int32), ('nx_max', ctypes.c_int32), ('R', ctypes.c_int32),
+        ('poisson_bc', ctypes.c_int32), ('use_migration', ctypes.c_int32), ('n_mesh', ctypes.c_int32),
+        ('z', ctypes.c_int32 * MAX_SPECIES),
+        ('educt', (ctypes.c_int32 * MAX_REACTANTS) * MAX_REACTIONS),
+        ('product', (ctypes.c_int32 * MAX_REACTANTS) * MAX_REACTIONS),
+        ('kf', ctypes.c_double * MAX_REACTIONS),
+        ('kr', ctypes.c_double * MAX_REACTIONS),
+        ('nu', (ctypes.c_double * MAX_REACTIONS) * MAX_SPECIES),
+    ]
+
+
+class CatintPnpCells(ctypes.Structure):
+    _fields_ = [('par', ctypes.c_void_p), ('nx', ctypes.c_void_p), ('mesh_id', ctypes.c_void_p),
+                ('mesh_xi', ctypes.c_void_p)]
+
+
+class CatintPnpControl(ctypes.Structure):
+    _fields_ = [('mode', ctypes.c_int32), ('max_steps', ctypes.c_int32), ('n_out', ctypes.c_int32),
+                ('polish_max_iter', ctypes.c_int32),
+                ('rtol', ctypes.c_double), ('atol', ctypes.c_double), ('h0', ctypes.c_double),
+                ('polish_rtol', ctypes.c_double), ('t_out', ctypes.POINTER(ctypes.c_double))]
+
+
+EXPORTS = ['catint_pnp_version', 'catint_pnp_last_error', 'catint_pnp_device_count',
+           'catint_pnp_workspace_bytes', 'catint_pnp_rhs_batch', 'catint_pnp_jacobian_batch',
+           'catint_pnp_solve_batch']
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library():
+    """dlopen the in-tree CUDA library (built by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.isfile(path):
+        raise RuntimeError('catint_b200: %s not found; run `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(there is no CPU fallback)' % path)
+    lib = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    lib.catint_pnp_version.restype = ctypes.c_int
+    lib.catint_pnp_last_error.restype = ctypes.c_char_p
+    lib.catint_pnp_device_count.restype = ctypes.c_int
+    lib.catint_pnp_workspace_bytes.restype = ctypes.c_size_t
+    lib.catint_pnp_workspace_bytes.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.c_int64]
+    lib.catint_pnp_rhs_batch.restype = ctypes.c_int
+    lib.catint_pnp_rhs_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
+                                         ctypes.c_int64, vp, vp, vp, vp, vp]
+    lib.catint_pnp_jacobian_batch.restype = ctypes.c_int
+    lib.catint_pnp_jacobian_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
+                                              ctypes.c_int64, vp, vp, vp, vp, vp, vp]
+    lib.catint_pnp_solve_batch.restype = ctypes.c_int
+    lib.catint_pnp_solve_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
+                                           ctypes.c_int64, vp, ctypes.POINTER(CatintPnpControl),
+                                           vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    _lib = lib
+    return lib
+
+
+def npar(S):
+    return 3 * S + 8
+
+
+class CellBatch(object):
+    """Structure-of-arrays description of B independent cells (host, numpy).
+
+    species-level tables are shared by the batch; everything a descriptor can
+    change is per cell (``par`` records, see include/catint_pnp.h).
+    """
+
+    def __init__(self, z, reactions, nu, par, nx, nx_max=None, use_migration=True,
+                 poisson_bc=BC_DIRICHLET_WALL_NEUMANN_BULK, mesh_id=None, mesh_xi=None, species=None):
+        self.z = np.asarray(z, dtype=np.int32)
+        self.S = len(self.z)
+        self.reactions = [(list(e), list(p), float(kf), float(kr)) for (e, p, kf, kr) in reactions]
+        self.R = len(self.reactions)
+        self.nu = np.asarray(nu, dtype=np.float64).reshape(self.S, max(self.R, 0)) if self.R else np.zeros((self.S, 0))
+        self.par = np.ascontiguousarray(par, dtype=np.float64)
+        self.nx = np.ascontiguousarray(nx, dtype=np.int32)
+        self.B = len(self.nx)
+        assert self.par.shape == (self.B, npar(self.S)), (self.par.shape, self.B, npar(self.S))
+        self.nx_max = int(nx_max if nx_max is not None else self.nx.max())
+        self.use_migration = bool(use_migration)
+        self.poisson_bc = int(poisson_bc)
+        self.mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.int32)
+        self.mesh_xi = None if mesh_xi is None else np.ascontiguousarray(mesh_xi, dtype=np.float64)
+        self.species = list(species) if species is not None else None
+        if self.S > MAX_SPECIES or self.R > MAX_REACTIONS:
+            raise ValueError('at most %d species and %d reactions' % (MAX_SPECIES, MAX_REACTIONS))
+
+    @property
+    def b(self):
+        return self.S + (2 if self.poisson_bc == BC_STERN_ROBIN else 1)
+
+    def shared_struct(self):
+        sh = CatintPnpShared()
+        sh.S, sh.nx_max, sh.R = self.S, self.nx_max, self.R
+        sh.poisson_bc, sh.use_migration = self.poisson_bc, int(self.use_migration)
+        sh.n_mesh = 0 if self.mesh_xi is None else int(self.mesh_xi.shape[0])
+        for k in range(self.S):
+            sh.z[k] = int(self.z[k])
+        for r in range(MAX_REACTIONS):
+            for e in range(MAX_REACTANTS):
+                sh.educt[r][e] = -1
+                sh.product[r][e] = -1
+        for r, (ed, pr, kf, kr) in enumerate(self.reactions):
+            if len(ed) > MAX_REACTANTS or len(pr) > MAX_REACTANTS:
+                raise ValueError('at most %d reactants per reaction side' % MAX_REACTANTS)
+            for e, k in enumerate(ed):
+                sh.educt[r][e] = int(k)
+            for e, k in enumerate(pr):
+                sh.product[r][e] = int(k)
+            sh.kf[r], sh.kr[r] = kf, kr
+            for k in range(self.S):
+                sh.nu[k][r] = float(self.nu[k, r])
+        return sh
+
+    def select(self, idx):
+        """sub-batch (used for sharding cells over ranks)."""
+        idx = np.asarray(idx)
+        return CellBatch(self.z, self.reactions, self.nu, self.par[idx], self.nx[idx], nx_max=self.nx_max,
+                         use_migration=self.use_migration, poisson_bc=self.poisson_bc,
+                         mesh_id=None if self.mesh_id is None else self.mesh_id[idx], mesh_xi=self.mesh_xi,
+                         species=self.species)
+
+
+def stoichiometry(S, reactions, rate_mode='summed'):
+    """nu[S,R] with R_k = sum_r nu[k,r]*net_r.  'summed' = live semantics of the
+    reference (catint/comsol_model.py:809-846); 'legacy_overwrite' = literal
+    behaviour of catint/calculator.py:145-194 where every reactant first resets
+    its rate, so only the last reaction touching a species survives, once."""
+    nu = np.zeros((S, len(reactions)))
+    for r, (ed, pr, kf, kr) in enumerate(reactions):
+        if rate_mode == 'summed':
+            for k in ed:
+                nu[k, r] -= 1.0
+            for k in pr:
+                nu[k, r] += 1.0
+        elif rate_mode == 'legacy_overwrite':
+            for k in ed:
+                nu[k, :] = 0.0
+                nu[k, r] = -1.0
+            for k in pr:
+                nu[k, :] = 0.0
+                nu[k, r] = +1.0
+        else:
+            raise ValueError(rate_mode)
+    return nu
+
+
+class DeviceBatch(object):
+    """CellBatch uploaded to one GPU (torch tensors keep the memory alive)."""
+
+    def __init__(self, batch, device, pinned=None):
+        import torch
+        self.batch = batch
+        self.device = torch.device(device)
+        src = pinned if pinned is not None else {}
+        def up(name, arr, dtype):
+            if arr is None:
+                return None
+            t = src.get(name)
+            if t is None:
+                t = torch.from_numpy(np.ascontiguousarray(arr))
+            return t.to(self.device, dtype=dtype, non_blocking=True)
+        self.par = up('par', batch.par, torch.float64)
+        self.nx = up('nx', batch.nx, torch.int32)
+        self.mesh_id = up('mesh_id', batch.mesh_id, torch.int32)
+        self.mesh_xi = up('mesh_xi', batch.mesh_xi, torch.float64)
+        self.shared = batch.shared_struct()
+        self.cells = CatintPnpCells()
+        self.cells.par = self.par.data_ptr()
+        self.cells.nx = self.nx.data_ptr()
+        self.cells.mesh_id = self.mesh_id.data_ptr() if self.mesh_id is not None else None
+        self.cells.mesh_xi = self.mesh_xi.data_ptr() if self.mesh_xi is not None else None
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in
+                             (self.par, self.nx, self.mesh_id, self.mesh_xi) if t is not None)
+
+
+class PnpBackend(object):
+    """Thin launcher: torch tensors in, torch tensors out, one CUDA stream."""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available() or self.lib.catint_pnp_device_count() <= 0:
+            raise RuntimeError('catint_b200: no B200 (sm_100) device visible; the solver has no CPU fallback')
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self._ws = None
+        self.launches = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError('%s failed (%d): %s' % (what, rc, self.lib.catint_pnp_last_error().decode()))
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload(self, batch, pinned=None):
+        with self.torch.cuda.device(self.device):
+            return DeviceBatch(batch, self.device, pinned=pinned)
+
+    def workspace(self, dbatch):
+        need = self.lib.catint_pnp_workspace_bytes(ctypes.byref(dbatch.shared), dbatch.batch.B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        return self._ws, need
+
+    # -- K1 ---------------------------------------------------------------
+    def rhs(self, dbatch, c):
+        """c [B,nx_max,S] (device, float64) -> (dcdt, g, phi)"""
+        torch = self.torch
+        b = dbatch.batch
+        assert c.shape == (b.B, b.nx_max, b.S) and c.dtype == torch.float64 and c.is_contiguous()
+        dcdt = torch.zeros_like(c)
+        g = torch.zeros((b.B, b.nx_max), dtype=torch.float64, device=self.device)
+        phi = torch.zeros_like(g)
+        with torch.cuda.device(self.device):
+            rc = self.lib.catint_pnp_rhs_batch(ctypes.byref(dbatch.shared), ctypes.byref(dbatch.cells), b.B,
+                                               c.data_ptr(), dcdt.data_ptr(), g.data_ptr(), phi.data_ptr(),
+                                               self._stream())
+        self._check(rc, 'catint_pnp_rhs_batch')
+        self.launches += 1
+        return dcdt, g, phi
+
+    # -- K2 ---------------------------------------------------------------
+    def jacobian(self, dbatch, y):
+        """y [B,nx_max,b] -> (F [B,nx,b], Lb, Db, Ub [B,nx,b,b])"""
+        torch = self.torch
+        b = dbatch.batch
+        nb = b.b
+        assert y.shape == (b.B, b.nx_max, nb) and y.dtype == torch.float64 and y.is_contiguous()
+        F = torch.zeros_like(y)
+        blocks = [torch.zeros((b.B, b.nx_max, nb, nb), dtype=torch.float64, device=self.device) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            rc = self.lib.catint_pnp_jacobian_batch(ctypes.byref(dbatch.shared), ctypes.byref(dbatch.cells), b.B,
+                                                    y.data_ptr(), F.data_ptr(), blocks[0].data_ptr(),
+                                                    blocks[1].data_ptr(), blocks[2].data_ptr(), self._stream())
+        self._check(rc, 'catint_pnp_jacobian_batch')
+        self.launches += 1
+        return F, blocks[0], blocks[1], blocks[2]
+
+    # -- K3 ---------------------------------------------------------------
+    def solve(self, dbatch, t_out, mode=MODE_STEADY, rtol=1.49012e-8, atol=1.49012e-8, y0=None,
+              max_steps=100000, h0=0.0, polish_rtol=1e-10, polish_max_iter=8):
+        """returns dict of device tensors: c [n_out,B,nx,S], phi, g [n_out,B,nx],
+        flux [B,S], status, n_steps, n_newton [B]"""
+        torch = self.torch
+        b = dbatch.batch
+        t_out = np.ascontiguousarray(np.atleast_1d(np.asarray(t_out, dtype=np.float64)))
+        n_out = len(t_out)
+        dev = self.device
+        out = {
+            'c': torch.zeros((n_out, b.B, b.nx_max, b.S), dtype=torch.float64, device=dev),
+            'phi': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=dev),
+            'g': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=dev),
+            'flux': torch.zeros((b.B, b.S), dtype=torch.float64, device=dev),
+            'status': torch.full((b.B,), -1, dtype=torch.int32, device=dev),
+            'n_steps': torch.zeros((b.B,), dtype=torch.int32, device=dev),
+            'n_newton': torch.zeros((b.B,), dtype=torch.int32, device=dev),
+        }
+        ws, need = self.workspace(dbatch)
+        ctl = CatintPnpControl()
+        ctl.mode, ctl.max_steps, ctl.n_out, ctl.polish_max_iter = int(mode), int(max_steps), n_out, int(polish_max_iter)
+        ctl.rtol, ctl.atol, ctl.h0, ctl.polish_rtol = float(rtol), float(atol), float(h0), float(polish_rtol)
+        ctl.t_out = t_out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if y0 is not None:
+            assert y0.shape == (b.B, b.nx_max, b.S) and y0.dtype == torch.float64 and y0.is_contiguous()
+        with torch.cuda.device(dev):
+            rc = self.lib.catint_pnp_solve_batch(
+                ctypes.byref(dbatch.shared), ctypes.byref(dbatch.cells), b.B,
+                y0.data_ptr() if y0 is not None else None, ctypes.byref(ctl),
+                out['c'].data_ptr(), out['phi'].data_ptr(), out['g'].data_ptr(), out['flux'].data_ptr(),
+                out['status'].data_ptr(), out['n_steps'].data_ptr(), out['n_newton'].data_ptr(),
+                ws.data_ptr(), ctypes.c_size_t(need), self._stream())
+        self._check(rc, 'catint_pnp_solve_batch')
+        self.launches += 1
+        return out

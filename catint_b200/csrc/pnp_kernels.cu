@@ -1,0 +1,1029 @@
+// pnp_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/catint_pnp.h
+//
+//   K1  pnp_rhs_kernel       dc/dt of the reference ODE (streaming stencil, HBM bound)
+//   K2  pnp_jacobian_kernel  residual + block-tridiagonal Jacobian blocks (parity/debug)
+//   K3  pnp_bdf_kernel       per-cell BDF/Newton integrator with fused assembly +
+//                            block-Thomas solve (see pnp_solver.cuh)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/catint_pnp.h"
+#include "pnp_solver.cuh"
+
+namespace catint {
+
+// ===========================================================================
+// cell set-up shared by all kernels
+// ===========================================================================
+__device__ __forceinline__ void load_cell(const DevTables& tb, const double* par, const int* nx,
+                                          const int* mesh_id, const double* mesh_xi, long long cell,
+                                          int lane, CellScalars& cs, CellSpecies* sp) {
+    const int S = tb.S;
+    const double* p = par + (size_t)cell * CATINT_PNP_NPAR(S);
+    cs.n = nx[cell];
+    const int mid = mesh_id ? mesh_id[cell] : -1;
+    cs.uniform = mid < 0;
+    cs.xi = mid < 0 ? nullptr : mesh_xi + (size_t)mid * tb.nx_max;
+    cs.beta = p[CATINT_PNP_P_BETA(S)];
+    cs.eps = p[CATINT_PNP_P_EPS(S)];
+    cs.phi_wall = p[CATINT_PNP_P_PHIWALL(S)];
+    cs.g_bulk = p[CATINT_PNP_P_GBULK(S)];
+    cs.cstern = p[CATINT_PNP_P_CSTERN(S)];
+    cs.dx = p[CATINT_PNP_P_SCALE(S)];
+    if (lane < S) {
+        sp->cb[lane] = p[CATINT_PNP_P_CBULK(S) + lane];
+        sp->J[lane] = p[CATINT_PNP_P_FLUX(S) + lane];
+        sp->D[lane] = p[CATINT_PNP_P_DIFF(S) + lane];
+        const double q = tb.z[lane] * UNIT_F;
+        sp->q[lane] = q;
+        sp->bq[lane] = cs.beta * q;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// g from the concentrations stored in y (default Poisson BCs): g_{n-1}=g_bulk,
+// g_i = g_{i+1} + h_i*sum_k q_k c_{k,i}/eps, g_0 by linear extrapolation
+// (calculator_old.py:753-759,793-796).  Sequential, one lane; y is [n][NB].
+template <int NB>
+__device__ void consistent_field(const WarpState<NB>& ws, double* y) {
+    constexpr int S = NB - 1;
+    const int n = ws.cs.n;
+    if (ws.lane == 0) {
+        if (!ws.tb->use_migration) {
+            for (int i = 0; i < n; ++i) y[(size_t)i * NB + S] = 0.0;
+        } else {
+            double g = ws.cs.g_bulk;
+            y[(size_t)(n - 1) * NB + S] = g;
+            for (int i = n - 2; i >= 1; --i) {
+                const NodeCoef k = interior_coef(ws.cs, i);
+                double lapl = 0.0;
+                for (int s = 0; s < S; ++s) lapl -= ws.sp->q[s] * y[(size_t)i * NB + s] / ws.cs.eps;
+                g = g - lapl * k.hi;
+                y[(size_t)i * NB + S] = g;
+            }
+            const WallCoef w = wall_coef(ws.cs);
+            const double g1 = y[NB + S], g2 = y[2 * NB + S];
+            y[S] = g1 + (g1 - g2) * w.ext;
+        }
+    }
+    __syncwarp();
+}
+
+// ===========================================================================
+// K3: the integrator
+// ===========================================================================
+template <int NB>
+struct Bdf {
+    int q, qwait, nst;
+    double h, hscale, t, etamax, saved_tq5;
+    double tau[QMAX + 2], l[QMAX + 2], tq[6];
+};
+
+template <int NB>
+__device__ void set_bdf(Bdf<NB>& B) {
+    const int q = B.q;
+    const double h = B.h;
+    double* l = B.l; double* tq = B.tq; const double* tau = B.tau;
+    for (int i = 0; i < QMAX + 2; ++i) l[i] = 0.0;
+    l[0] = l[1] = 1.0;
+    double xi_inv = 1.0, xistar_inv = 1.0, alpha0 = -1.0, alpha0_hat = -1.0, hsum = h;
+    if (q > 1) {
+        for (int j = 2; j < q; ++j) {
+            hsum += tau[j - 1];
+            xi_inv = h / hsum;
+            alpha0 -= 1.0 / j;
+            for (int i = j; i >= 1; --i) l[i] += l[i - 1] * xi_inv;
+        }
+        alpha0 -= 1.0 / q;
+        xistar_inv = -l[1] - alpha0;
+        hsum += tau[q - 1];
+        xi_inv = h / hsum;
+        alpha0_hat = -l[1] - xi_inv;
+        for (int i = q; i >= 1; --i) l[i] += l[i - 1] * xistar_inv;
+    }
+    const double A1 = 1.0 - alpha0_hat + alpha0;
+    const double A2 = 1.0 + q * A1;
+    tq[2] = fabs(A1 / (alpha0 * A2));
+    tq[5] = fabs(A2 * xistar_inv / (l[q] * xi_inv));
+    tq[1] = 1.0; tq[3] = 1.0;
+    if (B.qwait == 1) {
+        if (q > 1) {
+            const double C = xistar_inv / l[q];
+            const double A3 = alpha0 + 1.0 / q;
+            const double A4 = alpha0_hat + xi_inv;
+            tq[1] = fabs(C * (1.0 - A4 + A3) / A3);
+        }
+        hsum += tau[q];
+        xi_inv = h / hsum;
+        const double A5 = alpha0 - 1.0 / (q + 1);
+        const double A6 = alpha0_hat - xi_inv;
+        tq[3] = fabs(((1.0 - A6 + A5) / A2) / (xi_inv * (q + 2) * A5));
+    }
+    tq[4] = NLSCOEF / tq[2];
+}
+
+// coefficients for an order increase / decrease (applied inside the begin-step pass)
+template <int NB>
+__device__ void increase_coef(const Bdf<NB>& B, double* l, double& A1) {
+    const int q = B.q;
+    for (int i = 0; i < QMAX + 2; ++i) l[i] = 0.0;
+    double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0, hsum = B.hscale;
+    l[2] = 1.0;
+    if (q > 1) {
+        for (int j = 1; j < q; ++j) {
+            hsum += B.tau[j + 1];
+            const double xi = hsum / B.hscale;
+            prod *= xi;
+            alpha0 -= 1.0 / (j + 1);
+            alpha1 += 1.0 / xi;
+            for (int i = j + 2; i >= 2; --i) l[i] = l[i] * xiold + l[i - 1];
+            xiold = xi;
+        }
+    }
+    A1 = (-alpha0 - alpha1) / prod;
+}
+
+template <int NB>
+__device__ void decrease_coef(const Bdf<NB>& B, double* l) {
+    const int q = B.q;
+    for (int i = 0; i < QMAX + 2; ++i) l[i] = 0.0;
+    l[2] = 1.0;
+    double hsum = 0.0;
+    for (int j = 1; j <= q - 2; ++j) {
+        hsum += B.tau[j];
+        const double xi = hsum / B.hscale;
+        for (int i = j + 2; i >= 2; --i) l[i] = l[i] * xi + l[i - 1];
+    }
+}
+
+// The history pass that opens every step attempt.  In one sweep over the N unknowns:
+//   (undo)   inverse Pascal of a rejected attempt
+//   (order)  raise (+1, needs acor in zb) or lower (-1) the order
+//   (scale)  zn[j] *= eta^j
+//   (predict) Pascal triangle
+//   y = zn[0], psi = rl1*zn[1] - zn[0]
+// q_old is the order the array currently has, q_new the order after the change.
+template <int NB>
+__device__ void history_pass(WarpState<NB>& ws, int q_old, int dq, bool undo, double eta,
+                             const double* lc, double A1, double rl1, bool predict) {
+    const int N = ws.N;
+    const int q_new = q_old + dq;
+    for (int idx = ws.lane; idx < N; idx += 32) {
+        double z[LMAX];
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j) z[j] = (j <= q_old) ? ws.zn[(size_t)j * N + idx] : 0.0;
+        if (undo) {
+#pragma unroll
+            for (int k = 1; k <= QMAX; ++k)
+#pragma unroll
+                for (int j = QMAX; j >= k; --j)
+                    if (k <= q_old && j <= q_old) z[j - 1] -= z[j];
+        }
+        if (dq > 0) {
+            const double zl = A1 * ws.zb[idx];
+#pragma unroll
+            for (int j = 2; j <= QMAX; ++j) {
+                if (j <= q_old) z[j] += lc[j] * zl;
+                if (j == q_new) z[j] = zl;
+            }
+            if (q_new == 1) z[1] = zl;   // cannot happen (q_old >= 1), kept for clarity
+        } else if (dq < 0) {
+            double zq = 0.0;
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j) if (j == q_old) zq = z[j];
+#pragma unroll
+            for (int j = 2; j < QMAX; ++j)
+                if (j < q_old) z[j] -= lc[j] * zq;
+        }
+        if (eta != 1.0) {
+            double f = eta;
+#pragma unroll
+            for (int j = 1; j <= QMAX; ++j) {
+                if (j <= q_new) z[j] *= f;
+                f *= eta;
+            }
+        }
+        if (predict) {
+#pragma unroll
+            for (int k = 1; k <= QMAX; ++k)
+#pragma unroll
+                for (int j = QMAX; j >= k; --j)
+                    if (k <= q_new && j <= q_new) z[j - 1] += z[j];
+        }
+#pragma unroll
+        for (int j = 0; j < LMAX; ++j)
+            if (j <= q_new) ws.zn[(size_t)j * N + idx] = z[j];
+        if (predict) {
+            ws.y[idx] = z[0];
+            ws.psi[idx] = rl1 * z[1] - z[0];
+        }
+    }
+    __syncwarp();
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
+    constexpr int S = NB - 1;
+    constexpr int WARPS = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cell = (long long)blockIdx.x * WARPS + warp;
+
+    // shared layout: tables | per warp { CellSpecies | scratch | [y psi zb] }
+    DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
+    {
+        const int words = (int)(sizeof(DevTables) / 4);
+        const int* src = reinterpret_cast<const int*>(&P.tb);
+        int* dst = reinterpret_cast<int*>(tb);
+        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
+    const int nxm = P.tb.nx_max;
+    const size_t state_doubles = P.state_in_smem ? (size_t)3 * nxm * NB : 0;
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
+                            (size_t)(scratch_doubles<NB>() + state_doubles) * sizeof(double);
+    unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
+    if (cell >= P.n_cells) return;
+
+    WarpState<NB> ws;
+    ws.lane = lane;
+    ws.tb = tb;
+    CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
+    ws.sp = sp;
+    ws.scratch = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
+    load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
+    const int n = ws.cs.n;
+    const int N = n * NB;
+    ws.N = N;
+    double* g = P.ws + (size_t)cell * P.ws_stride;
+    ws.zn = g;                 g += (size_t)LMAX * nxm * NB;
+    ws.ewt = g;                g += (size_t)nxm * NB;
+    ws.W = g;                  g += (size_t)nxm * NB * NB;
+    ws.V0 = g;                 g += (size_t)NB * NB;
+    if (P.state_in_smem) {
+        double* s = ws.scratch + scratch_doubles<NB>();
+        ws.y = s; ws.psi = s + (size_t)nxm * NB; ws.zb = s + (size_t)2 * nxm * NB;
+    } else {
+        ws.y = g; ws.psi = g + (size_t)nxm * NB; ws.zb = g + (size_t)2 * nxm * NB;
+    }
+
+    // ---- initial state: y0 (or bulk) with the consistent field --------------
+    for (int idx = lane; idx < N; idx += 32) {
+        const int i = idx / NB, r = idx - i * NB;
+        double v = 0.0;
+        if (r < S) v = P.y0 ? P.y0[((size_t)cell * nxm + i) * S + r] : sp->cb[r];
+        ws.y[idx] = v;
+        ws.psi[idx] = 0.0;
+    }
+    __syncwarp();
+    consistent_field<NB>(ws, ws.y);
+
+    const double rtol = P.rtol, atol = P.atol;
+    double* sl = ws.scratch + 2 * (NB + 1);
+    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB; double* sf = sua + NB;
+
+    // zn[0]=y, zn[1]=h*f(y) (mass rows), ewt; first step size from the initial rate of change
+    double fnorm = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double F = node_rows<NB>(ws, ws.y, i, sl, sa, sud, sua, sf);
+        if (lane < NB) {
+            const size_t idx = (size_t)i * NB + lane;
+            const bool mass = lane < S && i < n - 1;
+            const double yv = ws.y[idx];
+            const double w = 1.0 / (rtol * fabs(yv) + atol);
+            ws.ewt[idx] = w;
+            ws.zn[idx] = yv;
+            ws.zn[(size_t)N + idx] = mass ? F : 0.0;      // scaled by h below
+            if (mass) fnorm = fmax(fnorm, fabs(F) * w);
+        }
+        __syncwarp();
+    }
+    fnorm = warp_max(fnorm);
+
+    Bdf<NB> B;
+    B.q = 1; B.qwait = 2; B.nst = 0; B.t = 0.0; B.etamax = ETAMX1; B.saved_tq5 = 0.0;
+    for (int i = 0; i < QMAX + 2; ++i) { B.tau[i] = 0.0; B.l[i] = 0.0; }
+    const double t_end = P.t_out[P.n_out - 1];
+    double h0 = P.h0;
+    if (!(h0 > 0.0)) {
+        h0 = fnorm > 0.0 ? 1.0 / fnorm : 1e-6;
+        h0 = fmin(h0, 1e-3 * (t_end > 0.0 ? t_end : 1.0));
+    }
+    B.h = B.hscale = h0;
+    for (int idx = lane; idx < N; idx += 32) ws.zn[(size_t)N + idx] *= h0;
+    __syncwarp();
+
+    int status = CATINT_PNP_CELL_CONVERGED;
+    int nni = 0, iout = 0;
+    // pending transformation of the history array for the next attempt
+    int pend_dq = 0; bool pend_undo = false; double pend_eta = 1.0;
+    double lc[QMAX + 2]; double A1c = 0.0;
+    for (int i = 0; i < QMAX + 2; ++i) lc[i] = 0.0;
+
+    while (iout < P.n_out && status == CATINT_PNP_CELL_CONVERGED) {
+        if (B.nst >= P.max_steps) { status = CATINT_PNP_CELL_MAX_STEPS; break; }
+        int ncf = 0, nef = 0;
+        const double saved_t = B.t;
+        double dsm = 0.0;
+        bool accepted = false;
+        // ------------------------------------------------ attempts of one step
+        while (true) {
+            // order change (only on the first attempt) + rescale + predict, fused
+            const int q_old = B.q;
+            if (pend_dq > 0) increase_coef<NB>(B, lc, A1c);
+            else if (pend_dq < 0) decrease_coef<NB>(B, lc);
+            if (pend_dq != 0) { B.q += pend_dq; B.qwait = B.q + 1; }
+            if (pend_eta != 1.0) { B.h = B.hscale * pend_eta; B.hscale = B.h; }
+            B.t = saved_t + B.h;
+            set_bdf<NB>(B);
+            const double rl1 = 1.0 / B.l[1];
+            history_pass<NB>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+            pend_dq = 0; pend_undo = false; pend_eta = 1.0;
+            const double inv_gamma = B.l[1] / B.h;
+
+            // ---- Newton corrector --------------------------------------------
+            bool conv = false;
+            double crate = 1.0, delp = 0.0, acnrm = 0.0;
+            for (int m = 0; m < MAXCOR; ++m) {
+                const bool ok = forward_sweep<NB>(ws, inv_gamma);
+                ++nni;
+                if (!ok) break;
+                double del, acn;
+                backward_sweep<NB>(ws, del, acn, 0, 0.0, 0.0);
+                if (!(del <= 1e300)) break;
+                if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
+                const double dcon = del * fmin(1.0, crate) / B.tq[4];
+                if (dcon <= 1.0) { conv = true; acnrm = (m == 0) ? del : acn; break; }
+                if (m + 1 == MAXCOR || (m >= 1 && del > RDIV * delp)) break;
+                delp = del;
+            }
+            if (!conv) {
+                ++ncf;
+                B.etamax = 1.0;
+                B.t = saved_t;
+                if (ncf == MXNCF || B.h * ETACF < 1e-300) { status = CATINT_PNP_CELL_CORRECTOR_FAILED; break; }
+                pend_undo = true; pend_eta = ETACF;
+                continue;
+            }
+            dsm = acnrm * B.tq[2];
+            if (dsm <= 1.0) { accepted = true; break; }
+            // ---- error test failed ---------------------------------------------
+            ++nef;
+            B.etamax = 1.0;
+            B.t = saved_t;
+            if (nef == MXNEF) { status = CATINT_PNP_CELL_ERROR_TEST_FAILED; break; }
+            pend_undo = true;
+            if (nef <= MXNEF1) {
+                double eta = 1.0 / (pow(BIAS2 * dsm, 1.0 / (B.q + 1)) + ADDON);
+                eta = fmax(ETAMIN, eta);
+                if (nef >= SMALL_NEF) eta = fmin(eta, ETAMXF);
+                pend_eta = eta;
+            } else if (B.q > 1) {
+                pend_dq = -1;
+                pend_eta = ETAMIN;
+            } else {
+                // order 1 and still failing: restart the history from the last accepted state
+                history_pass<NB>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
+                pend_undo = false;
+                B.h *= ETAMIN; B.hscale = B.h;
+                B.qwait = LONG_WAIT;
+                for (int idx = lane; idx < N; idx += 32) ws.y[idx] = ws.zn[idx];
+                __syncwarp();
+                for (int i = 0; i < n; ++i) {
+                    const double F = node_rows<NB>(ws, ws.y, i, sl, sa, sud, sua, sf);
+                    if (lane < NB) {
+                        const bool mass = lane < S && i < n - 1;
+                        ws.zn[(size_t)N + (size_t)i * NB + lane] = mass ? B.h * F : 0.0;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (!accepted) break;
+
+        // ------------------------------------------------ complete the step
+        ++B.nst;
+        const int q = B.q;
+        for (int i = q; i >= 2; --i) B.tau[i] = B.tau[i - 1];
+        if (q == 1 && B.nst > 1) B.tau[2] = B.tau[1];
+        B.tau[1] = B.h;
+        --B.qwait;
+        const bool save_acor = (B.qwait == 1 && q != QMAX);
+        const bool want_eta = (B.etamax != 1.0) && (B.qwait == 0);
+        const bool want_up = want_eta && q != QMAX && B.saved_tq5 != 0.0;
+        double cquot = 0.0;
+        if (want_up) cquot = (B.tq[5] / B.saved_tq5) * pow(B.h / B.tau[2], (double)(q + 1));
+        double ddn = 0.0, dup = 0.0;
+        // correction pass: zn[j] += l[j]*acor, norms for the order selection, new weights
+        for (int idx = lane; idx < N; idx += 32) {
+            const int i = idx / NB, r = idx - i * NB;
+            const bool mass = r < S && i < n - 1;
+            const double yv = ws.y[idx];
+            const double ac = yv - ws.zn[idx];
+            const double w = ws.ewt[idx];
+            if (want_up && mass) dup = fmax(dup, fabs(ac - cquot * ws.zn[(size_t)QMAX * N + idx]) * w);
+            ws.zn[idx] = yv;
+#pragma unroll
+            for (int j = 1; j <= QMAX; ++j) {
+                if (j <= q) {
+                    const double v = ws.zn[(size_t)j * N + idx] + B.l[j] * ac;
+                    ws.zn[(size_t)j * N + idx] = v;
+                    if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w);
+                }
+            }
+            if (save_acor) ws.zn[(size_t)QMAX * N + idx] = ac;
+            ws.zb[idx] = ac;
+            ws.ewt[idx] = 1.0 / (rtol * fabs(yv) + atol);
+        }
+        __syncwarp();
+        if (save_acor) B.saved_tq5 = B.tq[5];
+
+        // ------------------------------------------------ next order and step size
+        int qprime = q;
+        double eta = 1.0;
+        if (B.etamax == 1.0) {
+            B.qwait = max(B.qwait, 2);
+        } else {
+            const double etaq = 1.0 / (pow(BIAS2 * dsm, 1.0 / (q + 1)) + ADDON);
+            if (B.qwait != 0) {
+                eta = etaq;
+            } else {
+                B.qwait = 2;
+                ddn = warp_max(ddn) * B.tq[1];
+                dup = warp_max(dup) * B.tq[3];
+                double etaqm1 = 0.0, etaqp1 = 0.0;
+                if (q > 1) etaqm1 = 1.0 / (pow(BIAS1 * ddn, 1.0 / q) + ADDON);
+                if (want_up) etaqp1 = 1.0 / (pow(BIAS3 * dup, 1.0 / (q + 2)) + ADDON);
+                const double etam = fmax(etaqm1, fmax(etaq, etaqp1));
+                if (etam < THRESH) eta = 1.0;
+                else if (etam == etaq) eta = etaq;
+                else if (etam == etaqm1) { eta = etaqm1; qprime = q - 1; }
+                else { eta = etaqp1; qprime = q + 1; }
+            }
+            if (eta < THRESH) eta = 1.0;
+            else eta = fmin(eta, B.etamax);
+        }
+        B.etamax = ETAMX2;
+
+        // ------------------------------------------------ dense output
+        while (iout < P.n_out && B.t >= P.t_out[iout] * (1.0 - 1e-14)) {
+            const double s = (P.t_out[iout] - B.t) / B.h;
+            const bool last = (iout == P.n_out - 1);
+            double* co = P.c_out + ((size_t)iout * P.n_cells + cell) * nxm * S;
+            double* go = P.g_out ? P.g_out + ((size_t)iout * P.n_cells + cell) * nxm : nullptr;
+            for (int idx = lane; idx < N; idx += 32) {
+                const int i = idx / NB, r = idx - i * NB;
+                double v = 0.0;
+#pragma unroll
+                for (int j = QMAX; j >= 0; --j)
+                    if (j <= q) v = v * s + ws.zn[(size_t)j * N + idx];
+                if (last) ws.y[idx] = v;           // kept for the steady polish / final outputs
+                if (!(last && P.mode == CATINT_PNP_MODE_STEADY)) {
+                    if (r < S) co[(size_t)i * S + r] = v;
+                    else if (go) go[i] = v;
+                }
+            }
+            __syncwarp();
+            ++iout;
+        }
+        if (iout >= P.n_out) break;
+        pend_dq = qprime - q;
+        pend_eta = eta;
+    }
+
+    // ---------------------------------------------------- steady-state polish
+    if (status == CATINT_PNP_CELL_CONVERGED && P.mode == CATINT_PNP_MODE_STEADY) {
+        double cscale = lane < S ? fabs(sp->cb[lane]) : 0.0;
+        cscale = warp_max(cscale);
+        const double patol = 1e-12 * fmax(cscale, 1e-300);
+        bool done = false;
+        for (int it = 0; it < P.polish_max_iter && !done; ++it) {
+            // psi = -y makes the mass term vanish together with inv_gamma = 0
+            const bool ok = forward_sweep<NB>(ws, 0.0);
+            ++nni;
+            if (!ok) break;
+            double del, acn;
+            backward_sweep<NB>(ws, del, acn, 1, P.polish_rtol, patol);
+            if (!(del <= 1e300)) break;
+            if (del <= 1.0) done = true;
+        }
+        if (!done) status = CATINT_PNP_CELL_POLISH_FAILED;
+    }
+
+    // ---------------------------------------------------- final outputs
+    {
+        const int io = P.n_out - 1;
+        double* co = P.c_out + ((size_t)io * P.n_cells + cell) * nxm * S;
+        double* go = P.g_out ? P.g_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
+        double* po = P.phi_out ? P.phi_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
+        if (P.mode == CATINT_PNP_MODE_STEADY || status != CATINT_PNP_CELL_CONVERGED) {
+            for (int idx = lane; idx < N; idx += 32) {
+                const int i = idx / NB, r = idx - i * NB;
+                const double v = ws.y[idx];
+                if (r < S) co[(size_t)i * S + r] = v;
+                else if (go) go[i] = v;
+            }
+        }
+        __syncwarp();
+        // potential by the forward cumulative sum of the reference (calculator_old.py:798-800)
+        if (po && lane == 0) {
+            double v = ws.cs.phi_wall;
+            po[0] = v;
+            double vm1 = v, vm2 = v;
+            for (int i = 1; i <= n - 2; ++i) {
+                const NodeCoef k = interior_coef(ws.cs, i);
+                v = v + ws.y[(size_t)i * NB + S] * k.him;
+                po[i] = v;
+                vm2 = vm1; vm1 = v;
+            }
+            if (n >= 3) {
+                const double ratio = ws.cs.uniform ? 1.0 :
+                    (ws.cs.xi[n - 1] - ws.cs.xi[n - 2]) / (ws.cs.xi[n - 2] - ws.cs.xi[n - 3]);
+                po[n - 1] = vm1 + (vm1 - vm2) * ratio;
+            }
+        }
+        if (P.flux_out && lane < S) {
+            const WallCoef w = wall_coef(ws.cs);
+            const double bq = tb->use_migration ? sp->bq[lane] : 0.0;
+            P.flux_out[(size_t)cell * S + lane] =
+                -sp->D[lane] * ((ws.y[2 * NB + lane] - ws.y[lane]) * w.w0 + bq * ws.y[NB + lane] * ws.y[NB + S]);
+        }
+        if (lane == 0) {
+            P.status[cell] = status;
+            P.n_steps[cell] = B.nst;
+            P.n_newton[cell] = nni;
+        }
+    }
+}
+
+// ===========================================================================
+// K2: residual and Jacobian blocks (one warp per cell), for parity checks
+// ===========================================================================
+struct JacParams {
+    DevTables tb;
+    const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
+    const double* y; long long n_cells;
+    double* F; double* Lb; double* Db; double* Ub;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
+    constexpr int S = NB - 1;
+    constexpr int WARPS = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cell = (long long)blockIdx.x * WARPS + warp;
+    DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
+    {
+        const int words = (int)(sizeof(DevTables) / 4);
+        const int* src = reinterpret_cast<const int*>(&P.tb);
+        int* dst = reinterpret_cast<int*>(tb);
+        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
+    unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
+    if (cell >= P.n_cells) return;
+    WarpState<NB> ws;
+    ws.lane = lane; ws.tb = tb;
+    CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
+    ws.sp = sp;
+    ws.scratch = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
+    load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
+    const int n = ws.cs.n, nxm = P.tb.nx_max;
+    const double* y = P.y + (size_t)cell * nxm * NB;
+    double* sl = ws.scratch + 2 * (NB + 1);
+    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB; double* sf = sua + NB;
+    for (int i = 0; i < n; ++i) {
+        __syncwarp();
+        const double F = node_rows<NB>(ws, y, i, sl, sa, sud, sua, sf);
+        __syncwarp();
+        const size_t nb = ((size_t)cell * nxm + i);
+        if (P.F && lane < NB) P.F[nb * NB + lane] = F;
+        // blocks are d(row)/d(col) of F itself (not of the Newton matrix)
+        if (lane < NB) {
+            const int j = lane;     // column
+            const double* yi = y + (size_t)i * NB;
+            double Dcol[NB], Lcol[NB], Ucol[NB];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) { Dcol[r] = 0.0; Lcol[r] = 0.0; Ucol[r] = 0.0; }
+            if (i == 0) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    if (r == j) { Dcol[r] = sa[r]; Ucol[r] = sud[r]; Lcol[r] = sl[r]; }   // Lcol = extra block (0,2)
+                    if (j == S && r < S) Ucol[r] = sua[r];
+                }
+            } else if (i == n - 1) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) if (r == j) Dcol[r] = -1.0;
+            } else {
+                const NodeCoef k = interior_coef(ws.cs, i);
+                if (j < S) {
+                    for (int t = tb->tbeg[j]; t < tb->tbeg[j + 1]; ++t) {
+                        double v = tb->tcoef[t];
+                        if (tb->ti1[t] >= 0) v *= yi[tb->ti1[t]];
+                        if (tb->ti2[t] >= 0) v *= yi[tb->ti2[t]];
+                        if (tb->ti3[t] >= 0) v *= yi[tb->ti3[t]];
+                        const double* nur = tb->nu[tb->tr[t]];
+#pragma unroll
+                        for (int r = 0; r < S; ++r) Dcol[r] = fma(nur[r], v, Dcol[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) if (r == j) Dcol[r] -= sp->D[j] * (k.am + k.ap);
+                    if (tb->use_migration) Dcol[S] = (sp->q[j] / ws.cs.eps) * k.hi;
+                } else {
+                    Dcol[S] = -1.0;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    if (r == j) { Lcol[r] = sl[r]; Ucol[r] = sud[r]; }
+                    if (j == S && r < S) { Lcol[r] = sa[r]; Ucol[r] = sua[r]; }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                if (P.Db) P.Db[(nb * NB + r) * NB + j] = Dcol[r];
+                if (P.Lb) P.Lb[(nb * NB + r) * NB + j] = Lcol[r];
+                if (P.Ub) P.Ub[(nb * NB + r) * NB + j] = Ucol[r];
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// K1: dc/dt of the reference ODE.  One warp per cell, lanes stride the nodes.
+// Pass 1: charge density and its suffix sum -> g (warp scan), kept in shared
+// memory; pass 2: stencil + reactions.  c is [B][nx_max][S].
+// ===========================================================================
+struct RhsParams {
+    DevTables tb;
+    const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
+    const double* c; long long n_cells;
+    double* dcdt; double* g_out; double* phi_out;
+};
+
+__global__ void __launch_bounds__(128) pnp_rhs_kernel(RhsParams P) {
+    constexpr int WARPS = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cell = (long long)blockIdx.x * WARPS + warp;
+    DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
+    {
+        const int words = (int)(sizeof(DevTables) / 4);
+        const int* src = reinterpret_cast<const int*>(&P.tb);
+        int* dst = reinterpret_cast<int*>(tb);
+        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    const int nxm = P.tb.nx_max, S = P.tb.S;
+    size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)nxm * sizeof(double);
+    unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
+    if (cell >= P.n_cells) return;
+    CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
+    double* gs = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
+    CellScalars cs;
+    load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, cs, sp);
+    const int n = cs.n;
+    const double* c = P.c + (size_t)cell * nxm * S;
+    double* out = P.dcdt + (size_t)cell * nxm * S;
+
+    // ---- pass 1: g_i = g_bulk - sum_{j=i}^{n-2} lapl_j*h_j  (i=1..n-2), lapl = -sum q c/eps
+    if (tb->use_migration) {
+        double carry = 0.0;           // sum over nodes already processed (towards the bulk)
+        for (int base = n - 2; base >= 1; base -= 32) {
+            const int i = base - lane;
+            double term = 0.0;
+            if (i >= 1) {
+                double lapl = 0.0;
+                for (int s = 0; s < S; ++s) lapl -= sp->q[s] * c[(size_t)i * S + s] / cs.eps;
+                const double hi = cs.uniform ? cs.dx : cs.dx * (cs.xi[i + 1] - cs.xi[i]);
+                term = lapl * hi;
+            }
+            // inclusive scan over lanes (lane 0 = node closest to the bulk)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(FULL, term, o);
+                if (lane >= o) term += v;
+            }
+            if (i >= 1) gs[i] = cs.g_bulk - (carry + term);
+            carry += __shfl_sync(FULL, term, 31);
+        }
+        if (lane == 0) {
+            gs[n - 1] = cs.g_bulk;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const WallCoef w = wall_coef(cs);
+            gs[0] = gs[1] + (gs[1] - gs[2]) * w.ext;
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) gs[i] = 0.0;
+    }
+    __syncwarp();
+
+    // ---- pass 2: stencil
+    for (int i = lane; i < n; i += 32) {
+        const double* c0 = c + (size_t)i * S;
+        if (i == n - 1) {
+            for (int s = 0; s < S; ++s) out[(size_t)i * S + s] = 0.0;        // frozen bulk node (:886)
+        } else if (i == 0) {
+            const WallCoef w = wall_coef(cs);
+            const double* c1 = c + S; const double* c2 = c + 2 * S;
+            for (int s = 0; s < S; ++s) {
+                const double bq = tb->use_migration ? sp->bq[s] : 0.0;
+                out[s] = (sp->D[s] * ((c2[s] - c0[s]) * w.w0 + bq * c1[s] * gs[1]) + sp->J[s]) * w.ih0;
+            }
+        } else {
+            const NodeCoef k = interior_coef(cs, i);
+            const double* cm = c0 - S; const double* cp = c0 + S;
+            const double gm = gs[i - 1], gp = gs[i + 1];
+            double net[MAXR];
+            for (int r = 0; r < tb->R; ++r) net[r] = net_rate(*tb, r, c0);
+            for (int s = 0; s < S; ++s) {
+                const double bq = tb->use_migration ? sp->bq[s] : 0.0;
+                double R = 0.0;
+                for (int r = 0; r < tb->R; ++r) R += tb->nu[r][s] * net[r];
+                double d2, dcg;
+                if (cs.uniform) {
+                    d2 = (cp[s] - 2.0 * c0[s] + cm[s]) / (cs.dx * cs.dx);               // :890
+                    dcg = (cp[s] * gp - cm[s] * gm) / (2.0 * cs.dx);                     // :892
+                } else {
+                    d2 = k.am * cm[s] - (k.am + k.ap) * c0[s] + k.ap * cp[s];
+                    dcg = (cp[s] * gp - cm[s] * gm) * k.ac;
+                }
+                out[(size_t)i * S + s] = sp->D[s] * (d2 + bq * dcg) + R;                  // :920-927
+            }
+        }
+    }
+    if (P.g_out) for (int i = lane; i < n; i += 32) P.g_out[(size_t)cell * nxm + i] = gs[i];
+    if (P.phi_out && lane == 0) {
+        double* po = P.phi_out + (size_t)cell * nxm;
+        double v = cs.phi_wall, vm1 = v, vm2 = v;
+        po[0] = v;
+        for (int i = 1; i <= n - 2; ++i) {
+            const double him = cs.uniform ? cs.dx : cs.dx * (cs.xi[i] - cs.xi[i - 1]);
+            v = v + gs[i] * him;
+            po[i] = v; vm2 = vm1; vm1 = v;
+        }
+        if (n >= 3) {
+            const double ratio = cs.uniform ? 1.0 : (cs.xi[n - 1] - cs.xi[n - 2]) / (cs.xi[n - 2] - cs.xi[n - 3]);
+            po[n - 1] = vm1 + (vm1 - vm2) * ratio;
+        }
+    }
+}
+
+}  // namespace catint
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace catint;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return code;
+}
+
+extern "C" int catint_pnp_version(void) { return 100; }
+extern "C" const char* catint_pnp_last_error(void) { return g_err; }
+
+extern "C" int catint_pnp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+static int build_tables(const CatintPnpShared* sh, DevTables& tb) {
+    memset(&tb, 0, sizeof(tb));
+    if (!sh) return fail(CATINT_PNP_EINVAL, "shared tables are NULL");
+    if (sh->S < 1 || sh->S > CATINT_PNP_MAX_SPECIES) return fail(CATINT_PNP_EINVAL, "S out of range");
+    if (sh->R < 0 || sh->R > CATINT_PNP_MAX_REACTIONS) return fail(CATINT_PNP_EINVAL, "R out of range");
+    if (sh->nx_max < 4) return fail(CATINT_PNP_EINVAL, "nx_max must be >= 4");
+    tb.S = sh->S; tb.R = sh->R; tb.nx_max = sh->nx_max;
+    tb.stern = sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN;
+    tb.use_migration = sh->use_migration != 0;
+    for (int k = 0; k < sh->S; ++k) tb.z[k] = (double)sh->z[k];
+    for (int r = 0; r < sh->R; ++r) {
+        int ne = 0, np = 0;
+        for (int e = 0; e < CATINT_PNP_MAX_REACTANTS; ++e) {
+            if (sh->educt[r][e] >= 0) {
+                if (sh->educt[r][e] >= sh->S) return fail(CATINT_PNP_EINVAL, "educt index out of range");
+                tb.ed[r][ne++] = (int8_t)sh->educt[r][e];
+            }
+            if (sh->product[r][e] >= 0) {
+                if (sh->product[r][e] >= sh->S) return fail(CATINT_PNP_EINVAL, "product index out of range");
+                tb.pr[r][np++] = (int8_t)sh->product[r][e];
+            }
+        }
+        tb.ned[r] = (int8_t)ne; tb.npr[r] = (int8_t)np;
+        tb.kf[r] = sh->kf[r]; tb.kr[r] = sh->kr[r];
+        for (int k = 0; k < sh->S; ++k) tb.nu[r][k] = sh->nu[k][r];
+    }
+    // derivative terms, grouped by the species the derivative is taken with respect to
+    int T = 0;
+    for (int j = 0; j < sh->S; ++j) {
+        tb.tbeg[j] = (int8_t)T;
+        for (int r = 0; r < sh->R; ++r) {
+            for (int side = 0; side < 2; ++side) {
+                const int8_t* lst = side == 0 ? tb.ed[r] : tb.pr[r];
+                const int cnt = side == 0 ? tb.ned[r] : tb.npr[r];
+                for (int p = 0; p < cnt; ++p) {
+                    if (lst[p] != j) continue;
+                    if (T >= MAXT) return fail(CATINT_PNP_EINVAL, "too many reaction derivative terms");
+                    int8_t others[3] = {-1, -1, -1};
+                    int no = 0;
+                    for (int p2 = 0; p2 < cnt; ++p2) if (p2 != p) others[no++] = lst[p2];
+                    tb.tr[T] = (int8_t)r;
+                    tb.ti1[T] = others[0]; tb.ti2[T] = others[1]; tb.ti3[T] = others[2];
+                    tb.tcoef[T] = side == 0 ? tb.kf[r] : -tb.kr[r];
+                    ++T;
+                }
+            }
+        }
+    }
+    tb.tbeg[sh->S] = (int8_t)T;
+    for (int j = sh->S + 1; j <= MAXS; ++j) tb.tbeg[j] = (int8_t)T;
+    tb.T = T;
+    return CATINT_PNP_OK;
+}
+
+static int block_size_of(const CatintPnpShared* sh) {
+    return sh->S + (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN ? 2 : 1);
+}
+
+static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
+    const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
+    // zn[LMAX][N] + ewt[N] + W[nx][NB][NB] + V0[NB][NB] + (y,psi,zb)[N] (used only when the state
+    // does not fit in shared memory, always reserved so that the size query is stateless)
+    size_t d = (size_t)LMAX * nxm * NB + nxm * NB + nxm * NB * NB + NB * NB + 3 * nxm * NB;
+    return (d + 15) & ~size_t(15);
+}
+
+extern "C" size_t catint_pnp_workspace_bytes(const CatintPnpShared* sh, int64_t n_cells) {
+    if (!sh || n_cells <= 0) return 0;
+    return ws_doubles_per_cell(sh) * sizeof(double) * (size_t)n_cells + 64 * sizeof(double);
+}
+
+static int check_cuda(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return CATINT_PNP_ECUDA;
+    }
+    return CATINT_PNP_OK;
+}
+
+template <int NB>
+static int launch_bdf(SolveParams& P, cudaStream_t st) {
+    const int WARPS = 4;
+    const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
+    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)(2 * (NB + 1) + 6 * NB) * sizeof(double);
+    const size_t state = (size_t)3 * P.tb.nx_max * NB * sizeof(double);
+    int dev = 0; cudaGetDevice(&dev);
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    size_t smem = base + WARPS * (per_warp_fixed + state);
+    P.state_in_smem = 1;
+    // keep two blocks per SM when the state lives in shared memory
+    if (smem > (size_t)max_optin / 2) {
+        if (smem > (size_t)max_optin) { P.state_in_smem = 0; smem = base + WARPS * per_warp_fixed; }
+    }
+    cudaFuncSetAttribute(pnp_bdf_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
+    pnp_bdf_kernel<NB><<<grid, WARPS * 32, smem, st>>>(P);
+    return check_cuda("pnp_bdf_kernel launch");
+}
+
+template <int NB>
+static int launch_jac(JacParams& P, cudaStream_t st) {
+    const int WARPS = 4;
+    const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)(2 * (NB + 1) + 6 * NB) * sizeof(double);
+    const size_t smem = base + WARPS * per_warp;
+    const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
+    pnp_jacobian_kernel<NB><<<grid, WARPS * 32, smem, st>>>(P);
+    return check_cuda("pnp_jacobian_kernel launch");
+}
+
+#define DISPATCH_NB(NBVAL, CALL, ...)                        \
+    switch (NBVAL) {                                         \
+        case 2: rc = CALL<2>(__VA_ARGS__); break;            \
+        case 3: rc = CALL<3>(__VA_ARGS__); break;            \
+        case 4: rc = CALL<4>(__VA_ARGS__); break;            \
+        case 5: rc = CALL<5>(__VA_ARGS__); break;            \
+        case 6: rc = CALL<6>(__VA_ARGS__); break;            \
+        case 7: rc = CALL<7>(__VA_ARGS__); break;            \
+        case 8: rc = CALL<8>(__VA_ARGS__); break;            \
+        case 9: rc = CALL<9>(__VA_ARGS__); break;            \
+        case 10: rc = CALL<10>(__VA_ARGS__); break;          \
+        case 11: rc = CALL<11>(__VA_ARGS__); break;          \
+        case 12: rc = CALL<12>(__VA_ARGS__); break;          \
+        case 13: rc = CALL<13>(__VA_ARGS__); break;          \
+        default: rc = fail(CATINT_PNP_EINVAL, "unsupported block size (S+1 must be 2..13)"); \
+    }
+
+static int check_common(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells) {
+    if (!sh || !cells) return fail(CATINT_PNP_EINVAL, "NULL argument");
+    if (n_cells <= 0) return fail(CATINT_PNP_EINVAL, "n_cells must be positive");
+    if (!cells->par || !cells->nx) return fail(CATINT_PNP_EINVAL, "cells->par / cells->nx are NULL");
+    if (sh->n_mesh > 0 && !cells->mesh_xi) return fail(CATINT_PNP_EINVAL, "mesh table missing");
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
+        return fail(CATINT_PNP_EINVAL, "Stern/Robin Poisson boundary is not available in this build");
+    if (catint_pnp_device_count() <= 0) return fail(CATINT_PNP_ENODEV, "no sm_100 CUDA device visible");
+    return CATINT_PNP_OK;
+}
+
+extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                    const double* c, double* dcdt, double* g_out, double* phi_out,
+                                    void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!c || !dcdt) return fail(CATINT_PNP_EINVAL, "c / dcdt are NULL");
+    RhsParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.c = c; P.n_cells = n_cells; P.dcdt = dcdt; P.g_out = g_out; P.phi_out = phi_out;
+    const int WARPS = 4;
+    const size_t smem = ((sizeof(DevTables) + 15) & ~size_t(15)) +
+                        WARPS * (((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)sh->nx_max * sizeof(double));
+    cudaFuncSetAttribute(pnp_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned grid = (unsigned)((n_cells + WARPS - 1) / WARPS);
+    pnp_rhs_kernel<<<grid, WARPS * 32, smem, (cudaStream_t)cuda_stream>>>(P);
+    return check_cuda("pnp_rhs_kernel launch");
+}
+
+extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                         const double* y, double* F, double* Lb, double* Db, double* Ub,
+                                         void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!y) return fail(CATINT_PNP_EINVAL, "y is NULL");
+    JacParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.y = y; P.n_cells = n_cells; P.F = F; P.Lb = Lb; P.Db = Db; P.Ub = Ub;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DISPATCH_NB(block_size_of(sh), launch_jac, P, st);
+    return rc;
+}
+
+extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                      const double* y0, const CatintPnpControl* ctl,
+                                      double* c_out, double* phi_out, double* g_out, double* flux_out,
+                                      int32_t* status, int32_t* n_steps, int32_t* n_newton,
+                                      void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!ctl || !ctl->t_out || ctl->n_out < 1) return fail(CATINT_PNP_EINVAL, "control / t_out missing");
+    if (!c_out || !status || !n_steps || !n_newton) return fail(CATINT_PNP_EINVAL, "output pointers are NULL");
+    if (!(ctl->rtol >= 0.0) || !(ctl->atol > 0.0)) return fail(CATINT_PNP_EINVAL, "need rtol >= 0 and atol > 0");
+    for (int k = 0; k < ctl->n_out; ++k)
+        if (!(ctl->t_out[k] > 0.0) || (k > 0 && !(ctl->t_out[k] > ctl->t_out[k - 1])))
+            return fail(CATINT_PNP_EINVAL, "t_out must be positive and increasing");
+    const size_t need = catint_pnp_workspace_bytes(sh, n_cells);
+    if (!workspace || workspace_bytes < need) return fail(CATINT_PNP_ENOMEM, "workspace too small");
+    if (ctl->n_out > 60) return fail(CATINT_PNP_EINVAL, "at most 60 output times per call");
+
+    SolveParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.y0 = y0; P.n_cells = n_cells;
+    P.mode = ctl->mode; P.max_steps = ctl->max_steps > 0 ? ctl->max_steps : 100000;
+    P.n_out = ctl->n_out; P.polish_max_iter = ctl->polish_max_iter > 0 ? ctl->polish_max_iter : 8;
+    P.rtol = ctl->rtol; P.atol = ctl->atol; P.h0 = ctl->h0;
+    P.polish_rtol = ctl->polish_rtol > 0.0 ? ctl->polish_rtol : 1e-10;
+    // the output times travel in the tail of the workspace
+    double* wsd = reinterpret_cast<double*>(workspace);
+    double* t_dev = wsd + ws_doubles_per_cell(sh) * (size_t)n_cells;
+    if (cudaMemcpyAsync(t_dev, ctl->t_out, sizeof(double) * ctl->n_out, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return check_cuda("copy of t_out");
+    P.t_out = t_dev;
+    P.c_out = c_out; P.phi_out = phi_out; P.g_out = g_out; P.flux_out = flux_out;
+    P.status = status; P.n_steps = n_steps; P.n_newton = n_newton;
+    P.ws = wsd; P.ws_stride = (long long)ws_doubles_per_cell(sh);
+    P.state_in_smem = 1;
+    DISPATCH_NB(block_size_of(sh), launch_bdf, P, st);
+    return rc;
+}
