@@ -275,16 +275,11 @@ class PnpBackend(object):
         return F, blocks[0], blocks[1], blocks[2]
 
     # -- K3 ---------------------------------------------------------------
-    def solve(self, dbatch, t_out, mode=MODE_STEADY, rtol=1.49012e-8, atol=1.49012e-8, y0=None,
-              max_steps=100000, h0=0.0, polish_rtol=1e-10, polish_max_iter=8):
-        """returns dict of device tensors: c [n_out,B,nx,S], phi, g [n_out,B,nx],
-        flux [B,S], status, n_steps, n_newton [B]"""
+    def alloc_outputs(self, dbatch, n_out):
         torch = self.torch
         b = dbatch.batch
-        t_out = np.ascontiguousarray(np.atleast_1d(np.asarray(t_out, dtype=np.float64)))
-        n_out = len(t_out)
         dev = self.device
-        out = {
+        return {
             'c': torch.zeros((n_out, b.B, b.nx_max, b.S), dtype=torch.float64, device=dev),
             'phi': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=dev),
             'g': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=dev),
@@ -293,6 +288,19 @@ class PnpBackend(object):
             'n_steps': torch.zeros((b.B,), dtype=torch.int32, device=dev),
             'n_newton': torch.zeros((b.B,), dtype=torch.int32, device=dev),
         }
+
+    def solve(self, dbatch, t_out, mode=MODE_STEADY, rtol=1.49012e-8, atol=1.49012e-8, y0=None,
+              max_steps=100000, h0=0.0, polish_rtol=1e-10, polish_max_iter=8, out=None):
+        """returns dict of device tensors: c [n_out,B,nx,S], phi, g [n_out,B,nx],
+        flux [B,S], status, n_steps, n_newton [B] (``out``: reuse a dict from alloc_outputs)"""
+        torch = self.torch
+        b = dbatch.batch
+        t_out = np.ascontiguousarray(np.atleast_1d(np.asarray(t_out, dtype=np.float64)))
+        n_out = len(t_out)
+        dev = self.device
+        if out is None:
+            out = self.alloc_outputs(dbatch, n_out)
+        assert out['c'].shape == (n_out, b.B, b.nx_max, b.S)
         ws, need = self.workspace(dbatch)
         ctl = CatintPnpControl()
         ctl.mode, ctl.max_steps, ctl.n_out, ctl.polish_max_iter = int(mode), int(max_steps), n_out, int(polish_max_iter)

@@ -1,0 +1,312 @@
+"""Calculator: the sweep / time-stepping driver (host side).
+
+Drop-in for the reference's ``catint.calculator.Calculator``
+(/root/reference/catint/calculator.py:53-241) restricted to the
+finite-difference PNP path whose integrators live in
+/root/reference/catint/calculator_old.py:210-1140 (``integrate_pnp``).
+
+Same constructor keywords (calculator.py:55-56), same calc-string parsing
+(:81-97), same time mesh and output indices (:105-138), same descriptor walk
+order and labels (:204-219).  Difference by design: instead of solving one
+descriptor point after the other, ``run()`` gathers the whole descriptor grid
+into one cell batch, integrates all cells concurrently on the GPU(s) (one warp
+per cell, cells sharded round-robin over the ranks of torch.distributed exactly
+like ``itask % mpi_size == mpi_rank`` at calculator.py:209-212) and then fills
+the result containers the reference's tools read (tp.cout, tp.potential,
+tp.efield, tp.total_charge, tp.alldata[i][...]; conventions of
+/root/reference/catint/comsol_reader.py:186-300).
+"""
+import sys
+import time
+
+import numpy as np
+
+from .units import unit_F
+from . import backend as _be
+
+# finite-difference integrators of the reference that map onto the BDF/Newton GPU integrator
+FD_ODE_CALCS = ['odeint', 'lsoda', 'vode']
+
+
+def build_cell_batch(tp, rate_mode='summed', points=None):
+    """Derive the per-cell parameter records for every point of the descriptor
+    grid of ``tp`` (or for the explicit list ``points`` of override dicts).
+
+    Returns (CellBatch, models) where models[i] is the DerivedModel of cell i
+    (light objects; used to label results)."""
+    keys = list(tp.descriptors)
+    if points is None:
+        points = []
+        for v1 in tp.descriptors[keys[0]]:
+            for v2 in tp.descriptors[keys[1]]:
+                points.append({keys[0]: float(v1), keys[1]: float(v2)})
+    models = []
+    cache = {}
+    for ov in points:
+        key = tuple(sorted(ov.items()))
+        if key not in cache:
+            cache[key] = tp.derive_for(**ov)
+        models.append(cache[key])
+    m0 = models[0]
+    names = list(m0.species)
+    S = len(names)
+    for m in models:
+        if list(m.species) != names:
+            tp.logger.error('| CI | -- | species set changes along the descriptor grid; cannot batch')
+            sys.exit()
+        if m.flux_bound is None:
+            tp.logger.error('| CI | -- | flux-equation / catmap fluxes are not available in the FD-PNP backend')
+            sys.exit()
+    # reaction table (species not transported -- H2O, e- -- drop out, calculator_old.py:169-171)
+    reactions = []
+    if m0.use_electrolyte_reactions and m0.electrolyte_reactions is not None:
+        for r in m0.electrolyte_reactions:
+            entry = m0.electrolyte_reactions[r]
+            if 'rates' not in entry:
+                continue
+            ed = [names.index(s) for s in entry['reaction'][0] if s in names]
+            pr = [names.index(s) for s in entry['reaction'][1] if s in names]
+            reactions.append((ed, pr, entry['rates'][0], entry['rates'][1]))
+    nu = _be.stoichiometry(S, reactions, rate_mode)
+    B = len(models)
+    par = np.zeros((B, _be.npar(S)))
+    nx = np.zeros(B, dtype=np.int32)
+    z = np.array([m0.species[s]['charge'] for s in names], dtype=np.int32)
+    for c, m in enumerate(models):
+        par[c, 0:S] = [m.species[s]['bulk_concentration'] for s in names]
+        par[c, S:2 * S] = m.flux_bound[:, 0]          # inward flux = +species[sp]['flux']
+        par[c, 2 * S:3 * S] = m.D
+        par[c, 3 * S + 0] = m.beta
+        par[c, 3 * S + 1] = m.eps
+        wall = m.pb_bound['potential']['wall']
+        gb = m.pb_bound['gradient']['bulk']
+        if wall is None or gb is None:
+            tp.logger.error('| CI | -- | the FD-PNP backend needs pb_bound with a wall potential and a bulk gradient '
+                            '(the reference default, transport.py:207-210)')
+            sys.exit()
+        par[c, 3 * S + 2] = wall
+        par[c, 3 * S + 3] = gb
+        par[c, 3 * S + 4] = m.system['Stern capacitance'] * 1e-2     # micro F/cm^2 -> F/m^2
+        par[c, 3 * S + 5] = m.dx
+        nx[c] = m.nx
+    batch = _be.CellBatch(z, reactions, nu, par, nx, use_migration=m0.use_migration, species=names)
+    return batch, models
+
+
+def shard_indices(n_cells, rank, world_size):
+    """round-robin cell -> rank map (calculator.py:209-212: itask % size == rank)"""
+    return np.arange(rank, n_cells, world_size)
+
+
+class Calculator():
+
+    def __init__(self, transport=None, dt=None, tmax=None, ntout=1, calc=None,
+                 scale_pb_grid=None, tau_jacobi=1e-7, tau_scf=5e-5, mix_scf=0.5, mode='time-dependent',
+                 rtol=1.49012e-8, atol=1.49012e-8, rate_mode='summed', device=None, max_steps=100000):
+        """Reference keywords (calculator.py:55-56) plus backend options:
+        rtol/atol  error tolerances of the BDF integrator (scipy odeint defaults)
+        rate_mode  'summed' (default) or 'legacy_overwrite' 
+        mode       'time-dependent': state at the output times of the time mesh
+                   'stationary': integrate to tmax, then Newton-polish the steady residual
+        """
+        self.mode = mode
+        self.tau_scf = tau_scf
+        self.mix_scf = mix_scf
+        if transport is None:
+            print('No transport object provided for calculator. Stopping here.')
+            sys.exit()
+        self.tp = transport
+        if calc is None:
+            calc = self.tp.calc
+        if calc is None:
+            self.tp.logger.error('No calculator found with this name. Aborting.')
+            sys.exit()
+        self.tp.ntout = ntout
+
+        self.use_lax_friedrich = False
+        parts = calc.split('--')
+        self.calc_method = None
+        if len(parts) > 1:
+            if parts[-1] == 'LF':
+                self.use_lax_friedrich = True
+            else:
+                self.calc_method = parts[-1]
+            self.calc = parts[0]
+        else:
+            self.calc = calc
+        self.calc_list = ['FTCS', 'Crank-Nicolson', 'odeint', 'vode', 'lsoda', 'dopri5', 'dop853', 'odeint',
+                          'odespy', 'comsol']
+        if self.calc not in self.calc_list:
+            self.tp.logger.error('No calculator found with this name. Aborting.')
+            sys.exit()
+        if self.calc not in FD_ODE_CALCS:
+            self.tp.logger.error('| CI | -- | calculator "{}" is outside the scope of the B200 FD-PNP backend '
+                                 '(available: {})'.format(self.calc, FD_ODE_CALCS))
+            sys.exit()
+        if self.use_lax_friedrich:
+            self.tp.logger.error('| CI | -- | Lax-Friedrichs terms are not available in the FD-PNP backend')
+            sys.exit()
+        self.scale_pb_grid = scale_pb_grid
+        self.tau_jacobi = tau_jacobi
+        self.rtol, self.atol = rtol, atol
+        self.rate_mode = rate_mode
+        self.device = device
+        self.max_steps = max_steps
+
+        # time mesh and output indices (calculator.py:105-138)
+        if dt is not None:
+            self.tp.dt = dt
+        if tmax is not None:
+            self.tp.tmax = tmax
+        if tmax is not None or dt is not None:
+            self.tp.tmesh = np.arange(0, self.tp.tmax + self.tp.dt, self.tp.dt)
+        else:
+            self.tp.logger.warning('No time mesh given, defaulting to range(0,1,0.1)')
+            self.tp.dt, self.tp.tmax = 0.1, 0.9
+            self.tp.tmesh = np.arange(0, 1, 0.1)
+        self.tp.nt = len(self.tp.tmesh)
+        self.tp.tmesh_init = self.tp.tmesh
+        self.tp.nt_init = self.tp.nt
+        self.tp.dt_init = self.tp.dt
+        self.tp.tmax_init = self.tp.tmax
+        self.oldtime = np.inf
+        self.tp.itout = []
+        stride = int(self.tp.nt / float(self.tp.ntout))
+        for it, t in enumerate(self.tp.tmesh):
+            if it == self.tp.nt - 1:
+                self.tp.itout.append(it)
+            elif it > 1 and stride > 0 and it % stride == 0:
+                self.tp.itout.append(it)
+        self.tp.ntout = len(self.tp.itout)
+        self.stats = {}
+
+    # ------------------------------------------------------------------
+    def get_rates(self, C):
+        """homogeneous rates [S,nx] of the concentrations C[S,nx] (host helper with the
+        semantics of self.rate_mode; the device evaluates the same table)."""
+        tp = self.tp
+        names = list(tp.species)
+        rates = np.zeros([tp.nspecies, C.shape[1]])
+        if not tp.use_electrolyte_reactions or tp.electrolyte_reactions is None:
+            return rates
+        rx = []
+        for r in tp.electrolyte_reactions:
+            e = tp.electrolyte_reactions[r]
+            if 'rates' in e:
+                rx.append(([names.index(s) for s in e['reaction'][0] if s in names],
+                           [names.index(s) for s in e['reaction'][1] if s in names], e['rates'][0], e['rates'][1]))
+        nu = _be.stoichiometry(tp.nspecies, rx, self.rate_mode)
+        for r, (ed, pr, kf, kr) in enumerate(rx):
+            net = kf * np.prod(C[ed, :], axis=0) - kr * np.prod(C[pr, :], axis=0)
+            rates += nu[:, r:r + 1] * net[None, :]
+        return rates
+
+    # ------------------------------------------------------------------
+    def output_times(self):
+        ts = [float(self.tp.tmesh[i]) for i in self.tp.itout if self.tp.tmesh[i] > 0.0]
+        if not ts:
+            ts = [float(self.tp.tmax)]
+        return ts
+
+    def solve_batch(self, batch, backend=None, pinned=None):
+        """host CellBatch -> host result dict (numpy).  Host->device copies, the
+        solve and the device->host copies all happen here."""
+        import torch
+        if backend is None:
+            backend = _be.PnpBackend(self.device)
+        db = backend.upload(batch, pinned=pinned)
+        mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT
+        out = backend.solve(db, self.output_times(), mode=mode, rtol=self.rtol, atol=self.atol,
+                            max_steps=self.max_steps)
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        host['h2d_bytes'] = db.h2d_bytes
+        host['d2h_bytes'] = sum(int(v.numel() * v.element_size()) for v in out.values())
+        return host
+
+    def run(self):
+        tp = self.tp
+        t0 = time.time()
+        keys = list(tp.descriptors)
+        batch, models = build_cell_batch(tp, rate_mode=self.rate_mode)
+        for i1, v1 in enumerate(tp.descriptors[keys[0]]):
+            for i2, v2 in enumerate(tp.descriptors[keys[1]]):
+                tp.logger.debug('| CI | -- | cell {} : {} = {} and {} = {}'.format(
+                    str(i1 + 1).zfill(4) + '_' + str(i2 + 1).zfill(4), keys[0], v1, keys[1], v2))
+        tp.logger.info('| CI | -- | Starting batched calculation of {} cells ({} x {})'.format(
+            batch.B, len(tp.descriptors[keys[0]]), len(tp.descriptors[keys[1]])))
+        from . import distributed as _dist
+        res = _dist.solve_sharded(self, batch)
+        t1 = time.time()
+        if res is not None:
+            self.scatter_results(batch, models, res)
+            nconv = int(np.sum(res['status'] == 0))
+            self.stats = {'cells': batch.B, 'converged': nconv, 'seconds': t1 - t0,
+                          'n_steps': res['n_steps'], 'n_newton': res['n_newton'], 'status': res['status']}
+            tp.logger.info('| CI | -- | {} of {} cells converged in {:.3f} s'.format(nconv, batch.B, t1 - t0))
+            for c in np.nonzero(res['status'] != 0)[0]:
+                tp.logger.warning('| CI | -- | cell {} ({}) did not converge: {}'.format(
+                    c, tp.alldata_names[c], _be.CELL_STATUS.get(int(res['status'][c]), res['status'][c])))
+            tp.save()
+        return res
+
+    # ------------------------------------------------------------------
+    def scatter_results(self, batch, models, res):
+        """fill tp.cout/potential/efield/total_charge (last cell, like the serial
+        reference loop would leave them) and tp.alldata[i] for every cell."""
+        tp = self.tp
+        names = list(tp.species)
+        S = len(names)
+        c_all = res['c']          # [n_out,B,nx_max,S]
+        q = np.array([tp.species[s]['charge'] for s in names]) * unit_F
+        for c in range(batch.B):
+            n = int(batch.nx[c])
+            m = models[c]
+            cfin = c_all[-1, c, :n, :]                 # [n,S]
+            g = res['g'][-1, c, :n]
+            phi = res['phi'][-1, c, :n]
+            ad = tp.alldata[c]
+            for k, sp in enumerate(names):
+                d = ad['species'].setdefault(sp, {})
+                d['concentration'] = list(cfin[:, k])
+                d['surface_concentration'] = float(cfin[0, k])
+                d['electrode_flux'] = float(res['flux'][c, k])
+                if m.electrode_reactions is not None and sp in m.electrode_reactions:
+                    er = m.electrode_reactions[sp]
+                    nprod = len([a for a in er['reaction'][1] if a == sp])
+                    d['electrode_current_density'] = d['electrode_flux'] * er['nel'] * unit_F / nprod / 10.
+            sysd = ad['system']
+            sysd['potential'] = list(phi)
+            sysd['efield'] = list(-g)
+            sysd['charge_density'] = list(cfin @ q)
+            sysd['surface_potential'] = float(phi[0])
+            with np.errstate(invalid='ignore', divide='ignore'):
+                if 'H+' in names:
+                    ph = -np.log10(cfin[:, names.index('H+')] / 1000.)
+                elif 'OH-' in names:
+                    ph = 14 + np.log10(cfin[:, names.index('OH-')] / 1000.)
+                else:
+                    ph = None
+            if ph is not None:
+                sysd['pH'] = list(ph)
+                if np.isfinite(ph[0]):
+                    sysd['surface_pH'] = float(ph[0])
+                else:
+                    tp.logger.warning('| CI | -- | negative surface concentration, surface pH cannot be evaluated '
+                                      'for cell {}'.format(c))
+            sysd['status'] = _be.CELL_STATUS.get(int(res['status'][c]), int(res['status'][c]))
+        # containers of the serial FD path (calculator_old.py:816-818, 966-973): last cell
+        last = batch.B - 1
+        n = int(batch.nx[last])
+        tp.cout = [np.ascontiguousarray(c_all[k, last, :n, :].T).reshape(-1) for k in range(c_all.shape[0])]
+        tp.efield = -res['g'][-1, last, :n]
+        tp.potential = res['phi'][-1, last, :n]
+        tp.total_charge = c_all[-1, last, :n, :] @ q
+        for k, sp in enumerate(names):
+            tp.species[sp]['surface_concentration'] = float(c_all[-1, last, 0, k])
+        last_sys = tp.alldata[last]['system']
+        if 'surface_pH' in last_sys:
+            tp.system['surface_pH'] = last_sys['surface_pH']
+        tp.system['surface_potential'] = last_sys['surface_potential']
+        tp.system['potential'] = np.array(last_sys['potential'])
+        tp.system['efield'] = np.array(last_sys['efield'])
+        tp.system['charge_density'] = np.array(last_sys['charge_density'])

@@ -1,0 +1,229 @@
+// pnp_capi.cu -- the C ABI of include/catint_pnp.h: argument checks, model-table
+// conversion and kernel launches.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pnp_kernels.cuh"
+#include "pnp_rhs.cuh"
+
+namespace catint {
+#define X(NB) extern template int launch_bdf<NB>(SolveParams&, cudaStream_t); \
+              extern template int launch_jac<NB>(JacParams&, cudaStream_t);
+X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+#undef X
+}
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace catint;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return code;
+}
+
+extern "C" int catint_pnp_version(void) { return 100; }
+extern "C" const char* catint_pnp_last_error(void) { return g_err; }
+
+extern "C" int catint_pnp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+static int build_tables(const CatintPnpShared* sh, DevTables& tb) {
+    memset(&tb, 0, sizeof(tb));
+    if (!sh) return fail(CATINT_PNP_EINVAL, "shared tables are NULL");
+    if (sh->S < 1 || sh->S > CATINT_PNP_MAX_SPECIES) return fail(CATINT_PNP_EINVAL, "S out of range");
+    if (sh->R < 0 || sh->R > CATINT_PNP_MAX_REACTIONS) return fail(CATINT_PNP_EINVAL, "R out of range");
+    if (sh->nx_max < 4) return fail(CATINT_PNP_EINVAL, "nx_max must be >= 4");
+    tb.S = sh->S; tb.R = sh->R; tb.nx_max = sh->nx_max;
+    tb.stern = sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN;
+    tb.use_migration = sh->use_migration != 0;
+    for (int k = 0; k < sh->S; ++k) tb.z[k] = (double)sh->z[k];
+    for (int r = 0; r < sh->R; ++r) {
+        int ne = 0, np = 0;
+        for (int e = 0; e < CATINT_PNP_MAX_REACTANTS; ++e) {
+            if (sh->educt[r][e] >= 0) {
+                if (sh->educt[r][e] >= sh->S) return fail(CATINT_PNP_EINVAL, "educt index out of range");
+                tb.ed[r][ne++] = (int8_t)sh->educt[r][e];
+            }
+            if (sh->product[r][e] >= 0) {
+                if (sh->product[r][e] >= sh->S) return fail(CATINT_PNP_EINVAL, "product index out of range");
+                tb.pr[r][np++] = (int8_t)sh->product[r][e];
+            }
+        }
+        tb.ned[r] = (int8_t)ne; tb.npr[r] = (int8_t)np;
+        tb.kf[r] = sh->kf[r]; tb.kr[r] = sh->kr[r];
+        for (int k = 0; k < sh->S; ++k) tb.nu[r][k] = sh->nu[k][r];
+    }
+    // derivative terms, grouped by the species the derivative is taken with respect to
+    int T = 0;
+    for (int j = 0; j < sh->S; ++j) {
+        tb.tbeg[j] = (int8_t)T;
+        for (int r = 0; r < sh->R; ++r) {
+            for (int side = 0; side < 2; ++side) {
+                const int8_t* lst = side == 0 ? tb.ed[r] : tb.pr[r];
+                const int cnt = side == 0 ? tb.ned[r] : tb.npr[r];
+                for (int p = 0; p < cnt; ++p) {
+                    if (lst[p] != j) continue;
+                    if (T >= MAXT) return fail(CATINT_PNP_EINVAL, "too many reaction derivative terms");
+                    int8_t others[3] = {-1, -1, -1};
+                    int no = 0;
+                    for (int p2 = 0; p2 < cnt; ++p2) if (p2 != p) others[no++] = lst[p2];
+                    tb.tr[T] = (int8_t)r;
+                    tb.ti1[T] = others[0]; tb.ti2[T] = others[1]; tb.ti3[T] = others[2];
+                    tb.tcoef[T] = side == 0 ? tb.kf[r] : -tb.kr[r];
+                    ++T;
+                }
+            }
+        }
+    }
+    tb.tbeg[sh->S] = (int8_t)T;
+    for (int j = sh->S + 1; j <= MAXS; ++j) tb.tbeg[j] = (int8_t)T;
+    tb.T = T;
+    return CATINT_PNP_OK;
+}
+
+static int block_size_of(const CatintPnpShared* sh) {
+    return sh->S + (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN ? 2 : 1);
+}
+
+static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
+    const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
+    // zn[LMAX][N] + ewt[N] + W[nx][NB][NB] + V0[NB][NB] + (y,psi,zb)[N] (used only when the state
+    // does not fit in shared memory, always reserved so that the size query is stateless)
+    size_t d = (size_t)LMAX * nxm * NB + nxm * NB + nxm * NB * NB + NB * NB + 3 * nxm * NB;
+    return (d + 15) & ~size_t(15);
+}
+
+extern "C" size_t catint_pnp_workspace_bytes(const CatintPnpShared* sh, int64_t n_cells) {
+    if (!sh || n_cells <= 0) return 0;
+    return ws_doubles_per_cell(sh) * sizeof(double) * (size_t)n_cells + 64 * sizeof(double);
+}
+
+static int check_cuda(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return CATINT_PNP_ECUDA;
+    }
+    return CATINT_PNP_OK;
+}
+
+#define DISPATCH_NB(NBVAL, CALL, ...)                        \
+    switch (NBVAL) {                                         \
+        case 2: rc = CALL<2>(__VA_ARGS__); break;            \
+        case 3: rc = CALL<3>(__VA_ARGS__); break;            \
+        case 4: rc = CALL<4>(__VA_ARGS__); break;            \
+        case 5: rc = CALL<5>(__VA_ARGS__); break;            \
+        case 6: rc = CALL<6>(__VA_ARGS__); break;            \
+        case 7: rc = CALL<7>(__VA_ARGS__); break;            \
+        case 8: rc = CALL<8>(__VA_ARGS__); break;            \
+        case 9: rc = CALL<9>(__VA_ARGS__); break;            \
+        case 10: rc = CALL<10>(__VA_ARGS__); break;          \
+        case 11: rc = CALL<11>(__VA_ARGS__); break;          \
+        case 12: rc = CALL<12>(__VA_ARGS__); break;          \
+        case 13: rc = CALL<13>(__VA_ARGS__); break;          \
+        default: rc = fail(CATINT_PNP_EINVAL, "unsupported block size (S+1 must be 2..13)"); \
+    }
+
+static int check_common(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells) {
+    if (!sh || !cells) return fail(CATINT_PNP_EINVAL, "NULL argument");
+    if (n_cells <= 0) return fail(CATINT_PNP_EINVAL, "n_cells must be positive");
+    if (!cells->par || !cells->nx) return fail(CATINT_PNP_EINVAL, "cells->par / cells->nx are NULL");
+    if (sh->n_mesh > 0 && !cells->mesh_xi) return fail(CATINT_PNP_EINVAL, "mesh table missing");
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
+        return fail(CATINT_PNP_EINVAL, "Stern/Robin Poisson boundary is not available in this build");
+    if (catint_pnp_device_count() <= 0) return fail(CATINT_PNP_ENODEV, "no sm_100 CUDA device visible");
+    return CATINT_PNP_OK;
+}
+
+extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                    const double* c, double* dcdt, double* g_out, double* phi_out,
+                                    void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!c || !dcdt) return fail(CATINT_PNP_EINVAL, "c / dcdt are NULL");
+    RhsParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.c = c; P.n_cells = n_cells; P.dcdt = dcdt; P.g_out = g_out; P.phi_out = phi_out;
+    const int WARPS = 4;
+    const size_t smem = ((sizeof(DevTables) + 15) & ~size_t(15)) +
+                        WARPS * (((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)sh->nx_max * sizeof(double));
+    cudaFuncSetAttribute(pnp_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned grid = (unsigned)((n_cells + WARPS - 1) / WARPS);
+    pnp_rhs_kernel<<<grid, WARPS * 32, smem, (cudaStream_t)cuda_stream>>>(P);
+    return check_cuda("pnp_rhs_kernel launch");
+}
+
+extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                         const double* y, double* F, double* Lb, double* Db, double* Ub,
+                                         void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!y) return fail(CATINT_PNP_EINVAL, "y is NULL");
+    JacParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.y = y; P.n_cells = n_cells; P.F = F; P.Lb = Lb; P.Db = Db; P.Ub = Ub;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DISPATCH_NB(block_size_of(sh), launch_jac, P, st);
+    if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_jacobian_kernel launch failed");
+    return rc;
+}
+
+extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                      const double* y0, const CatintPnpControl* ctl,
+                                      double* c_out, double* phi_out, double* g_out, double* flux_out,
+                                      int32_t* status, int32_t* n_steps, int32_t* n_newton,
+                                      void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    if (!ctl || !ctl->t_out || ctl->n_out < 1) return fail(CATINT_PNP_EINVAL, "control / t_out missing");
+    if (!c_out || !status || !n_steps || !n_newton) return fail(CATINT_PNP_EINVAL, "output pointers are NULL");
+    if (!(ctl->rtol >= 0.0) || !(ctl->atol > 0.0)) return fail(CATINT_PNP_EINVAL, "need rtol >= 0 and atol > 0");
+    for (int k = 0; k < ctl->n_out; ++k)
+        if (!(ctl->t_out[k] > 0.0) || (k > 0 && !(ctl->t_out[k] > ctl->t_out[k - 1])))
+            return fail(CATINT_PNP_EINVAL, "t_out must be positive and increasing");
+    const size_t need = catint_pnp_workspace_bytes(sh, n_cells);
+    if (!workspace || workspace_bytes < need) return fail(CATINT_PNP_ENOMEM, "workspace too small");
+    if (ctl->n_out > 60) return fail(CATINT_PNP_EINVAL, "at most 60 output times per call");
+
+    SolveParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
+    P.y0 = y0; P.n_cells = n_cells;
+    P.mode = ctl->mode; P.max_steps = ctl->max_steps > 0 ? ctl->max_steps : 100000;
+    P.n_out = ctl->n_out; P.polish_max_iter = ctl->polish_max_iter > 0 ? ctl->polish_max_iter : 8;
+    P.rtol = ctl->rtol; P.atol = ctl->atol; P.h0 = ctl->h0;
+    P.polish_rtol = ctl->polish_rtol > 0.0 ? ctl->polish_rtol : 1e-10;
+    // the output times travel in the tail of the workspace
+    double* wsd = reinterpret_cast<double*>(workspace);
+    double* t_dev = wsd + ws_doubles_per_cell(sh) * (size_t)n_cells;
+    if (cudaMemcpyAsync(t_dev, ctl->t_out, sizeof(double) * ctl->n_out, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return check_cuda("copy of t_out");
+    P.t_out = t_dev;
+    P.c_out = c_out; P.phi_out = phi_out; P.g_out = g_out; P.flux_out = flux_out;
+    P.status = status; P.n_steps = n_steps; P.n_newton = n_newton;
+    P.ws = wsd; P.ws_stride = (long long)ws_doubles_per_cell(sh);
+    P.state_in_smem = 1;
+    DISPATCH_NB(block_size_of(sh), launch_bdf, P, st);
+    if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
+    return rc;
+}

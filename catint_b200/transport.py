@@ -666,15 +666,8 @@ class Transport(object):
             pb_bound=copy.deepcopy(pb_bound), nx=nx)
         self._tables = self._load_tables()
 
-        model = derive_model(species, electrode_reactions, electrolyte_reactions, system, pb_bound, nx,
-                             self.logger, self._tables)
+        model = self.derive_for(_quiet=False)
         self._adopt(model)
-        # the reference keeps working on (and mutating) the caller's dicts; mirror
-        # the visible part of that: the caller's system dict receives the defaults
-        if system is not None:
-            for key in self.system:
-                system.setdefault(key, self.system[key])
-
         if self.debye_length > self.xmax / 2.:
             self.logger.warning('| CI | -- | Debye length is larger than 1/4th of the xmesh. Take care that the x '
                                 'discretization is not too coarse!.')
@@ -789,21 +782,29 @@ class Transport(object):
         return ca
 
     # ------------------------------------------------------------------
-    def derive_for(self, **system_overrides):
+    def derive_for(self, _quiet=True, **system_overrides):
         """model arrays for the same inputs with some system values replaced
-        (one sweep point).  Used by Calculator to build the cell batch."""
-        system = copy.deepcopy(self._inputs['system']) if self._inputs['system'] is not None else {}
-        system.update(system_overrides)
+        (one sweep point).  Used by Calculator to build the cell batch.
+
+        Backend extension: species[sp]['flux'] / ['current density'] /
+        ['bulk_concentration'] may be a callable f(system) -> float, evaluated
+        with the system values of the sweep point (descriptor-dependent fixed
+        fluxes, e.g. a Tafel law; an OH- concentration that follows bulk_pH)."""
+        system = copy.deepcopy(self._inputs['system']) if self._inputs['system'] is not None else None
+        if system_overrides:
+            system = {} if system is None else system
+            system.update(system_overrides)
         species = copy.deepcopy(self._inputs['species'])
-        # callables are the documented extension for descriptor-dependent fluxes
         if species is not None:
+            view = dict(SYSTEM_DEFAULTS)
+            view.update(system or {})
             for sp in species:
-                for key in ('flux', 'current density'):
+                for key in ('flux', 'current density', 'bulk_concentration'):
                     if callable(species[sp].get(key, None)):
-                        species[sp][key] = float(species[sp][key](system))
+                        species[sp][key] = float(species[sp][key](view))
         return derive_model(species, self._inputs['electrode_reactions'], self._inputs['electrolyte_reactions'],
                             system, self._inputs['pb_bound'], self._inputs['nx'], self.logger, self._tables,
-                            quiet=True)
+                            quiet=_quiet)
 
     # ------------------------------------------------------------------
     def initialize_descriptors(self, descriptors):

@@ -1,0 +1,67 @@
+"""Named synthetic workloads (SURVEY 8d / BASELINE.json configs) as Transport keyword dicts.
+
+C1  single cell CO2R at Au in 0.1 M-class KHCO3 (pH 6.8, CO2 saturated), L = 50 um,
+    nx = 100 (101 nodes), fixed fluxes i_CO = -10, i_H2 = -5 A/m^2
+C2  the same chemistry, 1024-point potential sweep phiM = linspace(-0.5,-1.5,1024) with
+    Tafel-law partial currents  i_CO = -10*10^(-(phiM+0.9)/0.12), i_H2 = -5*10^(...)
+    clipped at 150 A/m^2 each (the fixed-flux FD model only feels phiM through the fluxes)
+C4  10 species (adds CH4 from a third electrode reaction and inert Cl-),
+    bulk_pH x boundary-layer-thickness sweep
+
+Fresh dict objects on every call.  Descriptor-dependent currents are given as
+callables of the system dict (backend extension, see Transport.derive_for).
+"""
+import numpy as np
+
+
+def tafel_current(i_ref, phi_ref=-0.9, slope=0.12, clip=150.0):
+    def current(system):
+        i = i_ref * 10.0 ** (-(system['phiM'] - phi_ref) / slope)
+        return float(np.sign(i_ref) * min(abs(i), clip))
+    return current
+
+
+def co2r_inputs(pH=6.8, L=50e-6, i_CO=-10., i_H2=-5., nx=100, migration=True, reactions=True,
+                temperature=298., phiM=-0.9, extra_species=False):
+    system = {'temperature': temperature, 'pressure': 1.013, 'bulk_pH': pH, 'boundary thickness': L,
+              'epsilon': 78.36, 'migration': migration, 'electrode reactions': True,
+              'electrolyte reactions': reactions, 'phiM': phiM, 'phiPZC': 0.16, 'Stern capacitance': 20.}
+    electrolyte_reactions = ['bicarbonate-base', 'water-diss',
+                             {'additional_cell_reactions': 'bicarbonate-acid'}] if reactions else None
+    electrode_reactions = {'CO': {'reaction': 'CO2 + H2O + 2 e- -> CO + 2 OH-'},
+                           'H2': {'reaction': '2 H2O + 2 e- -> H2 + 2 OH-'}}
+    species = {'K+': {'bulk_concentration': 'charge_neutrality'},
+               'CO2': {'bulk_concentration': 'Henry'},
+               # follows the bulk_pH of the sweep point (a plain float would stay at the input pH)
+               'OH-': {'bulk_concentration': lambda system: 10 ** (system['bulk_pH'] - 14.) * 1000.},
+               'CO': {'bulk_concentration': 0.0, 'current density': i_CO},
+               'H2': {'bulk_concentration': 0.0, 'current density': i_H2}}
+    if extra_species:
+        electrode_reactions['CH4'] = {'reaction': 'CO2 + 6 H2O + 8 e- -> CH4 + 8 OH-'}
+        species['CH4'] = {'bulk_concentration': 0.0, 'current density': -2.0}
+        species['Cl-'] = {'bulk_concentration': 10.0}
+    return dict(species=species, electrode_reactions=electrode_reactions,
+                electrolyte_reactions=electrolyte_reactions, system=system, nx=nx)
+
+
+def c1():
+    return co2r_inputs()
+
+
+def c2(n_potentials=1024, phi_min=-0.5, phi_max=-1.5):
+    kw = co2r_inputs(i_CO=tafel_current(-10.), i_H2=tafel_current(-5.))
+    kw['descriptors'] = {'phiM': list(np.linspace(phi_min, phi_max, n_potentials))}
+    return kw
+
+
+def c4(n_pH=256, n_L=256):
+    kw = co2r_inputs(extra_species=True)
+    kw['descriptors'] = {'bulk_pH': list(np.linspace(6.0, 7.83, n_pH)),
+                         'boundary thickness': list(np.geomspace(10e-6, 200e-6, n_L))}
+    return kw
+
+
+def replicate_batch(batch, n_cells):
+    """tile a CellBatch to n_cells (synthetic weak-scaling workloads)."""
+    idx = np.arange(n_cells) % batch.B
+    return batch.select(idx)

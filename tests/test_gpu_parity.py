@@ -1,0 +1,224 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Run on the GPU box:
+    python -m pytest tests -m gpu
+
+Tolerances (stated per north_star): K1/K2 are the same arithmetic up to summation order ->
+1e-12 relative to the largest entry; converged profiles / potentials / fluxes 1e-6 relative
+(atol floor 1e-12*max c_bulk for values that cross zero)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, RHS_CASES, batch_from_setup, oracle_system_of_cell
+
+pytestmark = pytest.mark.gpu
+
+RTOL_PROFILE = 1e-6
+
+
+@pytest.fixture(scope='module')
+def bk():
+    import torch
+    from catint_b200 import backend as be
+    assert torch.cuda.is_available(), 'GPU tests need a B200'
+    return be.PnpBackend('cuda:0')
+
+
+def relerr(got, want, cscale, floor=1e-12):
+    return float(np.max(np.abs(got - want) / (np.abs(want) + floor * cscale)))
+
+
+def to_dev(a):
+    import torch
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device='cuda:0')
+
+
+# ---------------------------------------------------------------- K1 ----------------------
+@pytest.mark.parametrize('name', RHS_CASES)
+@pytest.mark.parametrize('mode,literal', [('summed', False), ('legacy_overwrite', True)])
+def test_rhs_kernel_matches_oracle(bk, name, mode, literal):
+    from oracle.fixtures import system_from_setup
+    su = load_golden('ref_%s.npz' % name)
+    S, n = len(su['z']), int(su['nx'])
+    batch = batch_from_setup(su, B=len(su['rhs_states']), rate_mode=mode, literal_sign=literal)
+    db = bk.upload(batch)
+    s = system_from_setup(su, mode, literal)
+    c = np.stack([st.reshape(S, n).T for st in su['rhs_states']])
+    dcdt, g, phi = bk.rhs(db, to_dev(c))
+    dcdt, g, phi = dcdt.cpu().numpy(), g.cpu().numpy(), phi.cpu().numpy()
+    for k, st in enumerate(su['rhs_states']):
+        ref, v, gg, _ = s.rhs(st, with_field=True)
+        ref = ref.reshape(S, n).T
+        assert np.max(np.abs(dcdt[k] - ref)) <= 1e-12 * np.max(np.abs(ref))
+        if s.use_migration:
+            assert np.max(np.abs(g[k] - gg)) <= 1e-12 * np.max(np.abs(gg))
+            assert np.max(np.abs(phi[k] - v)) <= 1e-12 * max(np.max(np.abs(v)), 1e-300)
+        if literal and mode == 'legacy_overwrite':
+            # the reference's own ode_func on the same state
+            r2 = su['rhs_ref'][k].reshape(S, n).T
+            assert np.max(np.abs(dcdt[k] - r2)) <= 1e-12 * np.max(np.abs(r2))
+
+
+# ---------------------------------------------------------------- K2 ----------------------
+@pytest.mark.parametrize('name', ['c1', 'c1_norx', 'c4', 'c1_L30', 'c1_nomig'])
+def test_jacobian_blocks_match_oracle(bk, name):
+    from oracle.fixtures import system_from_setup
+    from oracle.pnp_local import LocalForm
+    su = load_golden('ref_%s.npz' % name)
+    S, n = len(su['z']), int(su['nx'])
+    s = system_from_setup(su, 'summed')
+    lf = LocalForm(s)
+    batch = batch_from_setup(su, B=2)
+    db = bk.upload(batch)
+    for st in (su['rhs_states'][2], su['rhs_states'][4]):
+        y = lf.y_from_c(st.reshape(S, n))
+        F, L, Dg, U, E0 = lf.residual(y, blocks=True)
+        Fg, Lg, Dgg, Ug = [a[1].cpu().numpy() for a in bk.jacobian(db, to_dev(np.stack([y, y])))]
+        for got, want in ((Fg, F), (Dgg, Dg), (Ug, U), (Lg[1:], L[1:]), (Lg[0], E0)):
+            assert np.max(np.abs(got - want)) <= 1e-12 * max(np.max(np.abs(want)), 1e-300)
+
+
+# ---------------------------------------------------------------- K3 ----------------------
+GOLD = [('c1', 'summed', False), ('c1', 'legacy_overwrite', True), ('c1_nomig', 'summed', False),
+        ('c1_norx', 'summed', False), ('c1_pH7p5', 'summed', False)]
+
+
+@pytest.mark.parametrize('name,mode,literal', GOLD)
+def test_steady_state_matches_odeint_golden(bk, name, mode, literal):
+    """integrate to t=200 s + Newton polish == Newton root of the oracle's odeint end state
+    (and == the odeint end state itself) to 1e-6 relative; wall flux == imposed flux."""
+    from catint_b200 import backend as be
+    from oracle.fixtures import system_from_setup
+    su = load_golden('ref_%s.npz' % name)
+    go = load_golden('oracle_%s_%s.npz' % (name, mode))
+    S, n = len(su['z']), int(su['nx'])
+    batch = batch_from_setup(su, B=2, rate_mode=mode, literal_sign=literal)
+    out = bk.solve(bk.upload(batch), [200.0], mode=be.MODE_STEADY)
+    assert out['status'].tolist() == [0, 0]
+    cs = np.max(np.abs(su['c_bulk']))
+    got = out['c'][-1, 0].cpu().numpy()
+    assert np.array_equal(got, out['c'][-1, 1].cpu().numpy())           # identical cells, identical bits
+    assert relerr(got, go['newton_c'].reshape(S, n).T, cs) < RTOL_PROFILE
+    assert relerr(got, go['c_end'].reshape(S, n).T, cs) < RTOL_PROFILE
+    s = system_from_setup(su, mode, literal)
+    if s.use_migration:
+        gsc = np.max(np.abs(go['newton_grad']))
+        assert np.max(np.abs(out['g'][-1, 0].cpu().numpy() - go['newton_grad'])) < RTOL_PROFILE * gsc
+        psc = max(np.max(np.abs(go['newton_potential'])), 1e-300)
+        assert np.max(np.abs(out['phi'][-1, 0].cpu().numpy() - go['newton_potential'])) < RTOL_PROFILE * psc
+    J = batch.par[0, S:2 * S]
+    fl = out['flux'][0].cpu().numpy()
+    assert np.max(np.abs(fl - J)) < RTOL_PROFILE * np.max(np.abs(J))
+
+
+@pytest.mark.parametrize('name,mode,literal', [('c1', 'summed', False), ('c1_norx', 'summed', False)])
+def test_transient_outputs_match_odeint(bk, name, mode, literal):
+    """time-dependent mode at matching rtol/atol (scipy defaults): state at t=10 s and t=200 s.
+    Both integrators carry their own global error of order 100*tol, hence 1e-5 at t=10 s."""
+    from catint_b200 import backend as be
+    su = load_golden('ref_%s.npz' % name)
+    go = load_golden('oracle_%s_%s.npz' % (name, mode))
+    S, n = len(su['z']), int(su['nx'])
+    batch = batch_from_setup(su, B=1, rate_mode=mode, literal_sign=literal)
+    out = bk.solve(bk.upload(batch), [10.0, 200.0], mode=be.MODE_TRANSIENT)
+    assert out['status'].tolist() == [0]
+    cs = np.max(np.abs(su['c_bulk']))
+    assert relerr(out['c'][0, 0].cpu().numpy(), go['c_t10'].reshape(S, n).T, cs, floor=1e-9) < 1e-5
+    assert relerr(out['c'][1, 0].cpu().numpy(), go['c_end'].reshape(S, n).T, cs, floor=1e-9) < RTOL_PROFILE
+
+
+def test_potential_sweep_cells_match_odeint(bk, resultsdir):
+    """8 cells of the 1024-point C2 sweep (currents 0.005 ... 150 A/m^2) against their odeint goldens:
+    the discrete steady problem has several roots, the integrator must land on odeint's."""
+    from catint_b200 import backend as be, workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import build_cell_batch
+    go = load_golden('oracle_c2_sweep.npz')
+    tp = Transport(resultsdir=resultsdir, **workloads.c2())
+    batch, _ = build_cell_batch(tp)
+    cells = [int(c) for c in go['cells']]
+    assert np.array_equal(batch.par[cells], go['par'])
+    sub = batch.select(cells)
+    out = bk.solve(bk.upload(sub), [200.0], mode=be.MODE_STEADY)
+    assert out['status'].tolist() == [0] * len(cells)
+    S, n = sub.S, sub.nx_max
+    cs = np.max(np.abs(sub.par[0, :S]))
+    for k, c in enumerate(cells):
+        got = out['c'][-1, k].cpu().numpy()
+        assert relerr(got, go['newton_c_%d' % c].reshape(S, n).T, cs) < RTOL_PROFILE, c
+        assert relerr(got, go['c_end_%d' % c].reshape(S, n).T, cs, floor=1e-9) < RTOL_PROFILE, c
+
+
+def test_ragged_and_mixed_batch(bk):
+    """cells with 101 and 102 nodes, different bulk compositions and temperatures in one launch;
+    every cell must equal its own single-cell solve bit for bit, padding must stay untouched."""
+    from catint_b200 import backend as be
+    a, b, c = load_golden('ref_c1.npz'), load_golden('ref_c1_L30.npz'), load_golden('ref_c1_T320.npz')
+    parts = [batch_from_setup(x, B=1) for x in (a, b, c, b, a)]
+    par = np.concatenate([p.par for p in parts])
+    nx = np.concatenate([p.nx for p in parts])
+    mixed = be.CellBatch(parts[0].z, parts[0].reactions, parts[0].nu, par, nx, nx_max=104)
+    out = bk.solve(bk.upload(mixed), [50.0], mode=be.MODE_STEADY)
+    assert out['status'].tolist() == [0] * 5
+    cm = out['c'][-1].cpu().numpy()
+    assert np.all(cm[:, 102:, :] == 0.0) and np.all(cm[0, 101:, :] == 0.0)
+    for k, p in enumerate(parts):
+        single = be.CellBatch(p.z, p.reactions, p.nu, p.par, p.nx, nx_max=104)
+        o1 = bk.solve(bk.upload(single), [50.0], mode=be.MODE_STEADY)
+        assert np.array_equal(o1['c'][-1, 0].cpu().numpy(), cm[k])
+    assert not np.array_equal(cm[0, :101], cm[1, :101])
+
+
+def test_steady_state_is_a_root_of_the_rhs_kernel(bk):
+    """size-independent property at the full C2 size: every converged cell zeroes K1's dc/dt and
+    carries exactly the imposed wall flux; CO2 depletion grows monotonically with the current."""
+    import torch
+    from catint_b200 import backend as be, workloads
+    su = load_golden('ref_c1.npz')
+    S = 8
+    names = [str(s) for s in su['species']]
+    phis = np.linspace(-0.5, -1.5, 1024)
+    fl = np.zeros((1024, S))
+    for k, phi in enumerate(phis):
+        f = 10.0 ** (-(phi + 0.9) / 0.12)
+        jco, jh2 = min(10 * f, 150.) / 2 / 96485.33289, min(5 * f, 150.) / 2 / 96485.33289
+        fl[k, names.index('CO')] = jco; fl[k, names.index('H2')] = jh2
+        fl[k, names.index('CO2')] = -jco; fl[k, names.index('OH-')] = 2 * jco + 2 * jh2
+    batch = batch_from_setup(su, B=1024, fluxes=fl)
+    db = bk.upload(batch)
+    out = bk.solve(db, [200.0], mode=be.MODE_STEADY)
+    assert int((out['status'] == 0).sum()) == 1024
+    c = out['c'][-1].contiguous()
+    dcdt, _, _ = bk.rhs(db, c)
+    # scale: rate of change of the initial (bulk) state of the same cells
+    c0 = torch.tensor(np.broadcast_to(su['c_bulk'][None, None, :], (1024, 101, S)).copy(), device='cuda:0')
+    d0, _, _ = bk.rhs(db, c0)
+    ratio = dcdt.abs().amax(dim=(1, 2)) / d0.abs().amax(dim=(1, 2))
+    assert float(ratio.max()) < 1e-9
+    flux = out['flux'].cpu().numpy()
+    assert np.max(np.abs(flux - fl)) <= 1e-9 * np.max(np.abs(fl))
+    co2 = c[:, 0, names.index('CO2')].cpu().numpy()
+    assert np.all(np.diff(co2) <= 1e-9)
+    assert int(out['n_steps'].max()) < 5000
+
+
+def test_calculator_run_end_to_end(bk, resultsdir):
+    """the reference-facing call: Transport -> set_calculator -> Calculator.run() on a small sweep."""
+    from catint_b200 import workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import Calculator
+    kw = workloads.c2(n_potentials=8, phi_min=-0.8, phi_max=-1.0)
+    tp = Transport(resultsdir=resultsdir, model_name='sweep', **kw)
+    tp.set_calculator('odeint')
+    calc = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary')
+    res = calc.run()
+    assert calc.stats['converged'] == 8
+    go = load_golden('oracle_c1_summed.npz')
+    # phiM=-0.9 is not on this grid, but cell fluxes are monotone: compare conventions instead
+    ad = tp.alldata[3]
+    assert len(ad['species']['CO2']['concentration']) == 101
+    assert ad['species']['CO']['electrode_current_density'] == pytest.approx(
+        tp.derive_for(phiM=tp.alldata_names[3][0]).species['CO']['current density'] / (-10.), rel=1e-6)
+    assert ad['system']['status'] == 'converged'
+    assert len(tp.cout) == 1 and tp.cout[0].shape == (8 * 101,)
+    assert np.array_equal(tp.cout[0][101:202], np.array(tp.alldata[7]['species']['CO2']['concentration']))
+    import os
+    assert os.path.isfile(os.path.join(tp.outputfoldername, 'alldata.pkl'))
