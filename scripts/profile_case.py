@@ -1,0 +1,30 @@
+"""Short, profiler-friendly invocation of the hot path: the 1024-cell C2 batch integrated for a
+bounded number of BDF steps (enough to be representative, short enough for ncu's replays).
+    python scripts/profile_case.py [max_steps] [n_cells]
+"""
+import os, sys, time
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+os.environ.setdefault('CATINT_QUIET', '1')
+import numpy as np
+import torch
+import bench
+from catint_b200 import backend as be
+
+def main():
+    max_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    n_cells = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    tp, batch = bench.c2_batch(n_cells=n_cells)
+    bk = be.PnpBackend('cuda:0')
+    db = bk.upload(batch)
+    out = bk.alloc_outputs(db, 1)
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.time()
+        bk.solve(db, [bench.T_END], mode=be.MODE_STEADY, max_steps=max_steps, out=out)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        nn = float(out['n_newton'].double().sum())
+        print('rep %d: %.4f s, %d cells, newton total %.0f -> %.1f us per newton iteration per cell-warp, %.2f us amortised'
+              % (rep, dt, n_cells, nn, dt / (nn / n_cells) * 1e6, dt / nn * 1e6))
+
+if __name__ == '__main__':
+    main()

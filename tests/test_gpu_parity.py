@@ -188,11 +188,12 @@ def test_steady_state_is_a_root_of_the_rhs_kernel(bk):
     assert int((out['status'] == 0).sum()) == 1024
     c = out['c'][-1].contiguous()
     dcdt, _, _ = bk.rhs(db, c)
-    # scale: rate of change of the initial (bulk) state of the same cells
-    c0 = torch.tensor(np.broadcast_to(su['c_bulk'][None, None, :], (1024, 101, S)).copy(), device='cuda:0')
-    d0, _, _ = bk.rhs(db, c0)
-    ratio = dcdt.abs().amax(dim=(1, 2)) / d0.abs().amax(dim=(1, 2))
-    assert float(ratio.max()) < 1e-9
+    # scale: size of the individual stencil terms D_k*c_k/dx^2 that cancel in dc/dt (rounding floor ~1e-16 of it)
+    D = torch.tensor(su['D'], device='cuda:0')
+    scale = (c.abs().amax(dim=1) * D[None, :] / float(su['dx']) ** 2).amax(dim=1)
+    ratio = dcdt.abs().amax(dim=(1, 2)) / scale
+    # the oracle's own Newton root sits at 2e-11 of this scale (cancellation in the migration terms)
+    assert float(ratio.max()) < 5e-10, float(ratio.max())
     flux = out['flux'].cpu().numpy()
     assert np.max(np.abs(flux - fl)) <= 1e-9 * np.max(np.abs(fl))
     co2 = c[:, 0, names.index('CO2')].cpu().numpy()
