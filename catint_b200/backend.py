@@ -53,7 +53,7 @@ class CatintPnpControl(ctypes.Structure):
 
 EXPORTS = ['catint_pnp_version', 'catint_pnp_last_error', 'catint_pnp_device_count',
            'catint_pnp_workspace_bytes', 'catint_pnp_rhs_batch', 'catint_pnp_jacobian_batch',
-           'catint_pnp_solve_batch']
+           'catint_pnp_solve_batch', 'catint_pnp_debug_profile_buffer']
 
 
 def library_path():
@@ -85,7 +85,9 @@ def load_library():
     lib.catint_pnp_solve_batch.restype = ctypes.c_int
     lib.catint_pnp_solve_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
                                            ctypes.c_int64, vp, ctypes.POINTER(CatintPnpControl),
-                                           vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+                                           vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.catint_pnp_debug_profile_buffer.restype = None
+    lib.catint_pnp_debug_profile_buffer.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -287,6 +289,7 @@ class PnpBackend(object):
             'status': torch.full((b.B,), -1, dtype=torch.int32, device=dev),
             'n_steps': torch.zeros((b.B,), dtype=torch.int32, device=dev),
             'n_newton': torch.zeros((b.B,), dtype=torch.int32, device=dev),
+            'n_setups': torch.zeros((b.B,), dtype=torch.int32, device=dev),
         }
 
     def solve(self, dbatch, t_out, mode=MODE_STEADY, rtol=1.49012e-8, atol=1.49012e-8, y0=None,
@@ -314,6 +317,7 @@ class PnpBackend(object):
                 y0.data_ptr() if y0 is not None else None, ctypes.byref(ctl),
                 out['c'].data_ptr(), out['phi'].data_ptr(), out['g'].data_ptr(), out['flux'].data_ptr(),
                 out['status'].data_ptr(), out['n_steps'].data_ptr(), out['n_newton'].data_ptr(),
+                out['n_setups'].data_ptr(),
                 ws.data_ptr(), ctypes.c_size_t(need), self._stream())
         self._check(rc, 'catint_pnp_solve_batch')
         self.launches += 1

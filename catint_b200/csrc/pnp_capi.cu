@@ -27,7 +27,9 @@ static int fail(int code, const char* fmt, const char* a = "") {
     return code;
 }
 
-extern "C" int catint_pnp_version(void) { return 100; }
+static long long* g_prof = nullptr;      // debug hook, see catint_pnp_debug_profile_buffer
+extern "C" int catint_pnp_version(void) { return 101; }
+extern "C" void catint_pnp_debug_profile_buffer(void* dev_ptr) { g_prof = reinterpret_cast<long long*>(dev_ptr); }
 extern "C" const char* catint_pnp_last_error(void) { return g_err; }
 
 extern "C" int catint_pnp_device_count(void) {
@@ -101,9 +103,11 @@ static int block_size_of(const CatintPnpShared* sh) {
 
 static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
     const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
-    // zn[LMAX][N] + ewt[N] + W[nx][NB][NB] + V0[NB][NB] + (y,psi,zb)[N] (used only when the state
+    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1[NB][NBP] + (y,psi,zb)[N] (used only when the state
     // does not fit in shared memory, always reserved so that the size query is stateless)
-    size_t d = (size_t)LMAX * nxm * NB + nxm * NB + nxm * NB * NB + NB * NB + 3 * nxm * NB;
+    const size_t NBP = NB + (NB & 1);
+    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * NB * NBP) + align4(4 * nxm * NB) +
+               2 * align4(NB * NBP) + 3 * align4(nxm * NB);
     return (d + 15) & ~size_t(15);
 }
 
@@ -189,7 +193,7 @@ extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const Catint
 extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
                                       const double* y0, const CatintPnpControl* ctl,
                                       double* c_out, double* phi_out, double* g_out, double* flux_out,
-                                      int32_t* status, int32_t* n_steps, int32_t* n_newton,
+                                      int32_t* status, int32_t* n_steps, int32_t* n_newton, int32_t* n_setups,
                                       void* workspace, size_t workspace_bytes, void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
@@ -220,9 +224,10 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
         return check_cuda("copy of t_out");
     P.t_out = t_dev;
     P.c_out = c_out; P.phi_out = phi_out; P.g_out = g_out; P.flux_out = flux_out;
-    P.status = status; P.n_steps = n_steps; P.n_newton = n_newton;
+    P.status = status; P.n_steps = n_steps; P.n_newton = n_newton; P.n_setups = n_setups;
     P.ws = wsd; P.ws_stride = (long long)ws_doubles_per_cell(sh);
     P.state_in_smem = 1;
+    P.prof = g_prof;
     DISPATCH_NB(block_size_of(sh), launch_bdf, P, st);
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
     return rc;

@@ -4,51 +4,46 @@
 //   K2  pnp_jacobian_kernel  residual + block-tridiagonal Jacobian blocks (parity/debug)
 //   K3  pnp_bdf_kernel       per-cell BDF/Newton integrator with fused assembly +
 //                            block-Thomas solve (see pnp_solver.cuh)
+#pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 
-#pragma once
 #include "../../include/catint_pnp.h"
 #include "pnp_solver.cuh"
 
 namespace catint {
 
-// ===========================================================================
-// cell set-up shared by all kernels
-// ===========================================================================
-__device__ __forceinline__ void load_cell(const DevTables& tb, const double* par, const int* nx,
-                                          const int* mesh_id, const double* mesh_xi, long long cell,
-                                          int lane, CellScalars& cs, CellSpecies* sp) {
-    const int S = tb.S;
-    const double* p = par + (size_t)cell * CATINT_PNP_NPAR(S);
-    cs.n = nx[cell];
-    const int mid = mesh_id ? mesh_id[cell] : -1;
-    cs.uniform = mid < 0;
-    cs.xi = mid < 0 ? nullptr : mesh_xi + (size_t)mid * tb.nx_max;
-    cs.beta = p[CATINT_PNP_P_BETA(S)];
-    cs.eps = p[CATINT_PNP_P_EPS(S)];
-    cs.phi_wall = p[CATINT_PNP_P_PHIWALL(S)];
-    cs.g_bulk = p[CATINT_PNP_P_GBULK(S)];
-    cs.cstern = p[CATINT_PNP_P_CSTERN(S)];
-    cs.dx = p[CATINT_PNP_P_SCALE(S)];
-    if (lane < S) {
-        sp->cb[lane] = p[CATINT_PNP_P_CBULK(S) + lane];
-        sp->J[lane] = p[CATINT_PNP_P_FLUX(S) + lane];
-        sp->D[lane] = p[CATINT_PNP_P_DIFF(S) + lane];
-        const double q = tb.z[lane] * UNIT_F;
-        sp->q[lane] = q;
-        sp->bq[lane] = cs.beta * q;
-    }
-    __syncwarp();
-}
+constexpr int QMAX = 5;
+constexpr int LMAX = QMAX + 1;     // Nordsieck vectors zn[0..QMAX]
 
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
+// integrator constants (VODE/CVODE family)
+constexpr double ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
+constexpr double ETAMX1 = 1e4, ETAMX2 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1, ETACF = 0.25, THRESH = 1.5;
+constexpr int MXNCF = 10, MXNEF = 7, MXNEF1 = 3, SMALL_NEF = 2, LONG_WAIT = 10;
+constexpr int MAXCOR = 3, MSBP = 20;
+constexpr double CRDOWN = 0.3, RDIV = 2.0, NLSCOEF = 0.1, DGMAX = 0.3;
+
+struct SolveParams {
+    DevTables tb;
+    // per-cell inputs
+    const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
+    const double* y0;          // optional [B][nx_max][S]
+    long long n_cells;
+    // control
+    int mode, max_steps, n_out, polish_max_iter;
+    double rtol, atol, h0, polish_rtol;
+    const double* t_out;       // device [n_out]
+    // outputs
+    double* c_out; double* phi_out; double* g_out; double* flux_out;
+    int* status; int* n_steps; int* n_newton; int* n_setups;
+    // workspace (global), per cell: zn[LMAX][N], ewt[N], inv[nx][NB][NB], W[nx][NB][NB], V0[NB][NB],
+    // la[nx][2NB] (+ y,psi,zb if they do not fit in shared memory)
+    double* ws; long long ws_stride;   // doubles per cell
+    int state_in_smem;
+    long long* prof;           // optional [B][8] cycle counters per phase (debug hook), or nullptr
+};
 
 // g from the concentrations stored in y (default Poisson BCs): g_{n-1}=g_bulk,
 // g_i = g_{i+1} + h_i*sum_k q_k c_{k,i}/eps, g_0 by linear extrapolation
@@ -230,8 +225,11 @@ __device__ void history_pass(WarpState<NB>& ws, int q_old, int dq, bool undo, do
     __syncwarp();
 }
 
-template <int NB>
-__global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
+// SMEM = true: the Newton iterate, psi and the rhs/update vector live in shared memory and are
+// addressed with LDS/STS (a generic pointer would queue these critical-path accesses behind the
+// global prefetch loads in the L1TEX pipeline); SMEM = false: large grids, state in the workspace.
+template <int NB, bool SMEM>
+__global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     constexpr int S = NB - 1;
     constexpr int WARPS = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -249,12 +247,13 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
-    const size_t state_doubles = P.state_in_smem ? (size_t)3 * nxm * NB : 0;
+    const size_t state_doubles = SMEM ? (size_t)3 * nxm * NB : 0;
     const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
                             (size_t)(scratch_doubles<NB>() + state_doubles) * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
     if (cell >= P.n_cells) return;
 
+    const long long t_kernel0 = clock64();
     WarpState<NB> ws;
     ws.lane = lane;
     ws.tb = tb;
@@ -266,11 +265,14 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
     const int N = n * NB;
     ws.N = N;
     double* g = P.ws + (size_t)cell * P.ws_stride;
-    ws.zn = g;                 g += (size_t)LMAX * nxm * NB;
-    ws.ewt = g;                g += (size_t)nxm * NB;
-    ws.W = g;                  g += (size_t)nxm * NB * NB;
-    ws.V0 = g;                 g += (size_t)NB * NB;
-    if (P.state_in_smem) {
+    constexpr int NBP = padded<NB>();
+    ws.zn = g;                 g += align4((size_t)LMAX * nxm * NB);
+    ws.ewt = g;                g += align4((size_t)nxm * NB);
+    ws.inv = g;                g += align4((size_t)nxm * NB * NBP);
+    ws.la = g;                 g += align4((size_t)nxm * NB * 4);
+    ws.V0 = g;                 g += align4((size_t)NB * NBP);
+    ws.W1 = g;                 g += align4((size_t)NB * NBP);
+    if constexpr (SMEM) {
         double* s = ws.scratch + scratch_doubles<NB>();
         ws.y = s; ws.psi = s + (size_t)nxm * NB; ws.zb = s + (size_t)2 * nxm * NB;
     } else {
@@ -289,25 +291,21 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
     consistent_field<NB>(ws, ws.y);
 
     const double rtol = P.rtol, atol = P.atol;
-    double* sl = ws.scratch + 2 * (NB + 1);
-    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB; double* sf = sua + NB;
 
     // zn[0]=y, zn[1]=h*f(y) (mass rows), ewt; first step size from the initial rate of change
     double fnorm = 0.0;
-    for (int i = 0; i < n; ++i) {
-        const double F = node_rows<NB>(ws, ws.y, i, sl, sa, sud, sua, sf);
-        if (lane < NB) {
-            const size_t idx = (size_t)i * NB + lane;
-            const bool mass = lane < S && i < n - 1;
-            const double yv = ws.y[idx];
-            const double w = 1.0 / (rtol * fabs(yv) + atol);
-            ws.ewt[idx] = w;
-            ws.zn[idx] = yv;
-            ws.zn[(size_t)N + idx] = mass ? F : 0.0;      // scaled by h below
-            if (mass) fnorm = fmax(fnorm, fabs(F) * w);
-        }
-        __syncwarp();
+    for (int idx = lane; idx < N; idx += 32) {
+        const int i = idx / NB, r = idx - i * NB;
+        const bool mass = r < S && i < n - 1;
+        const double F = mass ? row_residual<NB>(ws, ws.y, i, r) : 0.0;
+        const double yv = ws.y[idx];
+        const double w = 1.0 / (rtol * fabs(yv) + atol);
+        ws.ewt[idx] = w;
+        ws.zn[idx] = yv;
+        ws.zn[(size_t)N + idx] = F;                       // scaled by h below
+        if (mass) fnorm = fmax(fnorm, fabs(F) * w);
     }
+    __syncwarp();
     fnorm = warp_max(fnorm);
 
     Bdf<NB> B;
@@ -323,8 +321,14 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
     for (int idx = lane; idx < N; idx += 32) ws.zn[(size_t)N + idx] *= h0;
     __syncwarp();
 
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // factor, residual, forward, backward, norms, history, correction, other
+    const bool prof_on = P.prof != nullptr;
+#define CATINT_TIC long long tic_ = prof_on ? clock64() : 0
+#define CATINT_TOC(k_) if (prof_on) pc[k_] += clock64() - tic_
     int status = CATINT_PNP_CELL_CONVERGED;
-    int nni = 0, iout = 0;
+    int nni = 0, iout = 0, nsetups = 0, nstlp = 0;
+    bool have_factors = false, force_setup = false;
+    double inv_gamma_p = 1.0;
     // pending transformation of the history array for the next attempt
     int pend_dq = 0; bool pend_undo = false; double pend_eta = 1.0;
     double lc[QMAX + 2]; double A1c = 0.0;
@@ -347,28 +351,61 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
             B.t = saved_t + B.h;
             set_bdf<NB>(B);
             const double rl1 = 1.0 / B.l[1];
-            history_pass<NB>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+            { CATINT_TIC; history_pass<NB>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true); CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
 
-            // ---- Newton corrector --------------------------------------------
+            // ---- modified Newton corrector (VODE/CVODE factor re-use) ---------------
+            // re-factor on the first step, after a failed attempt, every MSBP steps, or when
+            // gamma drifted by more than DGMAX since the factors were computed
             bool conv = false;
-            double crate = 1.0, delp = 0.0, acnrm = 0.0;
-            for (int m = 0; m < MAXCOR; ++m) {
-                const bool ok = forward_sweep<NB>(ws, inv_gamma);
-                ++nni;
-                if (!ok) break;
-                double del, acn;
-                backward_sweep<NB>(ws, del, acn, 0, 0.0, 0.0);
-                if (!(del <= 1e300)) break;
-                if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
-                const double dcon = del * fmin(1.0, crate) / B.tq[4];
-                if (dcon <= 1.0) { conv = true; acnrm = (m == 0) ? del : acn; break; }
-                if (m + 1 == MAXCOR || (m >= 1 && del > RDIV * delp)) break;
-                delp = del;
+            double acnrm = 0.0;
+            bool call_setup = !have_factors || force_setup || B.nst >= nstlp + MSBP ||
+                              fabs(inv_gamma_p / inv_gamma - 1.0) > DGMAX;
+            force_setup = false;
+            for (int pass = 0; pass < 2 && !conv; ++pass) {
+                bool jcur = false;
+                if (pass == 1) {
+                    // stale factors did not converge: restart the corrector from the prediction
+                    for (int idx = lane; idx < N; idx += 32) ws.y[idx] = ws.zn[idx];
+                    __syncwarp();
+                    call_setup = true;
+                }
+                if (call_setup) {
+                    CATINT_TIC;
+                    const bool ok = factor_sweep<NB>(ws, inv_gamma);
+                    CATINT_TOC(0);
+                    ++nsetups;
+                    have_factors = ok;
+                    inv_gamma_p = inv_gamma;
+                    nstlp = B.nst;
+                    jcur = true;
+                    if (!ok) break;
+                }
+                const double gamrat = inv_gamma_p / inv_gamma;          // gamma/gamma_p
+                const double dscale = (gamrat != 1.0) ? 2.0 * gamrat / (1.0 + gamrat) : 1.0;
+                double crate = 1.0, delp = 0.0;
+                bool bad = false;
+                for (int m = 0; m < MAXCOR; ++m) {
+                    { CATINT_TIC; residual_pass<NB>(ws, inv_gamma); CATINT_TOC(1); }
+                    { CATINT_TIC; forward_solve<NB>(ws); CATINT_TOC(2); }
+                    { CATINT_TIC; backward_solve<NB>(ws, dscale); CATINT_TOC(3); }
+                    double del, acn;
+                    { CATINT_TIC; newton_norms<NB>(ws, dscale, m > 0, del, acn, 0, 0.0, 0.0); CATINT_TOC(4); }
+                    ++nni;
+                    if (!(del <= 1e300)) { bad = true; break; }
+                    if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
+                    const double dcon = del * fmin(1.0, crate) / B.tq[4];
+                    if (dcon <= 1.0) { conv = true; acnrm = (m == 0) ? del : acn; break; }
+                    if (m + 1 == MAXCOR || (m >= 1 && del > RDIV * delp)) break;
+                    delp = del;
+                }
+                (void)bad;
+                if (jcur) break;            // fresh factors: a failure is a real failure
             }
             if (!conv) {
                 ++ncf;
+                force_setup = true;
                 B.etamax = 1.0;
                 B.t = saved_t;
                 if (ncf == MXNCF || B.h * ETACF < 1e-300) { status = CATINT_PNP_CELL_CORRECTOR_FAILED; break; }
@@ -379,6 +416,7 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
             if (dsm <= 1.0) { accepted = true; break; }
             // ---- error test failed ---------------------------------------------
             ++nef;
+            force_setup = true;
             B.etamax = 1.0;
             B.t = saved_t;
             if (nef == MXNEF) { status = CATINT_PNP_CELL_ERROR_TEST_FAILED; break; }
@@ -399,14 +437,12 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
                 B.qwait = LONG_WAIT;
                 for (int idx = lane; idx < N; idx += 32) ws.y[idx] = ws.zn[idx];
                 __syncwarp();
-                for (int i = 0; i < n; ++i) {
-                    const double F = node_rows<NB>(ws, ws.y, i, sl, sa, sud, sua, sf);
-                    if (lane < NB) {
-                        const bool mass = lane < S && i < n - 1;
-                        ws.zn[(size_t)N + (size_t)i * NB + lane] = mass ? B.h * F : 0.0;
-                    }
-                    __syncwarp();
+                for (int idx = lane; idx < N; idx += 32) {
+                    const int i = idx / NB, r = idx - i * NB;
+                    const bool mass = r < S && i < n - 1;
+                    ws.zn[(size_t)N + idx] = mass ? B.h * row_residual<NB>(ws, ws.y, i, r) : 0.0;
                 }
+                __syncwarp();
             }
         }
         if (!accepted) break;
@@ -424,6 +460,7 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
         double cquot = 0.0;
         if (want_up) cquot = (B.tq[5] / B.saved_tq5) * pow(B.h / B.tau[2], (double)(q + 1));
         double ddn = 0.0, dup = 0.0;
+        const long long tic_corr = prof_on ? clock64() : 0;
         // correction pass: zn[j] += l[j]*acor, norms for the order selection, new weights
         for (int idx = lane; idx < N; idx += 32) {
             const int i = idx / NB, r = idx - i * NB;
@@ -446,6 +483,7 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
             ws.ewt[idx] = 1.0 / (rtol * fabs(yv) + atol);
         }
         __syncwarp();
+        if (prof_on) pc[6] += clock64() - tic_corr;
         if (save_acor) B.saved_tq5 = B.tq[5];
 
         // ------------------------------------------------ next order and step size
@@ -508,12 +546,16 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
         const double patol = 1e-12 * fmax(cscale, 1e-300);
         bool done = false;
         for (int it = 0; it < P.polish_max_iter && !done; ++it) {
-            // psi = -y makes the mass term vanish together with inv_gamma = 0
-            const bool ok = forward_sweep<NB>(ws, 0.0);
-            ++nni;
+            // true Newton on the steady residual: inv_gamma = 0 removes the mass term
+            const bool ok = factor_sweep<NB>(ws, 0.0);
+            ++nsetups;
             if (!ok) break;
+            residual_pass<NB>(ws, 0.0);
+            forward_solve<NB>(ws);
+            backward_solve<NB>(ws, 1.0);
             double del, acn;
-            backward_sweep<NB>(ws, del, acn, 1, P.polish_rtol, patol);
+            newton_norms<NB>(ws, 1.0, false, del, acn, 1, P.polish_rtol, patol);
+            ++nni;
             if (!(del <= 1e300)) break;
             if (del <= 1.0) done = true;
         }
@@ -562,6 +604,11 @@ __global__ void __launch_bounds__(128) pnp_bdf_kernel(SolveParams P) {
             P.status[cell] = status;
             P.n_steps[cell] = B.nst;
             P.n_newton[cell] = nni;
+            if (P.n_setups) P.n_setups[cell] = nsetups;
+            if (prof_on) {
+                pc[7] = clock64() - t_kernel0;
+                for (int k_ = 0; k_ < 8; ++k_) P.prof[cell * 8 + k_] = pc[k_];
+            }
         }
     }
 }
@@ -603,14 +650,14 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
     const int n = ws.cs.n, nxm = P.tb.nx_max;
     const double* y = P.y + (size_t)cell * nxm * NB;
-    double* sl = ws.scratch + 2 * (NB + 1);
-    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB; double* sf = sua + NB;
+    double* sl = ws.scratch + 2 * (NB + 2);
+    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
     for (int i = 0; i < n; ++i) {
         __syncwarp();
-        const double F = node_rows<NB>(ws, y, i, sl, sa, sud, sua, sf);
+        node_coeffs<NB>(ws, y, i, sl, sa, sud, sua);
         __syncwarp();
         const size_t nb = ((size_t)cell * nxm + i);
-        if (P.F && lane < NB) P.F[nb * NB + lane] = F;
+        if (P.F && lane < NB) P.F[nb * NB + lane] = row_residual<NB>(ws, y, i, lane);
         // blocks are d(row)/d(col) of F itself (not of the Newton matrix)
         if (lane < NB) {
             const int j = lane;     // column
@@ -672,20 +719,23 @@ template <int NB>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
     const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)(2 * (NB + 1) + 6 * NB) * sizeof(double);
+    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
     const size_t state = (size_t)3 * P.tb.nx_max * NB * sizeof(double);
     int dev = 0; cudaGetDevice(&dev);
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    size_t smem = base + WARPS * (per_warp_fixed + state);
-    P.state_in_smem = 1;
-    // keep two blocks per SM when the state lives in shared memory
-    if (smem > (size_t)max_optin / 2) {
-        if (smem > (size_t)max_optin) { P.state_in_smem = 0; smem = base + WARPS * per_warp_fixed; }
-    }
-    cudaFuncSetAttribute(pnp_bdf_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_state = base + WARPS * (per_warp_fixed + state);
     const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
-    pnp_bdf_kernel<NB><<<grid, WARPS * 32, smem, st>>>(P);
+    if (smem_state <= (size_t)max_optin) {
+        P.state_in_smem = 1;
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
+        pnp_bdf_kernel<NB, true><<<grid, WARPS * 32, smem_state, st>>>(P);
+    } else {
+        P.state_in_smem = 0;
+        const size_t smem = base + WARPS * per_warp_fixed;
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pnp_bdf_kernel<NB, false><<<grid, WARPS * 32, smem, st>>>(P);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 
@@ -693,7 +743,7 @@ template <int NB>
 int launch_jac(JacParams& P, cudaStream_t st) {
     const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)(2 * (NB + 1) + 6 * NB) * sizeof(double);
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
     const size_t smem = base + WARPS * per_warp;
     const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
     pnp_jacobian_kernel<NB><<<grid, WARPS * 32, smem, st>>>(P);

@@ -1,67 +1,40 @@
-// pnp_solver.cuh -- fused per-cell implicit integrator (K2+K3 inside a BDF/Newton loop).
+// pnp_solver.cuh -- per-cell linear algebra of the implicit integrator (K2+K3 building blocks).
 //
-// One warp integrates one cell from t=0 to t_end: variable-order (1..5),
-// variable-step BDF in Nordsieck form with LSODA/CVODE-style step and order
-// control (weighted max norm over the concentrations, rtol/atol as passed to
-// scipy odeint at /root/reference/catint/calculator_old.py:947), Newton corrector
-// with the analytic block-tridiagonal Jacobian, block-Thomas solve with partial
-// pivoting inside the NBxNB blocks.  No tensor cores: the blocks are 9..13 wide
-// and the chain over nodes is sequential.
+// One warp owns one cell.  The Newton matrix  A = Mass/gamma - dF/dy  is block
+// tridiagonal (+ one wall block); it is FACTORED by a block-Thomas sweep with
+// partial pivoting inside the NB x NB blocks and the factors are kept in global
+// memory (L2) so that the modified-Newton iterations of the following steps only
+// run the cheap SOLVE sweeps (VODE/CVODE re-use policy):
 //
-// Lane mapping of the forward (elimination) sweep: the augmented block row
-// [A_D | A_U | rhs] has 2*NB+1 columns; lane j owns column j (NB registers).
-// Gauss-Jordan with row pivoting turns it into [I | W_i | z_i]; W_i goes to
-// global memory for the backward sweep, its columns are handed to the A_D lanes
-// of the next node by warp shuffles for the Schur update A_D' = A_D - A_L*W.
-// A_L and A_U are diagonal + one column (g) (+ one g-row entry), which keeps the
-// Schur update at O(NB) per lane.
-// Backward sweep: lane r owns row r:  d_i[r] = z_i[r] - sum_j W_i[r][j]*d_{i+1}[j].
+//   factor_sweep   lane j owns one column of the augmented block row
+//                  [A_D' | I | u_g]  (2*NB+1 <= 32 columns, NB registers per lane);
+//                  Gauss-Jordan with row pivoting turns it into [I | inv_i | W_i[:,g]];
+//                  inv_i = A_D'^{-1}, W_i = inv_i*A_U (A_U = diag + one column (g)),
+//                  both go to global memory; W columns are handed to the A_D lanes of
+//                  the next node by warp shuffles for the Schur update A_D' = A_D - A_L*W.
+//   residual_pass  lane per node: rhs = F(y) - Mass*(y+psi)/gamma  (K1 arithmetic on the
+//                  shared-memory state)
+//   forward_solve  lane r owns row r:  z_i = inv_i*(rhs_i - A_L z_{i-1})
+//   backward_sweep lane r owns row r:  d_i = z_i - W_i d_{i+1};  y += d; weighted max norms
+//
+// No tensor cores: the blocks are 9..13 wide and the chain over nodes is sequential.
 #pragma once
 #include "pnp_device.cuh"
 
 namespace catint {
 
-constexpr int QMAX = 5;
-constexpr int LMAX = QMAX + 1;     // Nordsieck vectors zn[0..QMAX]
-constexpr unsigned FULL = 0xffffffffu;
-
-// integrator constants (VODE/CVODE family)
-constexpr double ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
-constexpr double ETAMX1 = 1e4, ETAMX2 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1, ETACF = 0.25, THRESH = 1.5;
-constexpr int MXNCF = 10, MXNEF = 7, MXNEF1 = 3, SMALL_NEF = 2, LONG_WAIT = 10;
-constexpr int MAXCOR = 3;
-constexpr double CRDOWN = 0.3, RDIV = 2.0, NLSCOEF = 0.1;
-
-struct SolveParams {
-    DevTables tb;
-    // per-cell inputs
-    const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
-    const double* y0;          // optional [B][nx_max][S]
-    long long n_cells;
-    // control
-    int mode, max_steps, n_out, polish_max_iter;
-    double rtol, atol, h0, polish_rtol;
-    const double* t_out;       // device [n_out]
-    // outputs
-    double* c_out; double* phi_out; double* g_out; double* flux_out;
-    int* status; int* n_steps; int* n_newton;
-    // workspace (global): per cell  zn[LMAX][N], ewt[N], W[nx_max][NB][NB], V0[NB][NB] (+ y,psi,zb if not in smem)
-    double* ws; long long ws_stride;   // doubles per cell
-    int state_in_smem;
-};
-
-// ---------------------------------------------------------------------------
 template <int NB>
 struct WarpState {
-    // pointers (shared or global)
-    double* y;      // current Newton iterate              [n*NB]
+    double* y;      // current Newton iterate              [n*NB]   (shared or global)
     double* psi;    // rl1*zn1 - zn0 (mass rows)           [n*NB]
     double* zb;     // rhs -> z -> delta                   [n*NB]
-    double* zn;     // Nordsieck array                     [LMAX][N]
+    double* zn;     // Nordsieck array                     [LMAX][N] (global)
     double* ewt;    // error weights                       [N]
-    double* W;      // [n][NB][NB]
-    double* V0;     // [NB][NB]
-    double* scratch;            // shared, per warp: 2*(NB+1) + 6*NB doubles
+    double* inv;    // A_D'^{-1}, rows padded to NBP       [n][NB][NBP]
+    double* W1;     // inv_1*A_U1' (dense because of the wall block)   [NB][NBP]
+    double* V0;     // inv_0*A_E                           [NB][NBP]
+    double* la;     // per row: l, a (A_L), ud, ua (A_U, g-row scaled)  [n][NB][4]
+    double* scratch;            // shared, per warp
     const CellSpecies* sp;      // shared, per warp
     const DevTables* tb;        // shared, per block
     CellScalars cs;
@@ -70,26 +43,36 @@ struct WarpState {
 };
 
 template <int NB>
-__device__ __forceinline__ int scratch_doubles() { return 2 * (NB + 1) + 6 * NB; }
+__host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }
+// sub-arrays of the per-cell workspace start on 32-byte boundaries
+__host__ __device__ constexpr size_t align4(size_t doubles) { return (doubles + 3) & ~size_t(3); }
+// padded row length of the stored blocks (even -> 16-byte aligned rows, double2 loads)
+template <int NB>
+__host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 
 // ---------------------------------------------------------------------------
-// Gauss-Jordan elimination with partial (row) pivoting, lane j owns column j of
-// the NB x (2*NB+1) augmented block.  On exit columns NB..2NB hold
-// A_D^{-1}*[A_U | rhs].  Returns false on a zero/non-finite pivot.
+// Gauss-Jordan elimination with threshold partial pivoting; lane j owns column j
+// (columns >= NB are right-hand sides).  The pivot column travels through shared
+// memory (one writer, broadcast reads).  A row swap is a warp-uniform branch, so
+// it only costs when it happens.  Returns false on a zero/non-finite pivot.
 template <int NB>
 __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* pivbuf) {
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-        double* buf = pivbuf + (k & 1) * (NB + 1);
+        double* buf = pivbuf + (k & 1) * (NB + 2);
         if (lane == k) {
-            double best = fabs(A[k]);
-            int p = k;
+            // magnitude keys: high word of |a| with the row index in the low 4 bits
+            int best = ((__double2hiint(A[k]) & 0x7fffffff) & ~0xf) | k;
+            const int diag = best;
 #pragma unroll
             for (int r = k + 1; r < NB; ++r) {
-                const double v = fabs(A[r]);
-                if (v > best) { best = v; p = r; }
+                const int key = ((__double2hiint(A[r]) & 0x7fffffff) & ~0xf) | r;
+                best = max(best, key);
             }
+            // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
+            int p = best & 0xf;
+            if (diag + (3 << 20) >= best) p = k;
 #pragma unroll
             for (int r = 0; r < NB; ++r) buf[r] = A[r];
             buf[NB] = (double)p;
@@ -99,18 +82,21 @@ __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* 
         double col[NB];
 #pragma unroll
         for (int r = 0; r < NB; ++r) col[r] = buf[r];
-        // swap rows k and p (p >= k)
-        double ck = col[k], ak = A[k];
+        if (p != k) {           // warp-uniform
+            double ck = col[k], ak = A[k];
 #pragma unroll
-        for (int r = k + 1; r < NB; ++r) {
-            if (r == p) {
-                double t = col[r]; col[r] = ck; ck = t;
-                t = A[r]; A[r] = ak; ak = t;
+            for (int r = k + 1; r < NB; ++r) {
+                if (r == p) {
+                    double t = col[r]; col[r] = ck; ck = t;
+                    t = A[r]; A[r] = ak; ak = t;
+                }
             }
+            col[k] = ck; A[k] = ak;
         }
-        const double inv = 1.0 / ck;
+        const double ck = col[k];
+        const double inv = __drcp_rn(ck);
         ok = ok && (ck != 0.0) && (fabs(inv) < 1e300);
-        ak *= inv;
+        const double ak = A[k] * inv;
         A[k] = ak;
 #pragma unroll
         for (int r = 0; r < NB; ++r)
@@ -120,303 +106,490 @@ __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* 
 }
 
 // ---------------------------------------------------------------------------
-// Row quantities of node i, computed by lane r (< NB); everything the column
-// assembly needs is published through the per-warp scratch:
-//   sl[r], sa[r]   A_L: diagonal and g-column entries of row r
-//   sud[r], sua[r] A_U: diagonal and g-column entries of row r
-//   sf[r]          residual F_r (transport rows: dc/dt; algebraic rows: -constraint)
-// Returns F_r for lane r (0 for other lanes).
+// residual of row r at node i:  transport rows dc/dt, algebraic rows -constraint
+// (the g-row of interior nodes is returned UNSCALED)
 template <int NB>
-__device__ __forceinline__ double node_rows(const WarpState<NB>& ws, const double* y, int i,
-                                            double* sl, double* sa, double* sud, double* sua, double* sf) {
+__device__ __forceinline__ double row_residual(const WarpState<NB>& ws, const double* y, int i, int r) {
+    constexpr int S = NB - 1;
+    const int n = ws.cs.n;
+    const DevTables& tb = *ws.tb;
+    const double* y0 = y + (size_t)i * NB;
+    if (i == 0) {
+        const WallCoef w = wall_coef(ws.cs);
+        const double* y1 = y + NB;
+        const double* y2 = y + 2 * NB;
+        if (r < S)
+            return (ws.sp->D[r] * ((y2[r] - y0[r]) * w.w0 + ws.sp->bq[r] * y1[r] * y1[S]) + ws.sp->J[r]) * w.ih0;
+        return tb.use_migration ? -(y0[S] - y1[S] - (y1[S] - y2[S]) * w.ext) : -y0[S];
+    }
+    if (i == n - 1) {
+        if (r < S) return ws.sp->cb[r] - y0[r];
+        return (tb.use_migration ? ws.cs.g_bulk : 0.0) - y0[S];
+    }
+    const NodeCoef k = interior_coef(ws.cs, i);
+    const double* ym = y0 - NB;
+    const double* yp = y0 + NB;
+    if (r < S) {
+        double R = 0.0;
+        for (int rr = 0; rr < tb.R; ++rr) {
+            const double nu = tb.nu[rr][r];
+            if (nu != 0.0) R += nu * net_rate(tb, rr, y0);
+        }
+        const double cm = ym[r], c0 = y0[r], cp = yp[r];
+        return ws.sp->D[r] * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp
+                              + ws.sp->bq[r] * k.ac * (cp * yp[S] - cm * ym[S])) + R;
+    }
+    if (!tb.use_migration) return -y0[S];
+    double rho = 0.0;
+    for (int s = 0; s < S; ++s) rho += ws.sp->qe[s] * y0[s];
+    return -(y0[S] - yp[S] - rho * k.hi);
+}
+
+// Jacobian coefficients of row r (= lane) at node i, published through shared memory:
+//   interior: sl,sa = dF_r/dc_{r,i-1}, dF_r/dg_{i-1};  sud,sua = dF_r/dc_{r,i+1}, dF_r/dg_{i+1}
+//   wall:     sa = dF_r/dy_{r,0} (diagonal), sud,sua w.r.t. node 1, sl = dF_r/dy_{r,2} (extra block)
+template <int NB>
+__device__ __forceinline__ void node_coeffs(const WarpState<NB>& ws, const double* y, int i,
+                                            double* sl, double* sa, double* sud, double* sua) {
     constexpr int S = NB - 1;
     const int r = ws.lane;
     const int n = ws.cs.n;
-    const DevTables& tb = *ws.tb;
-    double F = 0.0, l = 0.0, a = 0.0, ud = 0.0, ua = 0.0;
-    if (r < NB) {
-        const double* y0 = y + (size_t)i * NB;
-        if (i == 0) {
-            const WallCoef w = wall_coef(ws.cs);
-            const double* y1 = y + NB;
-            const double* y2 = y + 2 * NB;
-            if (r < S) {
-                const double Dr = ws.sp->D[r], bq = tb.use_migration ? ws.sp->bq[r] : 0.0;
-                const double g1 = y1[S];
-                F = (Dr * ((y2[r] - y0[r]) * w.w0 + bq * y1[r] * g1) + ws.sp->J[r]) * w.ih0;
-                ud = Dr * bq * g1 * w.ih0;         // dF/dc_{r,1}
-                ua = Dr * bq * y1[r] * w.ih0;      // dF/dg_1
-                l = Dr * w.w0 * w.ih0;             // dF/dc_{r,2}   (extra wall block, diagonal)
-                a = -Dr * w.w0 * w.ih0;            // dF/dc_{r,0}   (A_D diagonal, without mass)
-            } else {   // g row: g_0 - g_1 - (g_1-g_2)*ext = 0
-                if (tb.use_migration) {
-                    F = -(y0[S] - y1[S] - (y1[S] - y2[S]) * w.ext);
-                    ud = 1.0 + w.ext;              // dF/dg_1
-                    l = -w.ext;                    // dF/dg_2
-                } else {
-                    F = -y0[S];
-                }
-                a = -1.0;                          // dF/dg_0
-            }
-        } else if (i == n - 1) {
-            if (r < S) F = ws.sp->cb[r] - y0[r];
-            else F = (tb.use_migration ? ws.cs.g_bulk : 0.0) - y0[S];
+    const bool mig = ws.tb->use_migration;
+    if (r >= NB) return;
+    double l = 0.0, a = 0.0, ud = 0.0, ua = 0.0;
+    const double* y0 = y + (size_t)i * NB;
+    if (i == 0) {
+        const WallCoef w = wall_coef(ws.cs);
+        const double* y1 = y + NB;
+        if (r < S) {
+            const double Dr = ws.sp->D[r], bq = ws.sp->bq[r];
+            ud = Dr * bq * y1[S] * w.ih0;
+            ua = Dr * bq * y1[r] * w.ih0;
+            l = Dr * w.w0 * w.ih0;
+            a = -l;
         } else {
-            const NodeCoef k = interior_coef(ws.cs, i);
+            if (mig) { ud = 1.0 + w.ext; l = -w.ext; }
+            a = -1.0;
+        }
+    } else if (i < n - 1) {
+        const NodeCoef k = interior_coef(ws.cs, i);
+        if (r < S) {
+            const double Dr = ws.sp->D[r], bq = ws.sp->bq[r];
             const double* ym = y0 - NB;
             const double* yp = y0 + NB;
-            if (r < S) {
-                const double Dr = ws.sp->D[r], bq = tb.use_migration ? ws.sp->bq[r] : 0.0;
-                const double cm = ym[r], c0 = y0[r], cp = yp[r], gm = ym[S], gp = yp[S];
-                const double R = tb.R ? reaction_source(tb, r, y0) : 0.0;
-                F = Dr * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp + bq * k.ac * (cp * gp - cm * gm)) + R;
-                l = Dr * (k.am - bq * k.ac * gm);      // dF/dc_{r,i-1}
-                a = -Dr * bq * k.ac * cm;              // dF/dg_{i-1}
-                ud = Dr * (k.ap + bq * k.ac * gp);     // dF/dc_{r,i+1}
-                ua = Dr * bq * k.ac * cp;              // dF/dg_{i+1}
-            } else {   // g row: g_i - g_{i+1} - rho_i*h_i = 0, rho = sum q c / eps
-                if (tb.use_migration) {
-                    double rho = 0.0;
-                    for (int s = 0; s < S; ++s) rho += ws.sp->q[s] * y0[s];
-                    rho /= ws.cs.eps;
-                    F = -(y0[S] - yp[S] - rho * k.hi);
-                    ud = 1.0;                          // dF/dg_{i+1}
-                } else {
-                    F = -y0[S];
-                }
-            }
+            l = Dr * (k.am - bq * k.ac * ym[S]);
+            a = -Dr * bq * k.ac * ym[r];
+            ud = Dr * (k.ap + bq * k.ac * yp[S]);
+            ua = Dr * bq * k.ac * yp[r];
+        } else if (mig) {
+            ud = 1.0;
         }
-        sl[r] = l; sa[r] = a; sud[r] = ud; sua[r] = ua; sf[r] = F;
     }
-    return F;
+    sl[r] = l; sa[r] = a; sud[r] = ud; sua[r] = ua;
+}
+
+// column j (< NB) of A_D = Mass*inv_gamma - dF_i/dy_i at an interior node, g-row scaled by sg
+template <int NB>
+__device__ __forceinline__ void interior_diag_column(const WarpState<NB>& ws, const double* yi, int j,
+                                                     const NodeCoef& k, double inv_gamma, double sg,
+                                                     double (&A)[NB]) {
+    constexpr int S = NB - 1;
+    const DevTables& tb = *ws.tb;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) A[r] = 0.0;
+    if (j < S) {
+        for (int t = tb.tbeg[j]; t < tb.tbeg[j + 1]; ++t) {
+            double v = tb.tcoef[t];
+            if (tb.ti1[t] >= 0) v *= yi[tb.ti1[t]];
+            if (tb.ti2[t] >= 0) v *= yi[tb.ti2[t]];
+            if (tb.ti3[t] >= 0) v *= yi[tb.ti3[t]];
+            const double* nur = tb.nu[tb.tr[t]];
+#pragma unroll
+            for (int r = 0; r < S; ++r) A[r] = fma(-nur[r], v, A[r]);
+        }
+        const double dd = inv_gamma + ws.sp->D[j] * (k.am + k.ap);
+#pragma unroll
+        for (int r = 0; r < S; ++r)
+            if (r == j) A[r] += dd;
+        if (tb.use_migration) A[S] = -tb.z[j];          // -(q_j*h/eps)*sg
+    } else {
+        A[S] = tb.use_migration ? sg : 1.0;
+    }
 }
 
 // ---------------------------------------------------------------------------
-// One Newton linear solve  (Mass*inv_gamma - dF/dy) * delta = F - Mass*(y+psi)*inv_gamma,
-// forward elimination part.  z_i -> zb, W_i -> global.  Returns false if a
-// block was singular.
+// Factorisation sweep.  Lanes: D = 0..NB-1 (columns of A_D'), I = NB..2NB-1 (identity ->
+// inverse), G = 2NB (g-column of A_U -> W[:,g]).  Stores inv_i (all nodes), the sparse
+// coefficients of A_L/A_U (la), V_0 and the dense W_1.
 template <int NB>
-__device__ bool forward_sweep(WarpState<NB>& ws, double inv_gamma) {
+__device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
     constexpr int S = NB - 1;
+    constexpr int NBP = padded<NB>();
     const int lane = ws.lane;
     const int n = ws.cs.n;
-    const DevTables& tb = *ws.tb;
+    const bool mig = ws.tb->use_migration;
     double* pivbuf = ws.scratch;
-    double* sl = ws.scratch + 2 * (NB + 1);
-    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB; double* sf = sua + NB;
-    const bool isD = lane < NB, isU = lane >= NB && lane < 2 * NB, isR = lane == 2 * NB;
-    const int j = isD ? lane : lane - NB;    // column index inside its block
+    double* sl = ws.scratch + 2 * (NB + 2);
+    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
+    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
+    const int j = isD ? lane : lane - NB;
+    // source lane of the W column that D-lane j needs for the next Schur update
+    const int wsrc = isD ? (j < S ? lane + NB : 2 * NB) : lane;
     double A[NB], Wp[NB];
 #pragma unroll
     for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
     bool ok = true;
     const double* y = ws.y;
 
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n - 1; ++i) {
         __syncwarp();
-        node_rows<NB>(ws, y, i, sl, sa, sud, sua, sf);
+        node_coeffs<NB>(ws, y, i, sl, sa, sud, sua);
         __syncwarp();
         const double* yi = y + (size_t)i * NB;
-        const bool mass_node = i < n - 1;
+        double* invcol = ws.inv + (size_t)i * NB * NBP + j;      // column j of inv_i (I lanes)
+        const NodeCoef k = (i > 0) ? interior_coef(ws.cs, i) : NodeCoef{0, 0, 0, 1, 1};
+        const double sg = (i > 0 && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
+        if (lane < NB) {
+            double4 v;
+            v.x = sl[lane]; v.y = sa[lane];
+            v.z = (lane == S) ? sud[lane] * sg : sud[lane];
+            v.w = sua[lane];
+            reinterpret_cast<double4*>(ws.la)[(size_t)i * NB + lane] = v;
+        }
 #pragma unroll
         for (int r = 0; r < NB; ++r) A[r] = 0.0;
 
         if (i == 0) {
-            // ---- wall node: [A_D0 | A_U0 | r0] then [A_D0 | A_E0 | 0] ----
-            for (int pass = 0; pass < 2; ++pass) {
+            // A_D0 is diag(mass*inv_gamma - sa); A_U0 = diag(-sud) + g-column(-sua); A_E = diag(-sl)
+            if (isD || isI) {
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = 0.0;
-                if (isD) {
+                for (int r = 0; r < NB; ++r)
+                    if (r == j) A[r] = isD ? ((j < S ? inv_gamma : 0.0) - sa[r]) : 1.0;
+            } else if (isG) {
 #pragma unroll
-                    for (int r = 0; r < NB; ++r)
-                        if (r == j) A[r] = (j < S ? inv_gamma : 0.0) - sa[r];
-                } else if (isU) {
-                    if (pass == 0) {
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r];
+            }
+            ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
+            double Wc[NB];
 #pragma unroll
-                        for (int r = 0; r < NB; ++r) {
-                            if (r == j) A[r] = -sud[r];
-                            if (j == S && r < S) A[r] = -sua[r];
-                        }
-                    } else {
+            for (int r = 0; r < NB; ++r) Wc[r] = A[r];
+            if (isI) {
+                const double ud = -sud[j], ae = -sl[j];
+                double* v0col = ws.V0 + j;
 #pragma unroll
-                        for (int r = 0; r < NB; ++r)
-                            if (r == j) A[r] = -sl[r];
-                    }
-                } else if (isR && pass == 0) {
-#pragma unroll
-                    for (int r = 0; r < NB; ++r)
-                        A[r] = sf[r] - (r < S ? (yi[r] + ws.psi[r]) * inv_gamma : 0.0);
+                for (int r = 0; r < NB; ++r) {
+                    invcol[r * NBP] = A[r];
+                    v0col[r * NBP] = A[r] * ae;
+                    if (j < S) Wc[r] = A[r] * ud;
                 }
-                ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
-                if (pass == 0) {
-                    if (isU) {
+            }
 #pragma unroll
-                        for (int r = 0; r < NB; ++r) ws.W[(size_t)r * NB + j] = A[r];
-                    }
-                    if (isR) {
+            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
+            // the I lanes keep V_0 columns for the modified A_U of node 1
+            if (isI) {
+                const double ae = -sl[j];
 #pragma unroll
-                        for (int r = 0; r < NB; ++r) ws.zb[r] = A[r];
-                    }
-                    // hand W_0 columns to the A_D lanes, keep z_0 in the rhs lane
-                    const int src = isD ? lane + NB : lane;
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, A[r], src);
-                } else if (isU) {
-                    // V_0 = A_D0^{-1} A_E0 stays in the A_U lanes for node 1
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) { ws.V0[(size_t)r * NB + j] = A[r]; Wp[r] = A[r]; }
-                }
-                __syncwarp();
+                for (int r = 0; r < NB; ++r) Wp[r] = A[r] * ae;
             }
             continue;
         }
 
-        // ---- assemble column j of [A_D | A_U | rhs] ----
-        if (i == n - 1) {
-            if (isD) {
+        // ---- interior node: column j of [A_D' | I | u_g] ----
+        double Dsave[NB];
+        if (isD) {
+            interior_diag_column<NB>(ws, yi, j, k, inv_gamma, sg, A);
+            const double wg = Wp[S];
 #pragma unroll
-                for (int r = 0; r < NB; ++r) if (r == j) A[r] = 1.0;
-            } else if (isR) {
+            for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;     // A_D - A_L*W_{i-1}
+            if (i == 1) {
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = sf[r];
+                for (int r = 0; r < NB; ++r) Dsave[r] = A[r];
             }
-        } else {
+        } else if (isI) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r)
+                if (r == j) A[r] = 1.0;
+        } else if (isG) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r] * sg;
+        }
+        ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
+        double Wc[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) Wc[r] = A[r];
+        if (isI) {
+            const double ud = -sud[j];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                invcol[r * NBP] = A[r];
+                if (j < S) Wc[r] = A[r] * ud;
+            }
+        }
+        if (i == 1) {
+            // A_U of node 1 is modified by the wall block: A_U1' = A_U1 - A_L1*V_0 (dense in
+            // general), so W_1 = inv_1*A_U1' comes from a second elimination [A_D1' | A_U1']
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < NB; ++r) A[r] = 0.0;
             if (isD) {
-                if (j < S) {
-                    const NodeCoef k = interior_coef(ws.cs, i);
-                    const double Dj = ws.sp->D[j];
-                    // reaction Jacobian column: -dR_k/dc_j
-                    for (int t = tb.tbeg[j]; t < tb.tbeg[j + 1]; ++t) {
-                        double v = tb.tcoef[t];
-                        if (tb.ti1[t] >= 0) v *= yi[tb.ti1[t]];
-                        if (tb.ti2[t] >= 0) v *= yi[tb.ti2[t]];
-                        if (tb.ti3[t] >= 0) v *= yi[tb.ti3[t]];
-                        const double* nur = tb.nu[tb.tr[t]];
 #pragma unroll
-                        for (int r = 0; r < S; ++r) A[r] = fma(-nur[r], v, A[r]);
-                    }
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) {
-                        if (r == j) A[r] += inv_gamma + Dj * (k.am + k.ap);
-                    }
-                    if (tb.use_migration) A[S] = -(ws.sp->q[j] / ws.cs.eps) * k.hi;
-                } else {
-                    A[S] = 1.0;
-                }
-            } else if (isU) {
+                for (int r = 0; r < NB; ++r) A[r] = Dsave[r];
+            } else if (isI) {
+                const double vg = Wp[S];
 #pragma unroll
                 for (int r = 0; r < NB; ++r) {
-                    if (r == j) A[r] = -sud[r];
-                    if (j == S && r < S) A[r] = -sua[r];
+                    double v = 0.0;
+                    if (r == j) v = (r < S) ? -sud[r] : -sud[r] * sg;
+                    if (j == S && r < S) v = -sua[r];
+                    if (r < S) v += sl[r] * Wp[r] + sa[r] * vg;
+                    A[r] = v;
                 }
-            } else if (isR) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r)
-                    A[r] = sf[r] - (r < S ? (yi[r] + ws.psi[(size_t)i * NB + r]) * inv_gamma : 0.0);
             }
-            // ---- Schur update with the previous node: A -= A_L * Wp,  A_L = -dF/dy_{i-1} ----
-            if (isD || isR || (isU && i == 1)) {
-                const double wg = Wp[S];
+            ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
 #pragma unroll
-                for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;
+            for (int r = 0; r < NB; ++r) Wc[r] = A[r];
+            if (isI) {
+                double* w1col = ws.W1 + j;
+#pragma unroll
+                for (int r = 0; r < NB; ++r) w1col[r * NBP] = A[r];
             }
-        }
-        (void)mass_node;
-        ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
-        if (isU) {
-            double* Wi = ws.W + (size_t)i * NB * NB;
+            const int src1 = isD ? lane + NB : lane;
 #pragma unroll
-            for (int r = 0; r < NB; ++r) Wi[(size_t)r * NB + j] = A[r];
+            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], src1);
+            continue;
         }
-        if (isR) {
 #pragma unroll
-            for (int r = 0; r < NB; ++r) ws.zb[(size_t)i * NB + r] = A[r];
-        }
-        const int src = isD ? lane + NB : lane;
-#pragma unroll
-        for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, A[r], src);
+        for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
+    }
+    // bulk node: identity rows, no coupling
+    {
+        const int i = n - 1;
+        for (int e = lane; e < NB * NBP; e += 32)
+            ws.inv[(size_t)i * NB * NBP + e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
+        if (lane < NB) reinterpret_cast<double4*>(ws.la)[(size_t)i * NB + lane] = make_double4(0, 0, 0, 0);
     }
     __syncwarp();
     return __all_sync(FULL, ok);
 }
 
 // ---------------------------------------------------------------------------
-// Backward substitution; y += delta, zb <- delta.  Returns the weighted max
-// norms  |delta|*w  and  |y-zn0|*w  over the error-controlled unknowns
-// (concentrations of nodes 0..n-2).  wmode 0: weights from ws.ewt;
-// wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
+// rhs = F(y) - Mass*(y+psi)*inv_gamma for every unknown; one lane per node.
+// The g-row of interior nodes carries the same scale as in factor_sweep.
 template <int NB>
-__device__ void backward_sweep(WarpState<NB>& ws, double& dnorm, double& anorm, int wmode,
-                               double prtol, double patol) {
+__device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
+    constexpr int S = NB - 1;
+    const int n = ws.cs.n;
+    const DevTables& tb = *ws.tb;
+    const double* y = ws.y;
+    for (int i = ws.lane; i < n; i += 32) {
+        const double* y0 = y + (size_t)i * NB;
+        double* out = ws.zb + (size_t)i * NB;
+        if (i == 0 || i == n - 1) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                double v = row_residual<NB>(ws, y, i, r);
+                if (i == 0 && r < S) v -= (y0[r] + ws.psi[r]) * inv_gamma;
+                out[r] = v;
+            }
+            continue;
+        }
+        const NodeCoef k = interior_coef(ws.cs, i);
+        const double* ym = y0 - NB;
+        const double* yp = y0 + NB;
+        const double gm = ym[S], gp = yp[S];
+        double F[S];
+        double rho = 0.0;
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            const double cm = ym[r], c0 = y0[r], cp = yp[r];
+            F[r] = ws.sp->D[r] * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp
+                                  + ws.sp->bq[r] * k.ac * (cp * gp - cm * gm))
+                   - (c0 + ws.psi[(size_t)i * NB + r]) * inv_gamma;
+            rho = fma(ws.sp->qe[r], c0, rho);
+        }
+        for (int rr = 0; rr < tb.R; ++rr) {
+            const double net = net_rate(tb, rr, y0);
+            const double* nur = tb.nu[rr];
+#pragma unroll
+            for (int r = 0; r < S; ++r) F[r] = fma(nur[r], net, F[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < S; ++r) out[r] = F[r];
+        if (tb.use_migration) out[S] = -(y0[S] - gp - rho * k.hi) * grow_scale(ws.cs, k.hi);
+        else out[S] = -y0[S];
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// Row loader for the solve sweeps: lane r keeps row r of inv_i (NB doubles) and its four
+// sparse coefficients, fetched a few nodes ahead of use (L2/HBM latency >> one node step).
+template <int NB>
+struct FactorRow {
+    double v[NB];
+    double4 co;      // l, a, ud, ua of this row
+};
+
+template <int NB>
+__device__ __forceinline__ void load_row(const WarpState<NB>& ws, int i, int r, bool act, FactorRow<NB>& f) {
+    constexpr int NBP = padded<NB>();
+    if (act && i >= 0 && i < ws.cs.n) {
+        const double2* p = reinterpret_cast<const double2*>(ws.inv + ((size_t)i * NB + r) * NBP);
+#pragma unroll
+        for (int c = 0; c < NBP / 2; ++c) {
+            const double2 t = p[c];
+            f.v[2 * c] = t.x;
+            if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
+        }
+        f.co = reinterpret_cast<const double4*>(ws.la)[(size_t)i * NB + r];
+    }
+}
+
+// z_r = sum_c row[c]*t[c] with t published through shared memory (double-buffered by parity)
+template <int NB>
+__device__ __forceinline__ double row_dot(const FactorRow<NB>& f, const double* tt) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+        s0 = fma(f.v[c], tt[c], s0);
+        if (c + 1 < NB) s1 = fma(f.v[c + 1], tt[c + 1], s1);
+    }
+    return s0 + s1;
+}
+
+constexpr int PF = 3;     // prefetch distance (nodes) of the solve sweeps
+
+// forward substitution with the stored factors:  z_i = inv_i*(rhs_i - A_L z_{i-1}), zb <- z.
+template <int NB>
+__device__ void forward_solve(WarpState<NB>& ws) {
     constexpr int S = NB - 1;
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
+    double* tbuf = ws.scratch;           // 2*NB doubles (the pivot buffer is free here)
+    FactorRow<NB> ring[PF];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) load_row<NB>(ws, p, r, act, ring[p]);
+    double zprev = 0.0;
+    for (int i0 = 0; i0 < n; i0 += PF) {
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int i = i0 + p;
+            if (i < n) {                       // warp-uniform
+                FactorRow<NB>& f = ring[p];
+                if (act) {
+                    double t = ws.zb[(size_t)i * NB + r];
+                    if (i > 0) {
+                        const double zs = ws.zb[(size_t)(i - 1) * NB + S];
+                        t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
+                    }
+                    tbuf[(i & 1) * NB + r] = t;
+                }
+                __syncwarp();
+                double z = 0.0;
+                if (act) {
+                    z = row_dot<NB>(f, tbuf + (i & 1) * NB);
+                    ws.zb[(size_t)i * NB + r] = z;
+                }
+                zprev = z;
+                load_row<NB>(ws, i + PF, r, act, f);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// Backward substitution  d_i = z_i - inv_i*(A_U d_{i+1})  (node 1: dense W_1; node 0: extra
+// wall block V_0);  y += scale*d, zb <- d.
+template <int NB>
+__device__ void backward_solve(WarpState<NB>& ws, double scale) {
+    constexpr int S = NB - 1;
+    constexpr int NBP = padded<NB>();
+    const int lane = ws.lane;
+    const int n = ws.cs.n;
+    const bool act = lane < NB;
+    const int r = act ? lane : 0;
+    double* tbuf = ws.scratch;
+    FactorRow<NB> ring[PF];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) load_row<NB>(ws, n - 2 - p, r, act, ring[p]);
+    // bulk node: d = z
+    if (act) {
+        const size_t idx = (size_t)(n - 1) * NB + r;
+        ws.y[idx] += ws.zb[idx] * scale;
+    }
+    __syncwarp();
+    for (int i0 = n - 2; i0 >= 0; i0 -= PF) {
+#pragma unroll
+        for (int p = 0; p < PF; ++p) {
+            const int i = i0 - p;
+            if (i >= 0) {                      // warp-uniform
+                FactorRow<NB>& f = ring[p];
+                double d = 0.0;
+                if (i == 1) {
+                    if (act) {
+                        const double* dn = ws.zb + 2 * NB;
+                        const double* Wr = ws.W1 + (size_t)r * NBP;
+                        double s = ws.zb[NB + r];
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) s = fma(-Wr[c], dn[c], s);
+                        d = s;
+                    }
+                } else {
+                    if (act) {
+                        const double* dn = ws.zb + (size_t)(i + 1) * NB;
+                        // t = A_U d_{i+1}: diag -ud, g column -ua (g row: -ud*sg, ua = 0)
+                        const double t = -(f.co.z * dn[r] + (r < S ? f.co.w * dn[S] : 0.0));
+                        tbuf[(i & 1) * NB + r] = t;
+                    }
+                    __syncwarp();
+                    if (act) {
+                        d = ws.zb[(size_t)i * NB + r] - row_dot<NB>(f, tbuf + (i & 1) * NB);
+                        if (i == 0) {
+                            const double* d2 = ws.zb + 2 * NB;
+                            const double* Vr = ws.V0 + (size_t)r * NBP;
+                            double s = 0.0;
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) s = fma(Vr[c], d2[c], s);
+                            d -= s;
+                        }
+                    }
+                }
+                if (act) {
+                    const size_t idx = (size_t)i * NB + r;
+                    ws.zb[idx] = d;
+                    ws.y[idx] += d * scale;
+                }
+                load_row<NB>(ws, i - PF, r, act, f);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// Weighted max norms of the Newton update (scale*zb) and of the accumulated correction
+// (y - zn0) over the error-controlled unknowns (concentrations of nodes 0..n-2).
+// wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
+template <int NB>
+__device__ void newton_norms(const WarpState<NB>& ws, double scale, bool want_acn, double& dnorm, double& anorm,
+                             int wmode, double prtol, double patol) {
+    constexpr int S = NB - 1;
+    const int n = ws.cs.n;
     double dmax = 0.0, amax = 0.0;
-    double Wrow[NB], Wnext[NB];
-    // prefetch W row of node n-2
-    if (n >= 2) {
-        const double* Wi = ws.W + (size_t)(n - 2) * NB * NB + (size_t)r * NB;
-#pragma unroll
-        for (int c = 0; c < NB; ++c) Wnext[c] = act ? Wi[c] : 0.0;
-    }
-    const double* zn0 = ws.zn;
-    for (int i = n - 1; i >= 0; --i) {
-        double d = 0.0;
-        if (i == n - 1) {
-            if (act) d = ws.zb[(size_t)i * NB + r];
-        } else {
-#pragma unroll
-            for (int c = 0; c < NB; ++c) Wrow[c] = Wnext[c];
-            if (i >= 1) {
-                const double* Wi = ws.W + (size_t)(i - 1) * NB * NB + (size_t)r * NB;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) Wnext[c] = act ? Wi[c] : 0.0;
-            }
-            if (act) {
-                const double* dn = ws.zb + (size_t)(i + 1) * NB;
-                double s0 = ws.zb[(size_t)i * NB + r], s1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < NB; c += 2) {
-                    s0 = fma(-Wrow[c], dn[c], s0);
-                    if (c + 1 < NB) s1 = fma(-Wrow[c + 1], dn[c + 1], s1);
-                }
-                d = s0 + s1;
-                if (i == 0) {
-                    const double* d2 = ws.zb + 2 * NB;
-                    const double* Vr = ws.V0 + (size_t)r * NB;
-                    double s = 0.0;
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) s = fma(Vr[c], d2[c], s);
-                    d -= s;
-                }
-            }
+    for (int idx = ws.lane; idx < ws.N; idx += 32) {
+        const int i = idx / NB, r = idx - i * NB;
+        if (r < S && i < n - 1) {
+            const double yv = ws.y[idx];
+            const double w = (wmode == 0) ? ws.ewt[idx] : 1.0 / (prtol * fabs(yv) + patol);
+            double ad = fabs(ws.zb[idx] * scale) * w;
+            if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
+            dmax = fmax(dmax, ad);
+            if (want_acn) amax = fmax(amax, fabs(yv - ws.zn[idx]) * w);
         }
-        if (act) {
-            const size_t idx = (size_t)i * NB + r;
-            ws.zb[idx] = d;
-            const double yn = ws.y[idx] + d;
-            ws.y[idx] = yn;
-            if (r < S && i < n - 1) {
-                double w;
-                if (wmode == 0) w = ws.ewt[idx];
-                else w = 1.0 / (prtol * fabs(yn) + patol);
-                double ad = fabs(d) * w;
-                if (!(ad <= 1e300)) ad = INFINITY;      // NaN/Inf must not be lost in fmax
-                dmax = fmax(dmax, ad);
-                if (wmode == 0) amax = fmax(amax, fabs(yn - zn0[idx]) * w);
-            }
-        }
-        __syncwarp();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        dmax = fmax(dmax, __shfl_xor_sync(FULL, dmax, o));
-        amax = fmax(amax, __shfl_xor_sync(FULL, amax, o));
-    }
-    // propagate NaN as failure
-    dnorm = dmax; anorm = amax;
+    dnorm = warp_max(dmax);
+    anorm = warp_max(amax);
 }
 
 }  // namespace catint

@@ -11,7 +11,7 @@ NVLink/NVSwitch on a B200 box; gloo in the CPU tests of the host logic).
 import numpy as np
 
 # result arrays and the axis that indexes cells
-_CELL_AXIS = {'c': 1, 'phi': 1, 'g': 1, 'flux': 0, 'status': 0, 'n_steps': 0, 'n_newton': 0}
+_CELL_AXIS = {'c': 1, 'phi': 1, 'g': 1, 'flux': 0, 'status': 0, 'n_steps': 0, 'n_newton': 0, 'n_setups': 0}
 
 
 def world():

@@ -15,9 +15,10 @@
  *                                 Jacobian, calculator_old.py:947) analytic block-tridiagonal
  *                                 Jacobian of the same residual in the local (c,g[,phi]) form
  *   catint_pnp_solve_batch     <- the integrator call               calculator_old.py:946-973
- *                                 (scipy odeint = ODEPACK LSODA) : variable-order BDF/Newton
- *                                 with per-cell adaptive step, same error control (rtol/atol,
- *                                 weighted max norm), block-Thomas linear solves
+ *                                 (scipy odeint = ODEPACK LSODA) : variable-order BDF with a
+ *                                 modified-Newton corrector, per-cell adaptive step, same error
+ *                                 control (rtol/atol, weighted max norm), block-Thomas factors
+ *                                 re-used across steps like LSODA re-uses its Jacobian
  *
  * Plain pointers and sizes only.  Unless stated otherwise every array pointer
  * is a DEVICE pointer owned by the caller; small model tables (CatintPnpShared)
@@ -131,6 +132,11 @@ const char* catint_pnp_last_error(void);
 /* number of visible CUDA devices of compute capability 10.x (0 if none) */
 int catint_pnp_device_count(void);
 
+/* Debug hook: device buffer of int64 [n_cells][8] that the next catint_pnp_solve_batch calls fill with
+ * SM cycle counts per phase (factor, residual, forward, backward, norms, history, correction, total);
+ * NULL (default) switches the instrumentation off. */
+void catint_pnp_debug_profile_buffer(void* dev_ptr);
+
 size_t catint_pnp_workspace_bytes(const CatintPnpShared* sh, int64_t n_cells);
 
 /* K1: dc/dt for every cell.  g_out/phi_out may be NULL. */
@@ -148,12 +154,12 @@ int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const CatintPnpCells* c
  *             c0, catint/transport.py:1396-1412)
  *   c_out     [n_out][B][nx_max][S]   phi_out, g_out [n_out][B][nx_max]
  *   flux_out  [B][S] discrete wall flux of the final state
- *   status, n_steps, n_newton  [B]
+ *   status, n_steps, n_newton  [B]; n_setups [B] (block factorisations, may be NULL)
  */
 int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
                            const double* y0, const CatintPnpControl* ctl,
                            double* c_out, double* phi_out, double* g_out, double* flux_out,
-                           int32_t* status, int32_t* n_steps, int32_t* n_newton,
+                           int32_t* status, int32_t* n_steps, int32_t* n_newton, int32_t* n_setups,
                            void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 #ifdef __cplusplus

@@ -49,6 +49,10 @@ class BdfIntegrator(object):
         self.M = lf.mass_diag()
         self.cmask = self.M > 0            # error-controlled unknowns
         self.stats = BdfStats()
+        self.fresh = fresh_jacobian
+        self._lu = None
+        self._gammap = 1.0
+        self._nstlp = 0
 
     # -- norms -----------------------------------------------------------
     def ewt(self, y):
@@ -153,37 +157,72 @@ class BdfIntegrator(object):
             self.zn[j] -= l[j] * self.zn[q]
 
     # -- the nonlinear corrector ------------------------------------------
-    def newton(self):
-        """solve  M*(rl1*zn1 + (y-zn0)) - gamma*F(y) = 0 ; returns (ok, acor, acnrm)"""
+    def _setup(self, y, gamma):
+        """assemble the Jacobian at y and factor  M/gamma - J  (CVODE's lsetup)."""
+        lf = self.lf
+        F, L, Dg, U, E0 = lf.residual(y, blocks=True)
+        J = lf.to_sparse(L, Dg, U, E0)
+        A = sp.diags((self.M / gamma).reshape(-1)) - J
+        self._lu = spla.splu(A.tocsc())
+        self._gammap = gamma
+        self._nstlp = self.stats.nst
+        self.stats.nsetups = getattr(self.stats, 'nsetups', 0) + 1
+        return F
+
+    def newton(self, force_setup=False):
+        """solve  M*(rl1*zn1 + (y-zn0)) - gamma*F(y) = 0 ; returns (ok, acor, acnrm).
+        fresh_jacobian=True: true Newton (setup in every iteration);
+        False: modified Newton with the VODE/CVODE re-use policy (setup on the first step, after
+        20 steps, when gamma drifted by more than 30 %, or after a failure with a stale matrix)."""
         lf = self.lf
         y0 = self.zn[0]
-        acor = np.zeros_like(y0)
-        y = y0.copy()
         gamma = self.h / self.l[1]
         rl1 = 1.0 / self.l[1]
         w = self.ewt_vec
-        crate = 1.0
-        delp = 0.0
-        for m in range(MAXCOR):
-            F, L, Dg, U, E0 = lf.residual(y, blocks=True)
-            J = lf.to_sparse(L, Dg, U, E0)
-            A = sp.diags((self.M / gamma).reshape(-1)) - J
-            rhs = F - self.M * (rl1 * self.zn[1] + acor) / gamma
-            d = spla.splu(A.tocsc()).solve(rhs.reshape(-1)).reshape(y.shape)
-            self.stats.nsolve += 1
-            self.stats.nni += 1
-            dl = self.norm(d, w)
-            acor += d
-            y = y0 + acor
-            if m > 0:
-                crate = max(CRDOWN * crate, dl / delp)
-            dcon = dl * min(1.0, crate) / self.tq[4]
-            if dcon <= 1.0:
-                return True, acor, (dl if m == 0 else self.norm(acor, w))
-            if m + 1 == MAXCOR or (m >= 1 and dl > RDIV * delp):
+        MSBP, DGMAX = 20, 0.3
+        call_setup = (self.fresh or force_setup or self._lu is None or self.stats.nst >= self._nstlp + MSBP
+                      or abs(gamma / self._gammap - 1.0) > DGMAX)
+        while True:
+            acor = np.zeros_like(y0)
+            y = y0.copy()
+            crate = 1.0
+            delp = 0.0
+            jcur = False
+            F = None
+            if call_setup:
+                F = self._setup(y, gamma)
+                jcur = True
+            gamrat = gamma / self._gammap
+            result = None
+            for m in range(MAXCOR):
+                if self.fresh and m > 0:
+                    F = self._setup(y, gamma)
+                elif F is None:
+                    F = lf.residual(y)
+                rhs = F - self.M * (rl1 * self.zn[1] + acor) / gamma
+                d = self._lu.solve(rhs.reshape(-1)).reshape(y.shape)
+                if gamrat != 1.0:
+                    d *= 2.0 * gamrat / (1.0 + gamrat)
+                self.stats.nsolve += 1
+                self.stats.nni += 1
+                dl = self.norm(d, w)
+                acor += d
+                y = y0 + acor
+                F = None
+                if m > 0:
+                    crate = max(CRDOWN * crate, dl / delp)
+                dcon = dl * min(1.0, crate) / self.tq[4]
+                if dcon <= 1.0:
+                    result = (True, acor, (dl if m == 0 else self.norm(acor, w)))
+                    break
+                if m + 1 == MAXCOR or (m >= 1 and dl > RDIV * delp):
+                    break
+                delp = dl
+            if result is not None:
+                return result
+            if jcur or self.fresh:
                 return False, acor, 0.0
-            delp = dl
-        return False, acor, 0.0
+            call_setup = True            # stale matrix: refresh and try once more
 
     # -- driver ------------------------------------------------------------
     def integrate(self, t_out, y0=None, h0=None, max_steps=200000, callback=None):
@@ -222,7 +261,7 @@ class BdfIntegrator(object):
                 self.predict()
                 self.t = saved_t + self.h
                 self.set_bdf()
-                ok, acor, acnrm = self.newton()
+                ok, acor, acnrm = self.newton(force_setup=(ncf > 0 or nef > 0))
                 if not ok:
                     st.ncfn += 1
                     ncf += 1

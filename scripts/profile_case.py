@@ -18,13 +18,24 @@ def main():
     bk = be.PnpBackend('cuda:0')
     db = bk.upload(batch)
     out = bk.alloc_outputs(db, 1)
+    prof = torch.zeros((n_cells, 8), dtype=torch.int64, device='cuda:0')
+    if os.environ.get('CATINT_PHASES'):
+        bk.lib.catint_pnp_debug_profile_buffer(prof.data_ptr())
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.time()
         bk.solve(db, [bench.T_END], mode=be.MODE_STEADY, max_steps=max_steps, out=out)
         torch.cuda.synchronize(); dt = time.time() - t0
         nn = float(out['n_newton'].double().sum())
+        ns = float(out['n_setups'].double().sum()); st = float(out['n_steps'].double().sum())
+        print('   steps/cell %.1f newton/cell %.1f setups/cell %.1f status0 %d' % (st / n_cells, nn / n_cells, ns / n_cells, int((out['status'] == 0).sum())))
         print('rep %d: %.4f s, %d cells, newton total %.0f -> %.1f us per newton iteration per cell-warp, %.2f us amortised'
               % (rep, dt, n_cells, nn, dt / (nn / n_cells) * 1e6, dt / nn * 1e6))
+
+    if os.environ.get('CATINT_PHASES'):
+        pr = prof.double().mean(dim=0).cpu().numpy()
+        names = ['factor', 'residual', 'forward', 'backward', 'norms', 'history', 'correction', 'total']
+        print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})
+        print('per call: factor %.0f cyc, residual %.0f, forward %.0f, backward %.0f, norms %.0f (per newton), history %.0f, correction %.0f (per step)' % (pr[0] / (ns / n_cells), pr[1] / (nn / n_cells), pr[2] / (nn / n_cells), pr[3] / (nn / n_cells), pr[4] / (nn / n_cells), pr[5] / (st / n_cells), pr[6] / (st / n_cells)))
 
 if __name__ == '__main__':
     main()
