@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
-    const size_t state_doubles = SMEM ? (size_t)3 * nxm * NB : 0;
+    const size_t state_doubles = (size_t)RING * (fac_rec<NB>() + 2 * padded<NB>()) + (SMEM ? (size_t)2 * nxm * NB : 0);
     const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
                             (size_t)(scratch_doubles<NB>() + state_doubles) * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
@@ -268,15 +268,16 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     constexpr int NBP = padded<NB>();
     ws.zn = g;                 g += align4((size_t)LMAX * nxm * NB);
     ws.ewt = g;                g += align4((size_t)nxm * NB);
-    ws.inv = g;                g += align4((size_t)nxm * NB * NBP);
-    ws.la = g;                 g += align4((size_t)nxm * NB * 4);
+    ws.fac = g;                g += align4((size_t)nxm * fac_rec<NB>());
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
+    ws.psi = g;                g += align4((size_t)nxm * NB);
+    double* sdyn = ws.scratch + scratch_doubles<NB>();
+    ws.ring = sdyn;            sdyn += (size_t)RING * (fac_rec<NB>() + 2 * padded<NB>());
     if constexpr (SMEM) {
-        double* s = ws.scratch + scratch_doubles<NB>();
-        ws.y = s; ws.psi = s + (size_t)nxm * NB; ws.zb = s + (size_t)2 * nxm * NB;
+        ws.y = sdyn; ws.zb = sdyn + (size_t)nxm * NB;
     } else {
-        ws.y = g; ws.psi = g + (size_t)nxm * NB; ws.zb = g + (size_t)2 * nxm * NB;
+        ws.y = g; ws.zb = g + align4((size_t)nxm * NB);
     }
 
     // ---- initial state: y0 (or bulk) with the consistent field --------------
@@ -389,9 +390,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 for (int m = 0; m < MAXCOR; ++m) {
                     { CATINT_TIC; residual_pass<NB>(ws, inv_gamma); CATINT_TOC(1); }
                     { CATINT_TIC; forward_solve<NB>(ws); CATINT_TOC(2); }
-                    { CATINT_TIC; backward_solve<NB>(ws, dscale); CATINT_TOC(3); }
                     double del, acn;
-                    { CATINT_TIC; newton_norms<NB>(ws, dscale, m > 0, del, acn, 0, 0.0, 0.0); CATINT_TOC(4); }
+                    { CATINT_TIC; backward_solve<NB>(ws, dscale, del, acn, 0, 0.0, 0.0); CATINT_TOC(3); }
                     ++nni;
                     if (!(del <= 1e300)) { bad = true; break; }
                     if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
@@ -461,26 +461,51 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         if (want_up) cquot = (B.tq[5] / B.saved_tq5) * pow(B.h / B.tau[2], (double)(q + 1));
         double ddn = 0.0, dup = 0.0;
         const long long tic_corr = prof_on ? clock64() : 0;
-        // correction pass: zn[j] += l[j]*acor, norms for the order selection, new weights
-        for (int idx = lane; idx < N; idx += 32) {
-            const int i = idx / NB, r = idx - i * NB;
-            const bool mass = r < S && i < n - 1;
-            const double yv = ws.y[idx];
-            const double ac = yv - ws.zn[idx];
-            const double w = ws.ewt[idx];
-            if (want_up && mass) dup = fmax(dup, fabs(ac - cquot * ws.zn[(size_t)QMAX * N + idx]) * w);
-            ws.zn[idx] = yv;
+        // correction pass: zn[j] += l[j]*acor, norms for the order selection, new weights.
+        // Two elements per lane and iteration, loads grouped ahead of the stores (memory-level
+        // parallelism; the history array streams from L2/HBM).
+        {
+            double lreg[LMAX];
 #pragma unroll
-            for (int j = 1; j <= QMAX; ++j) {
-                if (j <= q) {
-                    const double v = ws.zn[(size_t)j * N + idx] + B.l[j] * ac;
-                    ws.zn[(size_t)j * N + idx] = v;
-                    if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w);
+            for (int j = 0; j < LMAX; ++j) lreg[j] = B.l[j];
+            double* __restrict__ zn = ws.zn;
+            double* __restrict__ ewt = ws.ewt;
+            for (int base = lane; base < N; base += 64) {
+                int idx[2]; bool has[2]; double yv[2], w[2], z0[2], zq[2], zj[2][LMAX];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    idx[u] = base + 32 * u;
+                    has[u] = idx[u] < N;
+                    const int ii = has[u] ? idx[u] : base;
+                    yv[u] = ws.y[ii];
+                    z0[u] = zn[ii];
+                    w[u] = ewt[ii];
+                    zq[u] = want_up ? zn[(size_t)QMAX * N + ii] : 0.0;
+#pragma unroll
+                    for (int j = 1; j <= QMAX; ++j) zj[u][j] = (j <= q) ? zn[(size_t)j * N + ii] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!has[u]) continue;
+                    const int ii = idx[u];
+                    const int i = ii / NB, r = ii - i * NB;
+                    const bool mass = r < S && i < n - 1;
+                    const double ac = yv[u] - z0[u];
+                    if (want_up && mass) dup = fmax(dup, fabs(ac - cquot * zq[u]) * w[u]);
+                    zn[ii] = yv[u];
+#pragma unroll
+                    for (int j = 1; j <= QMAX; ++j) {
+                        if (j <= q) {
+                            const double v = zj[u][j] + lreg[j] * ac;
+                            zn[(size_t)j * N + ii] = v;
+                            if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w[u]);
+                        }
+                    }
+                    if (save_acor) zn[(size_t)QMAX * N + ii] = ac;
+                    ws.zb[ii] = ac;
+                    ewt[ii] = 1.0 / (rtol * fabs(yv[u]) + atol);
                 }
             }
-            if (save_acor) ws.zn[(size_t)QMAX * N + idx] = ac;
-            ws.zb[idx] = ac;
-            ws.ewt[idx] = 1.0 / (rtol * fabs(yv) + atol);
         }
         __syncwarp();
         if (prof_on) pc[6] += clock64() - tic_corr;
@@ -552,9 +577,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             if (!ok) break;
             residual_pass<NB>(ws, 0.0);
             forward_solve<NB>(ws);
-            backward_solve<NB>(ws, 1.0);
             double del, acn;
-            newton_norms<NB>(ws, 1.0, false, del, acn, 1, P.polish_rtol, patol);
+            backward_solve<NB>(ws, 1.0, del, acn, 1, P.polish_rtol, patol);
             ++nni;
             if (!(del <= 1e300)) break;
             if (del <= 1.0) done = true;
@@ -719,8 +743,9 @@ template <int NB>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
     const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
-    const size_t state = (size_t)3 * P.tb.nx_max * NB * sizeof(double);
+    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
+                                  (size_t)(scratch_doubles<NB>() + RING * (fac_rec<NB>() + 2 * padded<NB>())) * sizeof(double);
+    const size_t state = (size_t)2 * P.tb.nx_max * NB * sizeof(double);
     int dev = 0; cudaGetDevice(&dev);
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -19,6 +19,7 @@
 //
 // No tensor cores: the blocks are 9..13 wide and the chain over nodes is sequential.
 #pragma once
+#include <cuda_pipeline.h>
 #include "pnp_device.cuh"
 
 namespace catint {
@@ -30,10 +31,10 @@ struct WarpState {
     double* zb;     // rhs -> z -> delta                   [n*NB]
     double* zn;     // Nordsieck array                     [LMAX][N] (global)
     double* ewt;    // error weights                       [N]
-    double* inv;    // A_D'^{-1}, rows padded to NBP       [n][NB][NBP]
+    double* fac;    // per node record [ inv_i: NB x NBP | per row l, a (A_L), ud, ua (A_U): NB x 4 ]  (global)
     double* W1;     // inv_1*A_U1' (dense because of the wall block)   [NB][NBP]
     double* V0;     // inv_0*A_E                           [NB][NBP]
-    double* la;     // per row: l, a (A_L), ud, ua (A_U, g-row scaled)  [n][NB][4]
+    double* ring;   // shared: RING node records staged by cp.async ahead of the solve sweeps
     double* scratch;            // shared, per warp
     const CellSpecies* sp;      // shared, per warp
     const DevTables* tb;        // shared, per block
@@ -49,6 +50,10 @@ __host__ __device__ constexpr size_t align4(size_t doubles) { return (doubles + 
 // padded row length of the stored blocks (even -> 16-byte aligned rows, double2 loads)
 template <int NB>
 __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
+// doubles per node of the stored factors: inverse block (padded rows) + 4 coefficients per row
+template <int NB>
+__host__ __device__ constexpr int fac_rec() { return NB * padded<NB>() + NB * 4; }
+constexpr int RING = 8;   // node records in flight in the solve sweeps
 
 // ---------------------------------------------------------------------------
 // Gauss-Jordan elimination with threshold partial pivoting; lane j owns column j
@@ -246,7 +251,8 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
         node_coeffs<NB>(ws, y, i, sl, sa, sud, sua);
         __syncwarp();
         const double* yi = y + (size_t)i * NB;
-        double* invcol = ws.inv + (size_t)i * NB * NBP + j;      // column j of inv_i (I lanes)
+        double* rec = ws.fac + (size_t)i * fac_rec<NB>();
+        double* invcol = rec + j;                                   // column j of inv_i (I lanes)
         const NodeCoef k = (i > 0) ? interior_coef(ws.cs, i) : NodeCoef{0, 0, 0, 1, 1};
         const double sg = (i > 0 && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
         if (lane < NB) {
@@ -254,7 +260,7 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
             v.x = sl[lane]; v.y = sa[lane];
             v.z = (lane == S) ? sud[lane] * sg : sud[lane];
             v.w = sua[lane];
-            reinterpret_cast<double4*>(ws.la)[(size_t)i * NB + lane] = v;
+            reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
         }
 #pragma unroll
         for (int r = 0; r < NB; ++r) A[r] = 0.0;
@@ -364,9 +370,9 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
     // bulk node: identity rows, no coupling
     {
         const int i = n - 1;
-        for (int e = lane; e < NB * NBP; e += 32)
-            ws.inv[(size_t)i * NB * NBP + e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
-        if (lane < NB) reinterpret_cast<double4*>(ws.la)[(size_t)i * NB + lane] = make_double4(0, 0, 0, 0);
+        double* rec = ws.fac + (size_t)i * fac_rec<NB>();
+        for (int e = lane; e < NB * NBP; e += 32) rec[e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
+        if (lane < NB) reinterpret_cast<double4*>(rec + NB * NBP)[lane] = make_double4(0, 0, 0, 0);
     }
     __syncwarp();
     return __all_sync(FULL, ok);
@@ -388,7 +394,6 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
                 double v = row_residual<NB>(ws, y, i, r);
-                if (i == 0 && r < S) v -= (y0[r] + ws.psi[r]) * inv_gamma;
                 out[r] = v;
             }
             continue;
@@ -403,12 +408,21 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
         for (int r = 0; r < S; ++r) {
             const double cm = ym[r], c0 = y0[r], cp = yp[r];
             F[r] = ws.sp->D[r] * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp
-                                  + ws.sp->bq[r] * k.ac * (cp * gp - cm * gm))
-                   - (c0 + ws.psi[(size_t)i * NB + r]) * inv_gamma;
+                                  + ws.sp->bq[r] * k.ac * (cp * gp - cm * gm));
             rho = fma(ws.sp->qe[r], c0, rho);
         }
         for (int rr = 0; rr < tb.R; ++rr) {
-            const double net = net_rate(tb, rr, y0);
+            // educt/product indices of one reaction as two packed words (one LDS each, uniform)
+            const unsigned ew = *reinterpret_cast<const unsigned*>(tb.ed[rr]);
+            const unsigned pw = *reinterpret_cast<const unsigned*>(tb.pr[rr]);
+            const int ne = tb.ned[rr], np = tb.npr[rr];
+            double f = tb.kf[rr], b = tb.kr[rr];
+#pragma unroll
+            for (int e = 0; e < MAXRT; ++e) {
+                if (e < ne) f *= y0[(ew >> (8 * e)) & 0xff];
+                if (e < np) b *= y0[(pw >> (8 * e)) & 0xff];
+            }
+            const double net = f - b;
             const double* nur = tb.nu[rr];
 #pragma unroll
             for (int r = 0; r < S; ++r) F[r] = fma(nur[r], net, F[r]);
@@ -419,11 +433,31 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
         else out[S] = -y0[S];
     }
     __syncwarp();
+    if (inv_gamma != 0.0) {
+        // mass term of the BDF corrector, psi streamed from global memory (coalesced)
+        for (int idx = ws.lane; idx < ws.N; idx += 32) {
+            const int i = idx / NB, r = idx - i * NB;
+            if (r < S && i < n - 1) ws.zb[idx] -= (y[idx] + ws.psi[idx]) * inv_gamma;
+        }
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------
-// Row loader for the solve sweeps: lane r keeps row r of inv_i (NB doubles) and its four
-// sparse coefficients, fetched a few nodes ahead of use (L2/HBM latency >> one node step).
+// Solve sweeps with the stored factors.  The node records stream from global memory (L2/HBM)
+// into a shared-memory ring by cp.async, RING-1 nodes ahead of use, so that the sequential
+// chain over the nodes never waits for DRAM.  Lane r (< NB) owns row r.
+template <int NB>
+__device__ __forceinline__ void ring_issue(const WarpState<NB>& ws, int i, int slot) {
+    constexpr int REC = fac_rec<NB>();
+    if (i >= 0 && i < ws.cs.n) {
+        const double* src = ws.fac + (size_t)i * REC;
+        double* dst = ws.ring + (size_t)slot * REC;
+        for (int c = ws.lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+    }
+    __pipeline_commit();
+}
+
 template <int NB>
 struct FactorRow {
     double v[NB];
@@ -431,21 +465,19 @@ struct FactorRow {
 };
 
 template <int NB>
-__device__ __forceinline__ void load_row(const WarpState<NB>& ws, int i, int r, bool act, FactorRow<NB>& f) {
+__device__ __forceinline__ void ring_row(const WarpState<NB>& ws, int slot, int r, FactorRow<NB>& f) {
     constexpr int NBP = padded<NB>();
-    if (act && i >= 0 && i < ws.cs.n) {
-        const double2* p = reinterpret_cast<const double2*>(ws.inv + ((size_t)i * NB + r) * NBP);
+    const double* rec = ws.ring + (size_t)slot * fac_rec<NB>();
+    const double2* p = reinterpret_cast<const double2*>(rec + r * NBP);
 #pragma unroll
-        for (int c = 0; c < NBP / 2; ++c) {
-            const double2 t = p[c];
-            f.v[2 * c] = t.x;
-            if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
-        }
-        f.co = reinterpret_cast<const double4*>(ws.la)[(size_t)i * NB + r];
+    for (int c = 0; c < NBP / 2; ++c) {
+        const double2 t = p[c];
+        f.v[2 * c] = t.x;
+        if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
     }
+    f.co = reinterpret_cast<const double4*>(rec + NB * NBP)[r];
 }
 
-// z_r = sum_c row[c]*t[c] with t published through shared memory (double-buffered by parity)
 template <int NB>
 __device__ __forceinline__ double row_dot(const FactorRow<NB>& f, const double* tt) {
     double s0 = 0.0, s1 = 0.0;
@@ -457,9 +489,7 @@ __device__ __forceinline__ double row_dot(const FactorRow<NB>& f, const double* 
     return s0 + s1;
 }
 
-constexpr int PF = 3;     // prefetch distance (nodes) of the solve sweeps
-
-// forward substitution with the stored factors:  z_i = inv_i*(rhs_i - A_L z_{i-1}), zb <- z.
+// forward substitution:  z_i = inv_i*(rhs_i - A_L z_{i-1}), zb <- z.
 template <int NB>
 __device__ void forward_solve(WarpState<NB>& ws) {
     constexpr int S = NB - 1;
@@ -468,106 +498,134 @@ __device__ void forward_solve(WarpState<NB>& ws) {
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;           // 2*NB doubles (the pivot buffer is free here)
-    FactorRow<NB> ring[PF];
 #pragma unroll
-    for (int p = 0; p < PF; ++p) load_row<NB>(ws, p, r, act, ring[p]);
+    for (int p = 0; p < RING - 1; ++p) ring_issue<NB>(ws, p, p);
     double zprev = 0.0;
-    for (int i0 = 0; i0 < n; i0 += PF) {
-#pragma unroll
-        for (int p = 0; p < PF; ++p) {
-            const int i = i0 + p;
-            if (i < n) {                       // warp-uniform
-                FactorRow<NB>& f = ring[p];
-                if (act) {
-                    double t = ws.zb[(size_t)i * NB + r];
-                    if (i > 0) {
-                        const double zs = ws.zb[(size_t)(i - 1) * NB + S];
-                        t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
-                    }
-                    tbuf[(i & 1) * NB + r] = t;
-                }
-                __syncwarp();
-                double z = 0.0;
-                if (act) {
-                    z = row_dot<NB>(f, tbuf + (i & 1) * NB);
-                    ws.zb[(size_t)i * NB + r] = z;
-                }
-                zprev = z;
-                load_row<NB>(ws, i + PF, r, act, f);
-                __syncwarp();
+    for (int i = 0; i < n; ++i) {
+        __pipeline_wait_prior(RING - 2);
+        __syncwarp();
+        FactorRow<NB> f;
+        double z = 0.0;
+        if (act) {
+            ring_row<NB>(ws, i & (RING - 1), r, f);
+            double t = ws.zb[(size_t)i * NB + r];
+            if (i > 0) {
+                const double zs = ws.zb[(size_t)(i - 1) * NB + S];
+                t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
             }
+            tbuf[(i & 1) * NB + r] = t;
         }
+        __syncwarp();
+        if (act) {
+            z = row_dot<NB>(f, tbuf + (i & 1) * NB);
+            ws.zb[(size_t)i * NB + r] = z;
+        }
+        zprev = z;
+        ring_issue<NB>(ws, i + RING - 1, (i + RING - 1) & (RING - 1));
     }
+    __pipeline_wait_prior(0);
+    __syncwarp();
 }
 
 // Backward substitution  d_i = z_i - inv_i*(A_U d_{i+1})  (node 1: dense W_1; node 0: extra
-// wall block V_0);  y += scale*d, zb <- d.
+// wall block V_0);  y += scale*d, zb <- d.  Fused with the weighted max norms of the Newton
+// update (|scale*d|*w) and of the accumulated correction (|y-zn0|*w) over the error-controlled
+// unknowns (concentrations of nodes 0..n-2): the weights and zn0 of each node ride in a second
+// cp.async ring.  wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
 template <int NB>
-__device__ void backward_solve(WarpState<NB>& ws, double scale) {
+__device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, double& anorm,
+                               int wmode, double prtol, double patol) {
     constexpr int S = NB - 1;
     constexpr int NBP = padded<NB>();
+    constexpr int R2 = 2 * NBP;                  // doubles per node in the weight ring
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;
-    FactorRow<NB> ring[PF];
+    double* ring2 = ws.ring + (size_t)RING * fac_rec<NB>();
+    double dmax = 0.0, amax = 0.0;
+    auto issue = [&](int i, int slot) {
+        if (i >= 0 && i < n) {
+            const double* src = ws.fac + (size_t)i * fac_rec<NB>();
+            double* dst = ws.ring + (size_t)slot * fac_rec<NB>();
+            for (int c = lane; c < fac_rec<NB>() / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+            if (wmode == 0 && lane < 2 * NB) {
+                const double* s2 = (lane < NB ? ws.ewt : ws.zn - NB) + (size_t)i * NB + lane;
+                __pipeline_memcpy_async(ring2 + (size_t)slot * R2 + (lane < NB ? lane : NBP + lane - NB), s2, 8);
+            }
+        }
+        __pipeline_commit();
+    };
+    // sweep position k = 0,1,.. <-> node i = n-2-k
 #pragma unroll
-    for (int p = 0; p < PF; ++p) load_row<NB>(ws, n - 2 - p, r, act, ring[p]);
-    // bulk node: d = z
-    if (act) {
+    for (int p = 0; p < RING - 1; ++p) issue(n - 2 - p, p);
+    if (act) {   // bulk node: d = z (not error controlled)
         const size_t idx = (size_t)(n - 1) * NB + r;
         ws.y[idx] += ws.zb[idx] * scale;
     }
-    __syncwarp();
-    for (int i0 = n - 2; i0 >= 0; i0 -= PF) {
+    for (int k = 0; k <= n - 2; ++k) {
+        const int i = n - 2 - k;
+        __pipeline_wait_prior(RING - 2);
+        __syncwarp();
+        const int slot = k & (RING - 1);
+        FactorRow<NB> f;
+        double d = 0.0;
+        if (i == 1) {
+            if (act) {
+                const double* dn = ws.zb + 2 * NB;
+                const double* Wr = ws.W1 + (size_t)r * NBP;
+                double s = ws.zb[NB + r];
 #pragma unroll
-        for (int p = 0; p < PF; ++p) {
-            const int i = i0 - p;
-            if (i >= 0) {                      // warp-uniform
-                FactorRow<NB>& f = ring[p];
-                double d = 0.0;
-                if (i == 1) {
-                    if (act) {
-                        const double* dn = ws.zb + 2 * NB;
-                        const double* Wr = ws.W1 + (size_t)r * NBP;
-                        double s = ws.zb[NB + r];
+                for (int c = 0; c < NB; ++c) s = fma(-Wr[c], dn[c], s);
+                d = s;
+            }
+        } else {
+            if (act) {
+                ring_row<NB>(ws, slot, r, f);
+                const double* dn = ws.zb + (size_t)(i + 1) * NB;
+                // t = A_U d_{i+1}: diag -ud, g column -ua (g row: -ud*sg, ua = 0)
+                const double t = -(f.co.z * dn[r] + (r < S ? f.co.w * dn[S] : 0.0));
+                tbuf[(k & 1) * NB + r] = t;
+            }
+            __syncwarp();
+            if (act) {
+                d = ws.zb[(size_t)i * NB + r] - row_dot<NB>(f, tbuf + (k & 1) * NB);
+                if (i == 0) {
+                    const double* d2 = ws.zb + 2 * NB;
+                    const double* Vr = ws.V0 + (size_t)r * NBP;
+                    double s = 0.0;
 #pragma unroll
-                        for (int c = 0; c < NB; ++c) s = fma(-Wr[c], dn[c], s);
-                        d = s;
-                    }
-                } else {
-                    if (act) {
-                        const double* dn = ws.zb + (size_t)(i + 1) * NB;
-                        // t = A_U d_{i+1}: diag -ud, g column -ua (g row: -ud*sg, ua = 0)
-                        const double t = -(f.co.z * dn[r] + (r < S ? f.co.w * dn[S] : 0.0));
-                        tbuf[(i & 1) * NB + r] = t;
-                    }
-                    __syncwarp();
-                    if (act) {
-                        d = ws.zb[(size_t)i * NB + r] - row_dot<NB>(f, tbuf + (i & 1) * NB);
-                        if (i == 0) {
-                            const double* d2 = ws.zb + 2 * NB;
-                            const double* Vr = ws.V0 + (size_t)r * NBP;
-                            double s = 0.0;
-#pragma unroll
-                            for (int c = 0; c < NB; ++c) s = fma(Vr[c], d2[c], s);
-                            d -= s;
-                        }
-                    }
+                    for (int c = 0; c < NB; ++c) s = fma(Vr[c], d2[c], s);
+                    d -= s;
                 }
-                if (act) {
-                    const size_t idx = (size_t)i * NB + r;
-                    ws.zb[idx] = d;
-                    ws.y[idx] += d * scale;
-                }
-                load_row<NB>(ws, i - PF, r, act, f);
-                __syncwarp();
             }
         }
+        if (act) {
+            const size_t idx = (size_t)i * NB + r;
+            ws.zb[idx] = d;
+            const double ds = d * scale;
+            const double yn = ws.y[idx] + ds;
+            ws.y[idx] = yn;
+            if (r < S) {
+                double w, z0 = 0.0;
+                if (wmode == 0) { w = ring2[(size_t)slot * R2 + r]; z0 = ring2[(size_t)slot * R2 + NBP + r]; }
+                else w = 1.0 / (prtol * fabs(yn) + patol);
+                double ad = fabs(ds) * w;
+                if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
+                dmax = fmax(dmax, ad);
+                if (wmode == 0) amax = fmax(amax, fabs(yn - z0) * w);
+            }
+        }
+        issue(n - 2 - (k + RING - 1), (k + RING - 1) & (RING - 1));
     }
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    dnorm = warp_max(dmax);
+    anorm = warp_max(amax);
 }
 
+// ---------------------------------------------------------------------------
 // Weighted max norms of the Newton update (scale*zb) and of the accumulated correction
 // (y - zn0) over the error-controlled unknowns (concentrations of nodes 0..n-2).
 // wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).

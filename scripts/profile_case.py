@@ -31,7 +31,11 @@ def main():
         print('rep %d: %.4f s, %d cells, newton total %.0f -> %.1f us per newton iteration per cell-warp, %.2f us amortised'
               % (rep, dt, n_cells, nn, dt / (nn / n_cells) * 1e6, dt / nn * 1e6))
 
+    stp = out['n_steps'].cpu().numpy(); nw = out['n_newton'].cpu().numpy(); sts = out['n_setups'].cpu().numpy()
+    print('steps  min/mean/max', stp.min(), stp.mean(), stp.max(), ' newton', nw.min(), nw.mean(), nw.max(), ' setups', sts.min(), sts.mean(), sts.max())
+    print('steps by cell decile:', [int(stp[i]) for i in range(0, n_cells, max(1, n_cells // 10))])
     if os.environ.get('CATINT_PHASES'):
+        tot = prof[:, 7].double().cpu().numpy(); print('total cycles min/mean/max %.3g %.3g %.3g' % (tot.min(), tot.mean(), tot.max()))
         pr = prof.double().mean(dim=0).cpu().numpy()
         names = ['factor', 'residual', 'forward', 'backward', 'norms', 'history', 'correction', 'total']
         print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})
