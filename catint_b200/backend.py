@@ -20,7 +20,7 @@ MODE_TRANSIENT = 0
 MODE_STEADY = 1
 
 CELL_STATUS = {0: 'converged', 1: 'max_steps', 2: 'corrector_failed', 3: 'error_test_failed',
-               4: 'not_finite', 5: 'polish_failed'}
+               4: 'not_finite', 5: 'polish_failed', 6: 'step_underflow'}
 
 _LIB_NAME = 'libcatint_pnp.so'
 _lib = None

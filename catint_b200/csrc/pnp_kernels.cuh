@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             else if (pend_dq < 0) decrease_coef<NB>(B, lc);
             if (pend_dq != 0) { B.q += pend_dq; B.qwait = B.q + 1; }
             if (pend_eta != 1.0) { B.h = B.hscale * pend_eta; B.hscale = B.h; }
+            if (saved_t + B.h == saved_t) { status = CATINT_PNP_CELL_STEP_UNDERFLOW; break; }   // t+h == t
             B.t = saved_t + B.h;
             set_bdf<NB>(B);
             const double rl1 = 1.0 / B.l[1];

@@ -67,7 +67,8 @@ enum {
     CATINT_PNP_CELL_CORRECTOR_FAILED = 2,
     CATINT_PNP_CELL_ERROR_TEST_FAILED = 3,
     CATINT_PNP_CELL_NOT_FINITE = 4,
-    CATINT_PNP_CELL_POLISH_FAILED = 5    /* integrated to t_end but Newton on the steady residual did not converge */
+    CATINT_PNP_CELL_POLISH_FAILED = 5,   /* integrated to t_end but Newton on the steady residual did not converge */
+    CATINT_PNP_CELL_STEP_UNDERFLOW = 6   /* t+h == t: the discrete ODE blows up in finite time (LSODA: 'step size too small') */
 };
 
 /* Model tables shared by all cells of a batch (HOST memory). */

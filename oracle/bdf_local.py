@@ -258,6 +258,8 @@ class BdfIntegrator(object):
             ncf = nef = 0
             saved_t = self.t
             while True:
+                if saved_t + self.h == saved_t:
+                    raise RuntimeError('bdf: step size underflow at t=%g (h=%g): the solution blows up' % (saved_t, self.h))
                 self.predict()
                 self.t = saved_t + self.h
                 self.set_bdf()
