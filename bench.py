@@ -194,6 +194,44 @@ def run_reference(args):
     return 0
 
 
+def rhs_roofline(bk, batch, dev, n_cells=131072, reps=10):
+    """K1 (pnp_rhs_kernel) alone on a batch larger than L2: achieved HBM bandwidth of the streaming
+    RHS stage, algorithmic bytes 16*S*n per cell (read c, write dc/dt)."""
+    import torch
+    from catint_b200 import workloads
+    big = workloads.replicate_batch(batch, n_cells)
+    db = bk.upload(big)
+    S, n = big.S, big.nx_max
+    c = torch.empty((n_cells, n, S), dtype=torch.float64, device=dev)
+    c[:] = torch.tensor(big.par[0, :S], device=dev)[None, None, :]
+    c *= 1.0 + 0.01 * torch.rand_like(c)
+    lib = bk.lib
+    import ctypes
+    dcdt = torch.empty_like(c)
+    def launch():
+        rc = lib.catint_pnp_rhs_batch(ctypes.byref(db.shared), ctypes.byref(db.cells), n_cells, c.data_ptr(),
+                                      dcdt.data_ptr(), None, None,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 16.0 * S * n * n_cells
+    peak, which = measured_peaks()
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'pnp_rhs_kernel', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'frac': ach / peak, 'traffic': None, 'peak_source': which, 'cells': n_cells,
+            'algorithmic_bytes_per_launch': nbytes, 'ms_per_launch': ms,
+            'note': 'input+output 2x%.0f MB per launch (> 126 MB L2), back-to-back launches' % (nbytes / 2e6)}
+
+
 # ---------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -276,28 +314,43 @@ def run_gpu(args):
     if rank == 0:
         value = n_conv_all * args.steps / (dev_ms * 1e-3)
         e2e_value = e2e_conv_all / e2e_s
-        # roofline of pnp_bdf_kernel (one launch per step and rank).  Algorithmic bytes per Newton
-        # iteration and cell: state in + update out 16*S*n, plus W written in the
-        # forward and re-read in the backward sweep 16*b^2*n (W does not stay on chip in this design).
+        # roofline of pnp_bdf_kernel (one launch per step and rank).  Algorithmic bytes:
+        #   per Newton iteration  16*S*n (state in, update out) + 2*8*n*REC (the stored block factors are
+        #                         streamed once by the forward and once by the backward solve sweep)
+        #   per factorisation     8*n*REC written (REC = b*bp + 4*b doubles per node, bp = b rounded up to even)
+        #   per BDF step          26*8*n*b (Nordsieck history: predict pass reads/writes 6 vectors, correction
+        #                         pass reads 7 and writes 7)
         S, n, b = batch.S, int(batch.nx_max), batch.b
-        bytes_per_newton = 16.0 * S * n + 16.0 * b * b * n
-        flops_per_newton = n * (14.0 / 3.0 * b ** 3 + 4.0 * b ** 2)
+        rec = b * (b + (b & 1)) + 4 * b
+        bytes_newton = 16.0 * S * n + 16.0 * n * rec
+        bytes_factor = 8.0 * n * rec
+        bytes_step = 26.0 * 8.0 * n * b
+        setups_total = float(out['n_setups'].to(torch.float64).sum().item())
+        steps_total = float(out['n_steps'].to(torch.float64).sum().item())
+        algo_bytes = newton_total * bytes_newton + setups_total * bytes_factor + steps_total * bytes_step
+        flops = (setups_total * n * (8.0 / 3.0 * b ** 3 + 4.0 * b ** 2)        # block inverse + W column + Schur
+                 + newton_total * n * (4.0 * b ** 2 + 40.0 * S))             # two mat-vecs + residual
         launch_s = dev_ms * 1e-3 / args.steps
         peak, which = measured_peaks()
-        achieved = newton_total * bytes_per_newton / launch_s / 1e9            # this rank's launch
-        roofline = {'bound': 'hbm', 'kernel': 'pnp_bdf_kernel<9>', 'achieved': achieved, 'peak': peak,
+        achieved = algo_bytes / launch_s / 1e9                                  # this rank's launch
+        roofline = {'bound': 'hbm', 'kernel': 'pnp_bdf_kernel<9,true>', 'achieved': achieved, 'peak': peak,
                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': which,
-                    'newton_iterations_per_launch': newton_total, 'bytes_per_newton_iteration': bytes_per_newton,
-                    'fp64_tflops_algorithmic': newton_total * flops_per_newton / launch_s / 1e12,
-                    'note': 'n=101 solves run out of shared memory/L2; the kernel is fp64-issue/latency bound, '
-                            'the HBM fraction is reported as the contract asks (see DESIGN.md)'}
+                    'algorithmic_bytes_per_launch': algo_bytes,
+                    'newton_iterations_per_launch': newton_total, 'factorisations_per_launch': setups_total,
+                    'bdf_steps_per_launch': steps_total,
+                    'bytes_per_newton_iteration': bytes_newton, 'bytes_per_factorisation': bytes_factor,
+                    'bytes_per_bdf_step': bytes_step,
+                    'fp64_tflops_algorithmic': flops / launch_s / 1e12,
+                    'note': 'one warp per cell, 1024 cells = 7 warps/SM: the kernel is bound by the dependency '
+                            'latency of the sequential block sweeps, not by HBM (see DESIGN.md 6)'}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'cells/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'cells_per_gpu': CELLS_PER_GPU,
                        'l2': 'flushed between timed steps (256 MiB device write)',
-                       'mean_bdf_steps_per_cell': steps_mean, 'mean_newton_per_cell': newton_total / batch.B},
+                       'mean_bdf_steps_per_cell': steps_mean, 'mean_newton_per_cell': newton_total / batch.B,
+                       'mean_factorisations_per_cell': setups_total / batch.B},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d * args.gpus,
                     'd2h_bytes_per_step': d2h * args.gpus, 'steps': e2e_steps},
@@ -305,6 +358,8 @@ def run_gpu(args):
             'converged_cells_per_step': n_conv_all,
             'roofline': roofline,
         }
+        if args.gpus == 1:
+            line['roofline_rhs'] = rhs_roofline(bk, batch, dev)
         if args.gpus == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_cells = min(cores, batch.B)

@@ -33,13 +33,17 @@ extern "C" void catint_pnp_debug_profile_buffer(void* dev_ptr) { g_prof = reinte
 extern "C" const char* catint_pnp_last_error(void) { return g_err; }
 
 extern "C" int catint_pnp_device_count(void) {
+    // cudaGetDeviceProperties costs milliseconds: query once per process
+    static int cached = -1;
+    if (cached >= 0) return cached;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     int ok = 0;
     for (int d = 0; d < n; ++d) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
     }
+    cached = ok;
     return ok;
 }
 
@@ -165,13 +169,16 @@ extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCe
     if (rc) return rc;
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
     P.c = c; P.n_cells = n_cells; P.dcdt = dcdt; P.g_out = g_out; P.phi_out = phi_out;
-    const int WARPS = 4;
-    const size_t smem = ((sizeof(DevTables) + 15) & ~size_t(15)) +
-                        WARPS * (((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)sh->nx_max * sizeof(double));
-    cudaFuncSetAttribute(pnp_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const unsigned grid = (unsigned)((n_cells + WARPS - 1) / WARPS);
-    pnp_rhs_kernel<<<grid, WARPS * 32, smem, (cudaStream_t)cuda_stream>>>(P);
-    return check_cuda("pnp_rhs_kernel launch");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    switch (sh->S) {
+#define X(SV) case SV: rc = launch_rhs<SV>(P, st); break;
+        X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
+#undef X
+        default: rc = CATINT_PNP_EINVAL;
+    }
+    if (rc == CATINT_PNP_EINVAL) return fail(rc, "pnp_rhs_kernel: grid too large for shared memory (nx_max*S)");
+    if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_rhs_kernel launch failed");
+    return rc;
 }
 
 extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,

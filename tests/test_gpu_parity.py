@@ -44,17 +44,27 @@ def test_rhs_kernel_matches_oracle(bk, name, mode, literal):
     c = np.stack([st.reshape(S, n).T for st in su['rhs_states']])
     dcdt, g, phi = bk.rhs(db, to_dev(c))
     dcdt, g, phi = dcdt.cpu().numpy(), g.cpu().numpy(), phi.cpu().numpy()
+    eps_m = np.finfo(float).eps
     for k, st in enumerate(su['rhs_states']):
         ref, v, gg, _ = s.rhs(st, with_field=True)
         ref = ref.reshape(S, n).T
-        assert np.max(np.abs(dcdt[k] - ref)) <= 1e-12 * np.max(np.abs(ref))
+        C = st.reshape(S, n)
+        # "same arithmetic up to summation order": the charge density is a cancelling sum, so the bound is
+        # relative to the sum of the absolute terms (the bulk state cancels to 1e-11 of them), not to the result
+        rho_abs = (np.abs(s.q)[:, None] * np.abs(C)).sum(axis=0) / s.eps * s.dx
+        g_tol = 64 * eps_m * np.concatenate([np.cumsum(rho_abs[::-1])[::-1][1:], [0.0]]) + 1e-13 * np.max(np.abs(gg))
+        g_tol[0] = 3 * g_tol[1]
         if s.use_migration:
-            assert np.max(np.abs(g[k] - gg)) <= 1e-12 * np.max(np.abs(gg))
-            assert np.max(np.abs(phi[k] - v)) <= 1e-12 * max(np.max(np.abs(v)), 1e-300)
+            assert np.all(np.abs(g[k] - gg) <= g_tol)
+            v_tol = np.cumsum(g_tol) * s.dx + 1e-13 * max(np.max(np.abs(v)), 1e-300)
+            assert np.all(np.abs(phi[k] - v) <= 2 * v_tol + 2 * v_tol[-2])
+        mig = (s.D * np.abs(s.beta * s.q))[None, :] * np.abs(C.T) / s.dx            # |d(dc/dt)/dg| per node
+        d_tol = 1e-12 * np.max(np.abs(ref)) + mig * (np.roll(g_tol, 1) + np.roll(g_tol, -1) + g_tol)[:, None]
+        assert np.all(np.abs(dcdt[k] - ref) <= d_tol)
         if literal and mode == 'legacy_overwrite':
             # the reference's own ode_func on the same state
             r2 = su['rhs_ref'][k].reshape(S, n).T
-            assert np.max(np.abs(dcdt[k] - r2)) <= 1e-12 * np.max(np.abs(r2))
+            assert np.all(np.abs(dcdt[k] - r2) <= d_tol)
 
 
 # ---------------------------------------------------------------- K2 ----------------------
