@@ -89,7 +89,7 @@ def test_scatter_results_conventions(resultsdir):
     res = {'c': rng.uniform(0.1, 2.0, (n_out, B, n, S)), 'g': rng.normal(size=(n_out, B, n)),
            'phi': rng.normal(size=(n_out, B, n)), 'flux': batch.par[:, S:2 * S].copy(),
            'status': np.zeros(B, dtype=np.int32), 'n_steps': np.ones(B, dtype=np.int32),
-           'n_newton': np.ones(B, dtype=np.int32)}
+           'n_newton': np.ones(B, dtype=np.int32), 'n_setups': np.ones(B, dtype=np.int32)}
     calc.scatter_results(batch, models, res)
     names = list(tp.species)
     ad = tp.alldata[1]

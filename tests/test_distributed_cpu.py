@@ -23,7 +23,7 @@ def fake_solve(sub):
     c += np.arange(n)[None, None, :, None] + 0.01 * np.arange(S)[None, None, None, :] + np.arange(2)[:, None, None, None] * 100
     return {'c': c, 'phi': c[..., 0] * 2, 'g': c[..., 1] * 3, 'flux': sub.par[:, S:2 * S].copy(),
             'status': (key > np.median(key)).astype(np.int32), 'n_steps': (np.arange(B) + 7).astype(np.int32) * 0 + sub.nx,
-            'n_newton': sub.nx * 2}
+            'n_newton': sub.nx * 2, 'n_setups': sub.nx * 3}
 
 
 def make_batch(B=7):
@@ -61,13 +61,13 @@ def test_two_rank_gather_restores_cell_order():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    got = dict(q.get(timeout=60) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = fake_solve(make_batch())
     for r in range(2):
-        for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton'):
+        for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'):
             assert np.array_equal(got[r][k], want[k]), (r, k)
 
 
