@@ -28,9 +28,15 @@ from . import backend as _be
 FD_ODE_CALCS = ['odeint', 'lsoda', 'vode']
 
 
-def build_cell_batch(tp, rate_mode='summed', points=None):
+def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet', mesh=None):
     """Derive the per-cell parameter records for every point of the descriptor
     grid of ``tp`` (or for the explicit list ``points`` of override dicts).
+
+    poisson_bc  'dirichlet' = the reference FD default (wall potential, bulk gradient,
+                transport.py:207-210); 'stern' = Robin wall condition of the reference's COMSOL path
+                (surface charge C_S*((phiM-phiPZC)-phi(0)), comsol_model.py:613,982) with phi(L)=0
+    mesh        optional normalised node positions xi[n] in [0,1] (non-uniform mesh x = L*xi,
+                same for all cells); default: the reference's uniform mesh
 
     Returns (CellBatch, models) where models[i] is the DerivedModel of cell i
     (light objects; used to label results)."""
@@ -78,18 +84,34 @@ def build_cell_batch(tp, rate_mode='summed', points=None):
         par[c, 2 * S:3 * S] = m.D
         par[c, 3 * S + 0] = m.beta
         par[c, 3 * S + 1] = m.eps
-        wall = m.pb_bound['potential']['wall']
-        gb = m.pb_bound['gradient']['bulk']
-        if wall is None or gb is None:
-            tp.logger.error('| CI | -- | the FD-PNP backend needs pb_bound with a wall potential and a bulk gradient '
-                            '(the reference default, transport.py:207-210)')
-            sys.exit()
-        par[c, 3 * S + 2] = wall
-        par[c, 3 * S + 3] = gb
+        if poisson_bc == 'stern':
+            par[c, 3 * S + 2] = m.system['phiM'] - m.system['phiPZC']
+            par[c, 3 * S + 3] = 0.0
+        else:
+            wall = m.pb_bound['potential']['wall']
+            gb = m.pb_bound['gradient']['bulk']
+            if wall is None or gb is None:
+                tp.logger.error('| CI | -- | the FD-PNP backend needs pb_bound with a wall potential and a bulk '
+                                'gradient (the reference default, transport.py:207-210)')
+                sys.exit()
+            par[c, 3 * S + 2] = wall
+            par[c, 3 * S + 3] = gb
         par[c, 3 * S + 4] = m.system['Stern capacitance'] * 1e-2     # micro F/cm^2 -> F/m^2
-        par[c, 3 * S + 5] = m.dx
-        nx[c] = m.nx
-    batch = _be.CellBatch(z, reactions, nu, par, nx, use_migration=m0.use_migration, species=names)
+        if mesh is None:
+            par[c, 3 * S + 5] = m.dx
+            nx[c] = m.nx
+        else:
+            par[c, 3 * S + 5] = m.xmax                                  # x = L*xi
+            nx[c] = len(mesh)
+    if poisson_bc not in ('dirichlet', 'stern'):
+        tp.logger.error('| CI | -- | unknown poisson_bc "{}"'.format(poisson_bc))
+        sys.exit()
+    kw = {}
+    if mesh is not None:
+        kw = dict(mesh_id=np.zeros(B, dtype=np.int32), mesh_xi=np.asarray(mesh, dtype=np.float64)[None, :])
+    batch = _be.CellBatch(z, reactions, nu, par, nx, use_migration=m0.use_migration, species=names,
+                          poisson_bc=_be.BC_STERN_ROBIN if poisson_bc == 'stern' else _be.BC_DIRICHLET_WALL_NEUMANN_BULK,
+                          **kw)
     return batch, models
 
 
@@ -102,10 +124,13 @@ class Calculator():
 
     def __init__(self, transport=None, dt=None, tmax=None, ntout=1, calc=None,
                  scale_pb_grid=None, tau_jacobi=1e-7, tau_scf=5e-5, mix_scf=0.5, mode='time-dependent',
-                 rtol=1.49012e-8, atol=1.49012e-8, rate_mode='summed', device=None, max_steps=100000):
+                 rtol=1.49012e-8, atol=1.49012e-8, rate_mode='summed', device=None, max_steps=100000,
+                 poisson_bc='dirichlet', mesh=None):
         """Reference keywords (calculator.py:55-56) plus backend options:
         rtol/atol  error tolerances of the BDF integrator (scipy odeint defaults)
         rate_mode  'summed' (default) or 'legacy_overwrite' 
+        poisson_bc 'dirichlet' (reference FD default) or 'stern' (Robin wall of the COMSOL path)
+        mesh       optional normalised non-uniform node positions (see build_cell_batch)
         mode       'time-dependent': state at the output times of the time mesh
                    'stationary': integrate to tmax, then Newton-polish the steady residual
         """
@@ -150,6 +175,8 @@ class Calculator():
         self.tau_jacobi = tau_jacobi
         self.rtol, self.atol = rtol, atol
         self.rate_mode = rate_mode
+        self.poisson_bc = poisson_bc
+        self.mesh = mesh
         self.device = device
         self.max_steps = max_steps
 
@@ -227,7 +254,7 @@ class Calculator():
         tp = self.tp
         t0 = time.time()
         keys = list(tp.descriptors)
-        batch, models = build_cell_batch(tp, rate_mode=self.rate_mode)
+        batch, models = build_cell_batch(tp, rate_mode=self.rate_mode, poisson_bc=self.poisson_bc, mesh=self.mesh)
         for i1, v1 in enumerate(tp.descriptors[keys[0]]):
             for i2, v2 in enumerate(tp.descriptors[keys[1]]):
                 tp.logger.debug('| CI | -- | cell {} : {} = {} and {} = {}'.format(

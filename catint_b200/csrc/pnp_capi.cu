@@ -9,9 +9,12 @@
 #include "pnp_rhs.cuh"
 
 namespace catint {
-#define X(NB) extern template int launch_bdf<NB>(SolveParams&, cudaStream_t); \
-              extern template int launch_jac<NB>(JacParams&, cudaStream_t);
+#define X(NB) extern template int launch_bdf<NB, false>(SolveParams&, cudaStream_t); \
+              extern template int launch_jac<NB, false>(JacParams&, cudaStream_t);
 X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+#undef X
+#define X(NB) extern template int launch_bdf<NB, true>(SolveParams&, cudaStream_t);
+X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 #undef X
 }
 
@@ -130,21 +133,21 @@ static int check_cuda(const char* what) {
     return CATINT_PNP_OK;
 }
 
-#define DISPATCH_NB(NBVAL, CALL, ...)                        \
-    switch (NBVAL) {                                         \
-        case 2: rc = CALL<2>(__VA_ARGS__); break;            \
-        case 3: rc = CALL<3>(__VA_ARGS__); break;            \
-        case 4: rc = CALL<4>(__VA_ARGS__); break;            \
-        case 5: rc = CALL<5>(__VA_ARGS__); break;            \
-        case 6: rc = CALL<6>(__VA_ARGS__); break;            \
-        case 7: rc = CALL<7>(__VA_ARGS__); break;            \
-        case 8: rc = CALL<8>(__VA_ARGS__); break;            \
-        case 9: rc = CALL<9>(__VA_ARGS__); break;            \
-        case 10: rc = CALL<10>(__VA_ARGS__); break;          \
-        case 11: rc = CALL<11>(__VA_ARGS__); break;          \
-        case 12: rc = CALL<12>(__VA_ARGS__); break;          \
-        case 13: rc = CALL<13>(__VA_ARGS__); break;          \
-        default: rc = fail(CATINT_PNP_EINVAL, "unsupported block size (S+1 must be 2..13)"); \
+#define DISPATCH_NB(NBVAL, CALL, STV, ...)                          \
+    switch (NBVAL) {                                                \
+        case 2: rc = CALL<2, false>(__VA_ARGS__); break;            \
+        case 3: rc = CALL<3, STV>(__VA_ARGS__); break;              \
+        case 4: rc = CALL<4, STV>(__VA_ARGS__); break;              \
+        case 5: rc = CALL<5, STV>(__VA_ARGS__); break;              \
+        case 6: rc = CALL<6, STV>(__VA_ARGS__); break;              \
+        case 7: rc = CALL<7, STV>(__VA_ARGS__); break;              \
+        case 8: rc = CALL<8, STV>(__VA_ARGS__); break;              \
+        case 9: rc = CALL<9, STV>(__VA_ARGS__); break;              \
+        case 10: rc = CALL<10, STV>(__VA_ARGS__); break;            \
+        case 11: rc = CALL<11, STV>(__VA_ARGS__); break;            \
+        case 12: rc = CALL<12, STV>(__VA_ARGS__); break;            \
+        case 13: rc = CALL<13, STV>(__VA_ARGS__); break;            \
+        default: rc = fail(CATINT_PNP_EINVAL, "unsupported block size (2..13 unknowns per node)"); \
     }
 
 static int check_common(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells) {
@@ -152,8 +155,6 @@ static int check_common(const CatintPnpShared* sh, const CatintPnpCells* cells, 
     if (n_cells <= 0) return fail(CATINT_PNP_EINVAL, "n_cells must be positive");
     if (!cells->par || !cells->nx) return fail(CATINT_PNP_EINVAL, "cells->par / cells->nx are NULL");
     if (sh->n_mesh > 0 && !cells->mesh_xi) return fail(CATINT_PNP_EINVAL, "mesh table missing");
-    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
-        return fail(CATINT_PNP_EINVAL, "Stern/Robin Poisson boundary is not available in this build");
     if (catint_pnp_device_count() <= 0) return fail(CATINT_PNP_ENODEV, "no sm_100 CUDA device visible");
     return CATINT_PNP_OK;
 }
@@ -163,6 +164,8 @@ extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCe
                                     void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_rhs_batch: Stern/Robin Poisson boundary not available (use catint_pnp_solve_batch)");
     if (!c || !dcdt) return fail(CATINT_PNP_EINVAL, "c / dcdt are NULL");
     RhsParams P;
     rc = build_tables(sh, P.tb);
@@ -186,6 +189,8 @@ extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const Catint
                                          void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_jacobian_batch: Stern/Robin Poisson boundary not available");
     if (!y) return fail(CATINT_PNP_EINVAL, "y is NULL");
     JacParams P;
     rc = build_tables(sh, P.tb);
@@ -193,7 +198,7 @@ extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const Catint
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
     P.y = y; P.n_cells = n_cells; P.F = F; P.Lb = Lb; P.Db = Db; P.Ub = Ub;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    DISPATCH_NB(block_size_of(sh), launch_jac, P, st);
+    DISPATCH_NB(block_size_of(sh), launch_jac, false, P, st);
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_jacobian_kernel launch failed");
     return rc;
 }
@@ -236,7 +241,11 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
     P.ws = wsd; P.ws_stride = (long long)ws_doubles_per_cell(sh);
     P.state_in_smem = 1;
     P.prof = g_prof;
-    DISPATCH_NB(block_size_of(sh), launch_bdf, P, st);
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN) {
+        DISPATCH_NB(block_size_of(sh), launch_bdf, true, P, st);
+    } else {
+        DISPATCH_NB(block_size_of(sh), launch_bdf, false, P, st);
+    }
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
     return rc;
 }

@@ -48,26 +48,55 @@ struct SolveParams {
 // g from the concentrations stored in y (default Poisson BCs): g_{n-1}=g_bulk,
 // g_i = g_{i+1} + h_i*sum_k q_k c_{k,i}/eps, g_0 by linear extrapolation
 // (calculator_old.py:753-759,793-796).  Sequential, one lane; y is [n][NB].
-template <int NB>
-__device__ void consistent_field(const WarpState<NB>& ws, double* y) {
-    constexpr int S = NB - 1;
+template <int NB, bool ST>
+__device__ void consistent_field(const WarpState<NB, ST>& ws, double* y) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int n = ws.cs.n;
     if (ws.lane == 0) {
         if (!ws.tb->use_migration) {
-            for (int i = 0; i < n; ++i) y[(size_t)i * NB + S] = 0.0;
+            for (int i = 0; i < n; ++i) {
+                y[(size_t)i * NB + S] = 0.0;
+                if (ST) y[(size_t)i * NB + S + 1] = 0.0;
+            }
         } else {
-            double g = ws.cs.g_bulk;
-            y[(size_t)(n - 1) * NB + S] = g;
+            // T_i = sum_{j=i}^{n-2} lapl_j*h_j ; g_i = g_{n-1} - T_i
+            double T = 0.0;
+            y[(size_t)(n - 1) * NB + S] = 0.0;
             for (int i = n - 2; i >= 1; --i) {
                 const NodeCoef k = interior_coef(ws.cs, i);
                 double lapl = 0.0;
                 for (int s = 0; s < S; ++s) lapl -= ws.sp->q[s] * y[(size_t)i * NB + s] / ws.cs.eps;
-                g = g - lapl * k.hi;
-                y[(size_t)i * NB + S] = g;
+                T += lapl * k.hi;
+                y[(size_t)i * NB + S] = -T;
             }
             const WallCoef w = wall_coef(ws.cs);
+            double gb = ws.cs.g_bulk;
+            if (ST) {
+                // Robin wall + phi(L)=0 close the affine dependence on g_{n-1}:
+                //   g_0 = gb - A,  phi_0 = -gb*L + B,  (eps/Cs)*g_0 + (phiM-phiPZC) - phi_0 = 0
+                const double T1 = -y[NB + S], T2 = -y[2 * NB + S];
+                const double A = T1 + (T1 - T2) * w.ext;
+                double B = 0.0, L = 0.0;
+                for (int i = 1; i <= n - 1; ++i) {
+                    const NodeCoef k = interior_coef(ws.cs, i < n - 1 ? i : n - 2);
+                    const double him = i < n - 1 ? k.him : k.hi;
+                    B += (-y[(size_t)i * NB + S]) * him;
+                    L += him;
+                }
+                const double ec = ws.cs.eps / ws.cs.cstern;
+                gb = (ec * A - ws.cs.phi_wall + B) / (ec + L);
+            }
+            for (int i = 1; i <= n - 1; ++i) y[(size_t)i * NB + S] += gb;
             const double g1 = y[NB + S], g2 = y[2 * NB + S];
             y[S] = g1 + (g1 - g2) * w.ext;
+            if (ST) {
+                y[(size_t)(n - 1) * NB + S + 1] = 0.0;
+                for (int i = n - 1; i >= 1; --i) {
+                    const NodeCoef k = interior_coef(ws.cs, i < n - 1 ? i : n - 2);
+                    const double him = i < n - 1 ? k.him : k.hi;
+                    y[(size_t)(i - 1) * NB + S + 1] = y[(size_t)i * NB + S + 1] - y[(size_t)i * NB + S] * him;
+                }
+            }
         }
     }
     __syncwarp();
@@ -76,15 +105,15 @@ __device__ void consistent_field(const WarpState<NB>& ws, double* y) {
 // ===========================================================================
 // K3: the integrator
 // ===========================================================================
-template <int NB>
+template <int NB, bool ST>
 struct Bdf {
     int q, qwait, nst;
     double h, hscale, t, etamax, saved_tq5;
     double tau[QMAX + 2], l[QMAX + 2], tq[6];
 };
 
-template <int NB>
-__device__ void set_bdf(Bdf<NB>& B) {
+template <int NB, bool ST>
+__device__ void set_bdf(Bdf<NB, ST>& B) {
     const int q = B.q;
     const double h = B.h;
     double* l = B.l; double* tq = B.tq; const double* tau = B.tau;
@@ -127,8 +156,8 @@ __device__ void set_bdf(Bdf<NB>& B) {
 }
 
 // coefficients for an order increase / decrease (applied inside the begin-step pass)
-template <int NB>
-__device__ void increase_coef(const Bdf<NB>& B, double* l, double& A1) {
+template <int NB, bool ST>
+__device__ void increase_coef(const Bdf<NB, ST>& B, double* l, double& A1) {
     const int q = B.q;
     for (int i = 0; i < QMAX + 2; ++i) l[i] = 0.0;
     double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0, hsum = B.hscale;
@@ -147,8 +176,8 @@ __device__ void increase_coef(const Bdf<NB>& B, double* l, double& A1) {
     A1 = (-alpha0 - alpha1) / prod;
 }
 
-template <int NB>
-__device__ void decrease_coef(const Bdf<NB>& B, double* l) {
+template <int NB, bool ST>
+__device__ void decrease_coef(const Bdf<NB, ST>& B, double* l) {
     const int q = B.q;
     for (int i = 0; i < QMAX + 2; ++i) l[i] = 0.0;
     l[2] = 1.0;
@@ -167,8 +196,8 @@ __device__ void decrease_coef(const Bdf<NB>& B, double* l) {
 //   (predict) Pascal triangle
 //   y = zn[0], psi = rl1*zn[1] - zn[0]
 // q_old is the order the array currently has, q_new the order after the change.
-template <int NB>
-__device__ void history_pass(WarpState<NB>& ws, int q_old, int dq, bool undo, double eta,
+template <int NB, bool ST>
+__device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo, double eta,
                              const double* lc, double A1, double rl1, bool predict) {
     const int N = ws.N;
     const int q_new = q_old + dq;
@@ -228,9 +257,9 @@ __device__ void history_pass(WarpState<NB>& ws, int q_old, int dq, bool undo, do
 // SMEM = true: the Newton iterate, psi and the rhs/update vector live in shared memory and are
 // addressed with LDS/STS (a generic pointer would queue these critical-path accesses behind the
 // global prefetch loads in the L1TEX pipeline); SMEM = false: large grids, state in the workspace.
-template <int NB, bool SMEM>
+template <int NB, bool ST, bool SMEM>
 __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
-    constexpr int S = NB - 1;
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int WARPS = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -247,14 +276,14 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
-    const size_t state_doubles = (size_t)RING * (fac_rec<NB>() + 2 * padded<NB>()) + (SMEM ? (size_t)2 * nxm * NB : 0);
+    const size_t state_doubles = (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>()) + (SMEM ? (size_t)2 * nxm * NB : 0);
     const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
-                            (size_t)(scratch_doubles<NB>() + state_doubles) * sizeof(double);
+                            (size_t)(scratch_doubles<NB, ST>() + state_doubles) * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
     if (cell >= P.n_cells) return;
 
     const long long t_kernel0 = clock64();
-    WarpState<NB> ws;
+    WarpState<NB, ST> ws;
     ws.lane = lane;
     ws.tb = tb;
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
@@ -265,15 +294,15 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     const int N = n * NB;
     ws.N = N;
     double* g = P.ws + (size_t)cell * P.ws_stride;
-    constexpr int NBP = padded<NB>();
+    constexpr int NBP = padded<NB, ST>();
     ws.zn = g;                 g += align4((size_t)LMAX * nxm * NB);
     ws.ewt = g;                g += align4((size_t)nxm * NB);
-    ws.fac = g;                g += align4((size_t)nxm * fac_rec<NB>());
+    ws.fac = g;                g += align4((size_t)nxm * fac_rec<NB, ST>());
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
     ws.psi = g;                g += align4((size_t)nxm * NB);
-    double* sdyn = ws.scratch + scratch_doubles<NB>();
-    ws.ring = sdyn;            sdyn += (size_t)RING * (fac_rec<NB>() + 2 * padded<NB>());
+    double* sdyn = ws.scratch + scratch_doubles<NB, ST>();
+    ws.ring = sdyn;            sdyn += (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
     if constexpr (SMEM) {
         ws.y = sdyn; ws.zb = sdyn + (size_t)nxm * NB;
     } else {
@@ -289,7 +318,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         ws.psi[idx] = 0.0;
     }
     __syncwarp();
-    consistent_field<NB>(ws, ws.y);
+    consistent_field<NB, ST>(ws, ws.y);
 
     const double rtol = P.rtol, atol = P.atol;
 
@@ -298,7 +327,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     for (int idx = lane; idx < N; idx += 32) {
         const int i = idx / NB, r = idx - i * NB;
         const bool mass = r < S && i < n - 1;
-        const double F = mass ? row_residual<NB>(ws, ws.y, i, r) : 0.0;
+        const double F = mass ? row_residual<NB, ST>(ws, ws.y, i, r) : 0.0;
         const double yv = ws.y[idx];
         const double w = 1.0 / (rtol * fabs(yv) + atol);
         ws.ewt[idx] = w;
@@ -309,7 +338,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     __syncwarp();
     fnorm = warp_max(fnorm);
 
-    Bdf<NB> B;
+    Bdf<NB, ST> B;
     B.q = 1; B.qwait = 2; B.nst = 0; B.t = 0.0; B.etamax = ETAMX1; B.saved_tq5 = 0.0;
     for (int i = 0; i < QMAX + 2; ++i) { B.tau[i] = 0.0; B.l[i] = 0.0; }
     const double t_end = P.t_out[P.n_out - 1];
@@ -345,15 +374,15 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         while (true) {
             // order change (only on the first attempt) + rescale + predict, fused
             const int q_old = B.q;
-            if (pend_dq > 0) increase_coef<NB>(B, lc, A1c);
-            else if (pend_dq < 0) decrease_coef<NB>(B, lc);
+            if (pend_dq > 0) increase_coef<NB, ST>(B, lc, A1c);
+            else if (pend_dq < 0) decrease_coef<NB, ST>(B, lc);
             if (pend_dq != 0) { B.q += pend_dq; B.qwait = B.q + 1; }
             if (pend_eta != 1.0) { B.h = B.hscale * pend_eta; B.hscale = B.h; }
             if (saved_t + B.h == saved_t) { status = CATINT_PNP_CELL_STEP_UNDERFLOW; break; }   // t+h == t
             B.t = saved_t + B.h;
-            set_bdf<NB>(B);
+            set_bdf<NB, ST>(B);
             const double rl1 = 1.0 / B.l[1];
-            { CATINT_TIC; history_pass<NB>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true); CATINT_TOC(5); }
+            { CATINT_TIC; history_pass<NB, ST>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true); CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
 
@@ -375,7 +404,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 }
                 if (call_setup) {
                     CATINT_TIC;
-                    const bool ok = factor_sweep<NB>(ws, inv_gamma);
+                    const bool ok = factor_sweep<NB, ST>(ws, inv_gamma);
                     CATINT_TOC(0);
                     ++nsetups;
                     have_factors = ok;
@@ -389,10 +418,10 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 double crate = 1.0, delp = 0.0;
                 bool bad = false;
                 for (int m = 0; m < MAXCOR; ++m) {
-                    { CATINT_TIC; residual_pass<NB>(ws, inv_gamma); CATINT_TOC(1); }
-                    { CATINT_TIC; forward_solve<NB>(ws); CATINT_TOC(2); }
+                    { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); CATINT_TOC(1); }
+                    { CATINT_TIC; forward_solve<NB, ST>(ws); CATINT_TOC(2); }
                     double del, acn;
-                    { CATINT_TIC; backward_solve<NB>(ws, dscale, del, acn, 0, 0.0, 0.0); CATINT_TOC(3); }
+                    { CATINT_TIC; backward_solve<NB, ST>(ws, dscale, del, acn, 0, 0.0, 0.0); CATINT_TOC(3); }
                     ++nni;
                     if (!(del <= 1e300)) { bad = true; break; }
                     if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
@@ -432,7 +461,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 pend_eta = ETAMIN;
             } else {
                 // order 1 and still failing: restart the history from the last accepted state
-                history_pass<NB>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
+                history_pass<NB, ST>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
                 pend_undo = false;
                 B.h *= ETAMIN; B.hscale = B.h;
                 B.qwait = LONG_WAIT;
@@ -441,7 +470,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 for (int idx = lane; idx < N; idx += 32) {
                     const int i = idx / NB, r = idx - i * NB;
                     const bool mass = r < S && i < n - 1;
-                    ws.zn[(size_t)N + idx] = mass ? B.h * row_residual<NB>(ws, ws.y, i, r) : 0.0;
+                    ws.zn[(size_t)N + idx] = mass ? B.h * row_residual<NB, ST>(ws, ws.y, i, r) : 0.0;
                 }
                 __syncwarp();
             }
@@ -554,7 +583,25 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 if (last) ws.y[idx] = v;           // kept for the steady polish / final outputs
                 if (!(last && P.mode == CATINT_PNP_MODE_STEADY)) {
                     if (r < S) co[(size_t)i * S + r] = v;
-                    else if (go) go[i] = v;
+                    else if (r == S) { if (go) go[i] = v; }
+                    else if (P.phi_out) P.phi_out[((size_t)iout * P.n_cells + cell) * nxm + i] = v;
+                }
+            }
+            __syncwarp();
+            if (!ST && !last && P.phi_out && go && lane == 0) {
+                // potential of an intermediate output: forward cumulative sum of the g just written
+                double* po2 = P.phi_out + ((size_t)iout * P.n_cells + cell) * nxm;
+                double v = ws.cs.phi_wall, vm1 = v, vm2 = v;
+                po2[0] = v;
+                for (int i = 1; i <= n - 2; ++i) {
+                    const NodeCoef kc = interior_coef(ws.cs, i);
+                    v = v + go[i] * kc.him;
+                    po2[i] = v; vm2 = vm1; vm1 = v;
+                }
+                if (n >= 3) {
+                    const double ratio = ws.cs.uniform ? 1.0 :
+                        (ws.cs.xi[n - 1] - ws.cs.xi[n - 2]) / (ws.cs.xi[n - 2] - ws.cs.xi[n - 3]);
+                    po2[n - 1] = vm1 + (vm1 - vm2) * ratio;
                 }
             }
             __syncwarp();
@@ -571,18 +618,22 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         cscale = warp_max(cscale);
         const double patol = 1e-12 * fmax(cscale, 1e-300);
         bool done = false;
+        double del_prev = 0.0;
         for (int it = 0; it < P.polish_max_iter && !done; ++it) {
             // true Newton on the steady residual: inv_gamma = 0 removes the mass term
-            const bool ok = factor_sweep<NB>(ws, 0.0);
+            const bool ok = factor_sweep<NB, ST>(ws, 0.0);
             ++nsetups;
             if (!ok) break;
-            residual_pass<NB>(ws, 0.0);
-            forward_solve<NB>(ws);
+            residual_pass<NB, ST>(ws, 0.0);
+            forward_solve<NB, ST>(ws);
             double del, acn;
-            backward_solve<NB>(ws, 1.0, del, acn, 1, P.polish_rtol, patol);
+            backward_solve<NB, ST>(ws, 1.0, del, acn, 1, P.polish_rtol, patol);
             ++nni;
             if (!(del <= 1e300)) break;
-            if (del <= 1.0) done = true;
+            // converged, or stagnating at the rounding floor of the linear solve with an update that is
+            // already below 1e-8 relative (two orders under the 1e-6 parity tolerance)
+            if (del <= 1.0 || (it >= 1 && del > 0.5 * del_prev && del * P.polish_rtol <= 1e-8)) done = true;
+            del_prev = del;
         }
         if (!done) status = CATINT_PNP_CELL_POLISH_FAILED;
     }
@@ -598,12 +649,14 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 const int i = idx / NB, r = idx - i * NB;
                 const double v = ws.y[idx];
                 if (r < S) co[(size_t)i * S + r] = v;
-                else if (go) go[i] = v;
+                else if (r == S) { if (go) go[i] = v; }
+                else if (po) po[i] = v;
             }
         }
         __syncwarp();
-        // potential by the forward cumulative sum of the reference (calculator_old.py:798-800)
-        if (po && lane == 0) {
+        // potential by the forward cumulative sum of the reference (calculator_old.py:798-800);
+        // in Stern mode phi is an unknown of the state and has been written above
+        if (!ST && po && lane == 0) {
             double v = ws.cs.phi_wall;
             po[0] = v;
             double vm1 = v, vm2 = v;
@@ -648,9 +701,9 @@ struct JacParams {
     double* F; double* Lb; double* Db; double* Ub;
 };
 
-template <int NB>
+template <int NB, bool ST>
 __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
-    constexpr int S = NB - 1;
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int WARPS = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -664,10 +717,10 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     }
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB, ST>() * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
     if (cell >= P.n_cells) return;
-    WarpState<NB> ws;
+    WarpState<NB, ST> ws;
     ws.lane = lane; ws.tb = tb;
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
     ws.sp = sp;
@@ -679,10 +732,10 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
     for (int i = 0; i < n; ++i) {
         __syncwarp();
-        node_coeffs<NB>(ws, y, i, sl, sa, sud, sua);
+        node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
         __syncwarp();
         const size_t nb = ((size_t)cell * nxm + i);
-        if (P.F && lane < NB) P.F[nb * NB + lane] = row_residual<NB>(ws, y, i, lane);
+        if (P.F && lane < NB) P.F[nb * NB + lane] = row_residual<NB, ST>(ws, y, i, lane);
         // blocks are d(row)/d(col) of F itself (not of the Newton matrix)
         if (lane < NB) {
             const int j = lane;     // column
@@ -740,12 +793,12 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
 // launchers (explicitly instantiated per block size in pnp_inst.cu)
 // ===========================================================================
 namespace catint {
-template <int NB>
+template <int NB, bool ST>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
     const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
     const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
-                                  (size_t)(scratch_doubles<NB>() + RING * (fac_rec<NB>() + 2 * padded<NB>())) * sizeof(double);
+                                  (size_t)(scratch_doubles<NB, ST>() + RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>())) * sizeof(double);
     const size_t state = (size_t)2 * P.tb.nx_max * NB * sizeof(double);
     int dev = 0; cudaGetDevice(&dev);
     int max_optin = 0;
@@ -754,25 +807,25 @@ int launch_bdf(SolveParams& P, cudaStream_t st) {
     const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
     if (smem_state <= (size_t)max_optin) {
         P.state_in_smem = 1;
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
-        pnp_bdf_kernel<NB, true><<<grid, WARPS * 32, smem_state, st>>>(P);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
+        pnp_bdf_kernel<NB, ST, true><<<grid, WARPS * 32, smem_state, st>>>(P);
     } else {
         P.state_in_smem = 0;
         const size_t smem = base + WARPS * per_warp_fixed;
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pnp_bdf_kernel<NB, false><<<grid, WARPS * 32, smem, st>>>(P);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pnp_bdf_kernel<NB, ST, false><<<grid, WARPS * 32, smem, st>>>(P);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 
-template <int NB>
+template <int NB, bool ST>
 int launch_jac(JacParams& P, cudaStream_t st) {
     const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB>() * sizeof(double);
+    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + (size_t)scratch_doubles<NB, ST>() * sizeof(double);
     const size_t smem = base + WARPS * per_warp;
     const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
-    pnp_jacobian_kernel<NB><<<grid, WARPS * 32, smem, st>>>(P);
+    pnp_jacobian_kernel<NB, ST><<<grid, WARPS * 32, smem, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 

@@ -24,7 +24,7 @@
 
 namespace catint {
 
-template <int NB>
+template <int NB, bool ST>
 struct WarpState {
     double* y;      // current Newton iterate              [n*NB]   (shared or global)
     double* psi;    // rl1*zn1 - zn0 (mass rows)           [n*NB]
@@ -43,16 +43,16 @@ struct WarpState {
     int lane;
 };
 
-template <int NB>
+template <int NB, bool ST>
 __host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }
 // sub-arrays of the per-cell workspace start on 32-byte boundaries
 __host__ __device__ constexpr size_t align4(size_t doubles) { return (doubles + 3) & ~size_t(3); }
 // padded row length of the stored blocks (even -> 16-byte aligned rows, double2 loads)
-template <int NB>
+template <int NB, bool ST>
 __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 // doubles per node of the stored factors: inverse block (padded rows) + 4 coefficients per row
-template <int NB>
-__host__ __device__ constexpr int fac_rec() { return NB * padded<NB>() + NB * 4; }
+template <int NB, bool ST>
+__host__ __device__ constexpr int fac_rec() { return NB * padded<NB, ST>() + NB * 4; }
 constexpr int RING = 8;   // node records in flight in the solve sweeps
 
 // ---------------------------------------------------------------------------
@@ -60,7 +60,7 @@ constexpr int RING = 8;   // node records in flight in the solve sweeps
 // (columns >= NB are right-hand sides).  The pivot column travels through shared
 // memory (one writer, broadcast reads).  A row swap is a warp-uniform branch, so
 // it only costs when it happens.  Returns false on a zero/non-finite pivot.
-template <int NB>
+template <int NB, bool ST>
 __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* pivbuf) {
     bool ok = true;
 #pragma unroll
@@ -113,23 +113,29 @@ __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* 
 // ---------------------------------------------------------------------------
 // residual of row r at node i:  transport rows dc/dt, algebraic rows -constraint
 // (the g-row of interior nodes is returned UNSCALED)
-template <int NB>
-__device__ __forceinline__ double row_residual(const WarpState<NB>& ws, const double* y, int i, int r) {
-    constexpr int S = NB - 1;
+template <int NB, bool ST>
+__device__ __forceinline__ double row_residual(const WarpState<NB, ST>& ws, const double* y, int i, int r) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int n = ws.cs.n;
     const DevTables& tb = *ws.tb;
     const double* y0 = y + (size_t)i * NB;
+    constexpr int P = S + 1;      // phi unknown / row (Stern mode only)
     if (i == 0) {
         const WallCoef w = wall_coef(ws.cs);
         const double* y1 = y + NB;
         const double* y2 = y + 2 * NB;
         if (r < S)
             return (ws.sp->D[r] * ((y2[r] - y0[r]) * w.w0 + ws.sp->bq[r] * y1[r] * y1[S]) + ws.sp->J[r]) * w.ih0;
-        return tb.use_migration ? -(y0[S] - y1[S] - (y1[S] - y2[S]) * w.ext) : -y0[S];
+        if (r == S) return tb.use_migration ? -(y0[S] - y1[S] - (y1[S] - y2[S]) * w.ext) : -y0[S];
+        // Robin (Stern layer) wall condition: eps*g_0 = -C_S*((phiM-phiPZC) - phi_0)
+        return -((ws.cs.eps / ws.cs.cstern) * y0[S] + ws.cs.phi_wall - y0[P]);
     }
     if (i == n - 1) {
         if (r < S) return ws.sp->cb[r] - y0[r];
-        return (tb.use_migration ? ws.cs.g_bulk : 0.0) - y0[S];
+        if (!ST) return (tb.use_migration ? ws.cs.g_bulk : 0.0) - y0[S];
+        if (r == S) return -y0[P];                                           // phi(L) = 0
+        const NodeCoef k = interior_coef(ws.cs, i - 1);
+        return -(y0[P] - (y0 - NB)[P] - y0[S] * k.hi);                        // phi recursion, h_{n-2}
     }
     const NodeCoef k = interior_coef(ws.cs, i);
     const double* ym = y0 - NB;
@@ -144,19 +150,22 @@ __device__ __forceinline__ double row_residual(const WarpState<NB>& ws, const do
         return ws.sp->D[r] * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp
                               + ws.sp->bq[r] * k.ac * (cp * yp[S] - cm * ym[S])) + R;
     }
-    if (!tb.use_migration) return -y0[S];
-    double rho = 0.0;
-    for (int s = 0; s < S; ++s) rho += ws.sp->qe[s] * y0[s];
-    return -(y0[S] - yp[S] - rho * k.hi);
+    if (r == S) {
+        if (!tb.use_migration) return -y0[S];
+        double rho = 0.0;
+        for (int s = 0; s < S; ++s) rho += ws.sp->qe[s] * y0[s];
+        return -(y0[S] - yp[S] - rho * k.hi);
+    }
+    return -(y0[P] - ym[P] - y0[S] * k.him);                                  // phi_i = phi_{i-1} + g_i*h_{i-1}
 }
 
 // Jacobian coefficients of row r (= lane) at node i, published through shared memory:
 //   interior: sl,sa = dF_r/dc_{r,i-1}, dF_r/dg_{i-1};  sud,sua = dF_r/dc_{r,i+1}, dF_r/dg_{i+1}
 //   wall:     sa = dF_r/dy_{r,0} (diagonal), sud,sua w.r.t. node 1, sl = dF_r/dy_{r,2} (extra block)
-template <int NB>
-__device__ __forceinline__ void node_coeffs(const WarpState<NB>& ws, const double* y, int i,
+template <int NB, bool ST>
+__device__ __forceinline__ void node_coeffs(const WarpState<NB, ST>& ws, const double* y, int i,
                                             double* sl, double* sa, double* sud, double* sua) {
-    constexpr int S = NB - 1;
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int r = ws.lane;
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
@@ -172,9 +181,11 @@ __device__ __forceinline__ void node_coeffs(const WarpState<NB>& ws, const doubl
             ua = Dr * bq * y1[r] * w.ih0;
             l = Dr * w.w0 * w.ih0;
             a = -l;
-        } else {
+        } else if (r == S) {
             if (mig) { ud = 1.0 + w.ext; l = -w.ext; }
             a = -1.0;
+        } else {
+            a = 1.0;                       // dF_phi/dphi_0 (the (phi,g) entry is added in the assembly)
         }
     } else if (i < n - 1) {
         const NodeCoef k = interior_coef(ws.cs, i);
@@ -186,19 +197,23 @@ __device__ __forceinline__ void node_coeffs(const WarpState<NB>& ws, const doubl
             a = -Dr * bq * k.ac * ym[r];
             ud = Dr * (k.ap + bq * k.ac * yp[S]);
             ua = Dr * bq * k.ac * yp[r];
-        } else if (mig) {
-            ud = 1.0;
+        } else if (r == S) {
+            if (mig) ud = 1.0;
+        } else {
+            l = 1.0;                       // dF_phi/dphi_{i-1}
         }
+    } else if (ST && r == S + 1) {
+        l = 1.0;                           // bulk node, phi recursion row: dF/dphi_{n-2}
     }
     sl[r] = l; sa[r] = a; sud[r] = ud; sua[r] = ua;
 }
 
 // column j (< NB) of A_D = Mass*inv_gamma - dF_i/dy_i at an interior node, g-row scaled by sg
-template <int NB>
-__device__ __forceinline__ void interior_diag_column(const WarpState<NB>& ws, const double* yi, int j,
+template <int NB, bool ST>
+__device__ __forceinline__ void interior_diag_column(const WarpState<NB, ST>& ws, const double* yi, int j,
                                                      const NodeCoef& k, double inv_gamma, double sg,
                                                      double (&A)[NB]) {
-    constexpr int S = NB - 1;
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const DevTables& tb = *ws.tb;
 #pragma unroll
     for (int r = 0; r < NB; ++r) A[r] = 0.0;
@@ -217,8 +232,11 @@ __device__ __forceinline__ void interior_diag_column(const WarpState<NB>& ws, co
         for (int r = 0; r < S; ++r)
             if (r == j) A[r] += dd;
         if (tb.use_migration) A[S] = -tb.z[j];          // -(q_j*h/eps)*sg
-    } else {
+    } else if (j == S) {
         A[S] = tb.use_migration ? sg : 1.0;
+        if (ST) A[NB - 1] = -k.him;                // -dF_phi/dg_i
+    } else {
+        A[NB - 1] = 1.0;                           // -dF_phi/dphi_i
     }
 }
 
@@ -226,10 +244,10 @@ __device__ __forceinline__ void interior_diag_column(const WarpState<NB>& ws, co
 // Factorisation sweep.  Lanes: D = 0..NB-1 (columns of A_D'), I = NB..2NB-1 (identity ->
 // inverse), G = 2NB (g-column of A_U -> W[:,g]).  Stores inv_i (all nodes), the sparse
 // coefficients of A_L/A_U (la), V_0 and the dense W_1.
-template <int NB>
-__device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
-    constexpr int S = NB - 1;
-    constexpr int NBP = padded<NB>();
+template <int NB, bool ST>
+__device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
@@ -246,15 +264,18 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
     bool ok = true;
     const double* y = ws.y;
 
-    for (int i = 0; i < n - 1; ++i) {
+    const int n_fac = ST ? n : n - 1;      // Stern mode: the bulk node couples phi_{n-1} to phi_{n-2}
+    for (int i = 0; i < n_fac; ++i) {
         __syncwarp();
-        node_coeffs<NB>(ws, y, i, sl, sa, sud, sua);
+        node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
         __syncwarp();
         const double* yi = y + (size_t)i * NB;
-        double* rec = ws.fac + (size_t)i * fac_rec<NB>();
+        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
         double* invcol = rec + j;                                   // column j of inv_i (I lanes)
-        const NodeCoef k = (i > 0) ? interior_coef(ws.cs, i) : NodeCoef{0, 0, 0, 1, 1};
-        const double sg = (i > 0 && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
+        const bool bulk = (i == n - 1);
+        const NodeCoef k = bulk ? interior_coef(ws.cs, i - 1)
+                                : ((i > 0) ? interior_coef(ws.cs, i) : NodeCoef{0, 0, 0, 1, 1});
+        const double sg = (i > 0 && !bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
         if (lane < NB) {
             double4 v;
             v.x = sl[lane]; v.y = sa[lane];
@@ -271,11 +292,12 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r)
                     if (r == j) A[r] = isD ? ((j < S ? inv_gamma : 0.0) - sa[r]) : 1.0;
+                if (ST && isD && j == S) A[NB - 1] = ws.cs.eps / ws.cs.cstern;      // -dF_phi/dg_0 (Robin row)
             } else if (isG) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r];
             }
-            ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
+            ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
             double Wc[NB];
 #pragma unroll
             for (int r = 0; r < NB; ++r) Wc[r] = A[r];
@@ -303,10 +325,20 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
         // ---- interior node: column j of [A_D' | I | u_g] ----
         double Dsave[NB];
         if (isD) {
-            interior_diag_column<NB>(ws, yi, j, k, inv_gamma, sg, A);
+            if (!bulk) {
+                interior_diag_column<NB, ST>(ws, yi, j, k, inv_gamma, sg, A);
+            } else {
+                // Stern bulk node: c rows identity; row S: phi_{n-1} = 0; row P: phi recursion with h_{n-2}
+#pragma unroll
+                for (int r = 0; r < S; ++r)
+                    if (r == j) A[r] = 1.0;
+                if (j == S) A[NB - 1] = -k.hi;
+                if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
+            }
             const double wg = Wp[S];
 #pragma unroll
             for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;     // A_D - A_L*W_{i-1}
+            if (ST) A[NB - 1] += sl[NB - 1] * Wp[NB - 1];                       // phi row: A_L = -1 on the diagonal
             if (i == 1) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r) Dsave[r] = A[r];
@@ -319,7 +351,7 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r] * sg;
         }
-        ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
+        ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
         double Wc[NB];
 #pragma unroll
         for (int r = 0; r < NB; ++r) Wc[r] = A[r];
@@ -348,10 +380,11 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
                     if (r == j) v = (r < S) ? -sud[r] : -sud[r] * sg;
                     if (j == S && r < S) v = -sua[r];
                     if (r < S) v += sl[r] * Wp[r] + sa[r] * vg;
+                    if (ST && r == NB - 1) v += sl[r] * Wp[r];
                     A[r] = v;
                 }
             }
-            ok = gauss_jordan<NB>(A, lane, pivbuf) && ok;
+            ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
 #pragma unroll
             for (int r = 0; r < NB; ++r) Wc[r] = A[r];
             if (isI) {
@@ -367,10 +400,10 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
 #pragma unroll
         for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
     }
-    // bulk node: identity rows, no coupling
-    {
+    // bulk node (default Poisson BCs): identity rows, no coupling
+    if (!ST) {
         const int i = n - 1;
-        double* rec = ws.fac + (size_t)i * fac_rec<NB>();
+        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
         for (int e = lane; e < NB * NBP; e += 32) rec[e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
         if (lane < NB) reinterpret_cast<double4*>(rec + NB * NBP)[lane] = make_double4(0, 0, 0, 0);
     }
@@ -381,9 +414,9 @@ __device__ bool factor_sweep(WarpState<NB>& ws, double inv_gamma) {
 // ---------------------------------------------------------------------------
 // rhs = F(y) - Mass*(y+psi)*inv_gamma for every unknown; one lane per node.
 // The g-row of interior nodes carries the same scale as in factor_sweep.
-template <int NB>
-__device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
-    constexpr int S = NB - 1;
+template <int NB, bool ST>
+__device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int n = ws.cs.n;
     const DevTables& tb = *ws.tb;
     const double* y = ws.y;
@@ -393,7 +426,7 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
         if (i == 0 || i == n - 1) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
-                double v = row_residual<NB>(ws, y, i, r);
+                double v = row_residual<NB, ST>(ws, y, i, r);
                 out[r] = v;
             }
             continue;
@@ -431,6 +464,7 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
         for (int r = 0; r < S; ++r) out[r] = F[r];
         if (tb.use_migration) out[S] = -(y0[S] - gp - rho * k.hi) * grow_scale(ws.cs, k.hi);
         else out[S] = -y0[S];
+        if (ST) out[NB - 1] = -(y0[NB - 1] - ym[NB - 1] - y0[S] * k.him);
     }
     __syncwarp();
     if (inv_gamma != 0.0) {
@@ -447,9 +481,9 @@ __device__ void residual_pass(WarpState<NB>& ws, double inv_gamma) {
 // Solve sweeps with the stored factors.  The node records stream from global memory (L2/HBM)
 // into a shared-memory ring by cp.async, RING-1 nodes ahead of use, so that the sequential
 // chain over the nodes never waits for DRAM.  Lane r (< NB) owns row r.
-template <int NB>
-__device__ __forceinline__ void ring_issue(const WarpState<NB>& ws, int i, int slot) {
-    constexpr int REC = fac_rec<NB>();
+template <int NB, bool ST>
+__device__ __forceinline__ void ring_issue(const WarpState<NB, ST>& ws, int i, int slot) {
+    constexpr int REC = fac_rec<NB, ST>();
     if (i >= 0 && i < ws.cs.n) {
         const double* src = ws.fac + (size_t)i * REC;
         double* dst = ws.ring + (size_t)slot * REC;
@@ -458,16 +492,16 @@ __device__ __forceinline__ void ring_issue(const WarpState<NB>& ws, int i, int s
     __pipeline_commit();
 }
 
-template <int NB>
+template <int NB, bool ST>
 struct FactorRow {
     double v[NB];
     double4 co;      // l, a, ud, ua of this row
 };
 
-template <int NB>
-__device__ __forceinline__ void ring_row(const WarpState<NB>& ws, int slot, int r, FactorRow<NB>& f) {
-    constexpr int NBP = padded<NB>();
-    const double* rec = ws.ring + (size_t)slot * fac_rec<NB>();
+template <int NB, bool ST>
+__device__ __forceinline__ void ring_row(const WarpState<NB, ST>& ws, int slot, int r, FactorRow<NB, ST>& f) {
+    constexpr int NBP = padded<NB, ST>();
+    const double* rec = ws.ring + (size_t)slot * fac_rec<NB, ST>();
     const double2* p = reinterpret_cast<const double2*>(rec + r * NBP);
 #pragma unroll
     for (int c = 0; c < NBP / 2; ++c) {
@@ -478,8 +512,8 @@ __device__ __forceinline__ void ring_row(const WarpState<NB>& ws, int slot, int 
     f.co = reinterpret_cast<const double4*>(rec + NB * NBP)[r];
 }
 
-template <int NB>
-__device__ __forceinline__ double row_dot(const FactorRow<NB>& f, const double* tt) {
+template <int NB, bool ST>
+__device__ __forceinline__ double row_dot(const FactorRow<NB, ST>& f, const double* tt) {
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int c = 0; c < NB; c += 2) {
@@ -490,24 +524,24 @@ __device__ __forceinline__ double row_dot(const FactorRow<NB>& f, const double* 
 }
 
 // forward substitution:  z_i = inv_i*(rhs_i - A_L z_{i-1}), zb <- z.
-template <int NB>
-__device__ void forward_solve(WarpState<NB>& ws) {
-    constexpr int S = NB - 1;
+template <int NB, bool ST>
+__device__ void forward_solve(WarpState<NB, ST>& ws) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;           // 2*NB doubles (the pivot buffer is free here)
 #pragma unroll
-    for (int p = 0; p < RING - 1; ++p) ring_issue<NB>(ws, p, p);
+    for (int p = 0; p < RING - 1; ++p) ring_issue<NB, ST>(ws, p, p);
     double zprev = 0.0;
     for (int i = 0; i < n; ++i) {
         __pipeline_wait_prior(RING - 2);
         __syncwarp();
-        FactorRow<NB> f;
+        FactorRow<NB, ST> f;
         double z = 0.0;
         if (act) {
-            ring_row<NB>(ws, i & (RING - 1), r, f);
+            ring_row<NB, ST>(ws, i & (RING - 1), r, f);
             double t = ws.zb[(size_t)i * NB + r];
             if (i > 0) {
                 const double zs = ws.zb[(size_t)(i - 1) * NB + S];
@@ -517,11 +551,11 @@ __device__ void forward_solve(WarpState<NB>& ws) {
         }
         __syncwarp();
         if (act) {
-            z = row_dot<NB>(f, tbuf + (i & 1) * NB);
+            z = row_dot<NB, ST>(f, tbuf + (i & 1) * NB);
             ws.zb[(size_t)i * NB + r] = z;
         }
         zprev = z;
-        ring_issue<NB>(ws, i + RING - 1, (i + RING - 1) & (RING - 1));
+        ring_issue<NB, ST>(ws, i + RING - 1, (i + RING - 1) & (RING - 1));
     }
     __pipeline_wait_prior(0);
     __syncwarp();
@@ -532,24 +566,24 @@ __device__ void forward_solve(WarpState<NB>& ws) {
 // update (|scale*d|*w) and of the accumulated correction (|y-zn0|*w) over the error-controlled
 // unknowns (concentrations of nodes 0..n-2): the weights and zn0 of each node ride in a second
 // cp.async ring.  wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
-template <int NB>
-__device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, double& anorm,
+template <int NB, bool ST>
+__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnorm, double& anorm,
                                int wmode, double prtol, double patol) {
-    constexpr int S = NB - 1;
-    constexpr int NBP = padded<NB>();
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
     constexpr int R2 = 2 * NBP;                  // doubles per node in the weight ring
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;
-    double* ring2 = ws.ring + (size_t)RING * fac_rec<NB>();
+    double* ring2 = ws.ring + (size_t)RING * fac_rec<NB, ST>();
     double dmax = 0.0, amax = 0.0;
     auto issue = [&](int i, int slot) {
         if (i >= 0 && i < n) {
-            const double* src = ws.fac + (size_t)i * fac_rec<NB>();
-            double* dst = ws.ring + (size_t)slot * fac_rec<NB>();
-            for (int c = lane; c < fac_rec<NB>() / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+            const double* src = ws.fac + (size_t)i * fac_rec<NB, ST>();
+            double* dst = ws.ring + (size_t)slot * fac_rec<NB, ST>();
+            for (int c = lane; c < fac_rec<NB, ST>() / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
             if (wmode == 0 && lane < 2 * NB) {
                 const double* s2 = (lane < NB ? ws.ewt : ws.zn - NB) + (size_t)i * NB + lane;
                 __pipeline_memcpy_async(ring2 + (size_t)slot * R2 + (lane < NB ? lane : NBP + lane - NB), s2, 8);
@@ -569,7 +603,7 @@ __device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, d
         __pipeline_wait_prior(RING - 2);
         __syncwarp();
         const int slot = k & (RING - 1);
-        FactorRow<NB> f;
+        FactorRow<NB, ST> f;
         double d = 0.0;
         if (i == 1) {
             if (act) {
@@ -582,7 +616,7 @@ __device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, d
             }
         } else {
             if (act) {
-                ring_row<NB>(ws, slot, r, f);
+                ring_row<NB, ST>(ws, slot, r, f);
                 const double* dn = ws.zb + (size_t)(i + 1) * NB;
                 // t = A_U d_{i+1}: diag -ud, g column -ua (g row: -ud*sg, ua = 0)
                 const double t = -(f.co.z * dn[r] + (r < S ? f.co.w * dn[S] : 0.0));
@@ -590,7 +624,7 @@ __device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, d
             }
             __syncwarp();
             if (act) {
-                d = ws.zb[(size_t)i * NB + r] - row_dot<NB>(f, tbuf + (k & 1) * NB);
+                d = ws.zb[(size_t)i * NB + r] - row_dot<NB, ST>(f, tbuf + (k & 1) * NB);
                 if (i == 0) {
                     const double* d2 = ws.zb + 2 * NB;
                     const double* Vr = ws.V0 + (size_t)r * NBP;
@@ -629,10 +663,10 @@ __device__ void backward_solve(WarpState<NB>& ws, double scale, double& dnorm, d
 // Weighted max norms of the Newton update (scale*zb) and of the accumulated correction
 // (y - zn0) over the error-controlled unknowns (concentrations of nodes 0..n-2).
 // wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
-template <int NB>
-__device__ void newton_norms(const WarpState<NB>& ws, double scale, bool want_acn, double& dnorm, double& anorm,
+template <int NB, bool ST>
+__device__ void newton_norms(const WarpState<NB, ST>& ws, double scale, bool want_acn, double& dnorm, double& anorm,
                              int wmode, double prtol, double patol) {
-    constexpr int S = NB - 1;
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
     const int n = ws.cs.n;
     double dmax = 0.0, amax = 0.0;
     for (int idx = ws.lane; idx < ws.N; idx += 32) {

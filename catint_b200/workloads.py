@@ -65,3 +65,22 @@ def replicate_batch(batch, n_cells):
     """tile a CellBatch to n_cells (synthetic weak-scaling workloads)."""
     idx = np.arange(n_cells) % batch.B
     return batch.select(idx)
+
+
+def geometric_mesh(n_nodes=1001, first_spacing=5e-11, L=50e-6):
+    """normalised node positions xi in [0,1] of the graded mesh x_i = L*(r^i-1)/(r^(n-1)-1) whose first
+    interval is `first_spacing` (0.05 nm = lambda_D/20 at the wall)."""
+    from scipy.optimize import brentq
+    m = n_nodes - 1
+    f = lambda r: L * (r - 1.0) / (r ** m - 1.0) - first_spacing
+    r = brentq(f, 1.0 + 1e-9, 2.0)
+    i = np.arange(n_nodes, dtype=float)
+    return (r ** i - 1.0) / (r ** m - 1.0)
+
+
+def c3(n_phi=128, n_pH=128):
+    """CO2R/KHCO3 with the Stern-layer (Robin) Poisson boundary on a 1001-node graded mesh,
+    potential x pH sweep (use Calculator(..., poisson_bc='stern', mesh=geometric_mesh()))."""
+    kw = co2r_inputs(i_CO=tafel_current(-10.), i_H2=tafel_current(-5.))
+    kw['descriptors'] = {'phiM': list(np.linspace(-0.5, -1.5, n_phi)), 'bulk_pH': list(np.linspace(6.0, 7.8, n_pH))}
+    return kw

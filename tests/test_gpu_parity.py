@@ -299,3 +299,34 @@ def test_thousand_node_grid_uses_global_state(bk, resultsdir):
     assert st['status'].tolist() == [0, 0, 0]
     assert relerr(st['c'][-1, 2].cpu().numpy(), go['newton_c'], cs) < RTOL_PROFILE
     assert np.max(np.abs(st['phi'][-1, 0].cpu().numpy() - go['phi'])) < RTOL_PROFILE * np.max(np.abs(go['phi']))
+
+
+@pytest.mark.parametrize('nn', [201])
+def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
+    """C3-type cells: Stern-layer (Robin) Poisson boundary, phi carried as an unknown (block size S+2),
+    geometric mesh with a 0.05 nm first interval; phiM x bulk_pH corner cells against the CPU BDF oracle +
+    Newton root of the same discrete system (extension beyond the reference FD code).  A cell
+    whose discrete ODE blows up in finite time in the oracle must be reported as failed by the GPU too."""
+    from catint_b200 import backend as be, workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import build_cell_batch
+    go = load_golden('oracle_c3_cells_n%d.npz' % nn)
+    tp = Transport(resultsdir=resultsdir, **workloads.c3(n_phi=2, n_pH=2))
+    batch, _ = build_cell_batch(tp, poisson_bc='stern', mesh=workloads.geometric_mesh(nn, 5e-11))
+    assert batch.b == 10 and batch.nx_max == nn
+    assert np.array_equal(batch.par, go['par']) and np.allclose(batch.mesh_xi[0], go['mesh'], rtol=0, atol=0)
+    out = bk.solve(bk.upload(batch), [200.0], mode=be.MODE_STEADY, max_steps=50000)
+    status = out['status'].cpu().numpy()
+    n_ok = 0
+    for c in range(batch.B):
+        if not bool(go['ok_%d' % c]):
+            assert status[c] != 0, c
+            continue
+        n_ok += 1
+        assert status[c] == 0, (c, status)
+        cs = np.max(np.abs(batch.par[c, :8]))
+        got = out['c'][-1, c].cpu().numpy()
+        assert relerr(got, go['newton_c_%d' % c], cs) < RTOL_PROFILE, c
+        assert np.max(np.abs(out['phi'][-1, c].cpu().numpy() - go['phi_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['phi_%d' % c]))
+        assert np.max(np.abs(out['g'][-1, c].cpu().numpy() - go['g_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['g_%d' % c]))
+    assert n_ok >= 2
