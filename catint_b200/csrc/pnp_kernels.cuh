@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/catint_pnp.h"
 #include "pnp_solver.cuh"
@@ -201,7 +202,7 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo
                              const double* lc, double A1, double rl1, bool predict) {
     const int N = ws.N;
     const int q_new = q_old + dq;
-    for (int idx = ws.lane; idx < N; idx += 32) {
+    for (int idx = ws.vlane; idx < N; idx += ws.vstride) {
         double z[LMAX];
 #pragma unroll
         for (int j = 0; j < LMAX; ++j) z[j] = (j <= q_old) ? ws.zn[(size_t)j * N + idx] : 0.0;
@@ -257,13 +258,79 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo
 // SMEM = true: the Newton iterate, psi and the rhs/update vector live in shared memory and are
 // addressed with LDS/STS (a generic pointer would queue these critical-path accesses behind the
 // global prefetch loads in the L1TEX pipeline); SMEM = false: large grids, state in the workspace.
-template <int NB, bool ST, bool SMEM>
-__global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
+//
+// PAIR = false: one warp per cell, four cells per block.
+// PAIR = true : one block of two warps per cell (twisted block elimination).  Warp 0 eliminates the
+//   nodes 0..m-1 downwards and owns the coupling node m = n/2, warp 1 eliminates n-1..m+1 upwards;
+//   both halves of every sweep run concurrently, which halves the sequential depth of the factor and
+//   solve sweeps; the element-wise passes over the Nordsieck history are split between the warps.
+//   Both warps execute the same (scalar) step/order control on identical norms, so they stay in
+//   lock step; a named hardware barrier (bar.sync id, 64) is the pair barrier.  Experimental, see
+//   launch_bdf.
+constexpr int PAIR_CELLS = 6;      // cells (warp pairs) per block in PAIR mode (shared memory: 6 x 35.6 KB at b=9)
+
+template <bool PAIR>
+__device__ __forceinline__ void pair_sync(int bar_id) { if constexpr (PAIR) pair_barrier(bar_id); }
+
+// max over the two warps of a pair (xn: two shared doubles)
+template <bool PAIR>
+__device__ __forceinline__ double pair_max(double v, double* xn, int half, int lane, int bar_id) {
+    v = warp_max(v);
+    if constexpr (PAIR) {
+        if (lane == 0) xn[half] = v;
+        pair_barrier(bar_id);
+        v = fmax(xn[0], xn[1]);
+        pair_barrier(bar_id);
+    }
+    return v;
+}
+
+// One linear solve with the stored factors + update of the iterate:  zb holds the rhs on entry and the
+// (unscaled) update on exit, y += scale*update; returns the weighted max norms of the scaled update
+// and of the accumulated correction (identical on both warps of a pair).
+template <int NB, bool ST, bool PAIR>
+__device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid, int half, double* xn,
+                             double& del, double& acn, int wmode, double prtol, double patol,
+                             long long* pc, bool prof_on) {
+    const int n = ws.cs.n;
+    double dmax = 0.0, amax = 0.0;
+    if constexpr (!PAIR) {
+        { long long t0 = prof_on ? clock64() : 0; forward_solve<NB, ST>(ws, 0, n, +1); if (prof_on) pc[2] += clock64() - t0; }
+        long long t0 = prof_on ? clock64() : 0;
+        apply_node<NB, ST>(ws, scale, n - 1, dmax, amax, wmode, prtol, patol);        // bulk node: d = z
+        backward_solve<NB, ST>(ws, scale, n - 2, n - 1, -1, dmax, amax, wmode, prtol, patol);
+        del = warp_max(dmax);
+        acn = warp_max(amax);
+        if (prof_on) pc[3] += clock64() - t0;
+    } else {
+        long long t0 = prof_on ? clock64() : 0;
+        if (half == 0) forward_solve<NB, ST>(ws, 0, mid, +1);
+        else forward_solve<NB, ST>(ws, n - 1, n - 1 - mid, -1);
+        pair_barrier(ws.bar_id);
+        if (half == 0) {
+            solve_middle<NB, ST>(ws, mid);
+            apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
+        }
+        pair_barrier(ws.bar_id);
+        if (prof_on) pc[2] += clock64() - t0;
+        t0 = prof_on ? clock64() : 0;
+        if (half == 0) backward_solve<NB, ST>(ws, scale, mid - 1, mid, -1, dmax, amax, wmode, prtol, patol);
+        else backward_solve<NB, ST>(ws, scale, mid + 1, n - 1 - mid, +1, dmax, amax, wmode, prtol, patol);
+        del = pair_max<PAIR>(dmax, xn, half, ws.lane, ws.bar_id);
+        acn = pair_max<PAIR>(amax, xn, half, ws.lane, ws.bar_id);
+        if (prof_on) pc[3] += clock64() - t0;
+    }
+}
+
+template <int NB, bool ST, bool SMEM, bool PAIR>
+__global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pnp_bdf_kernel(SolveParams P) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
-    constexpr int WARPS = 4;
+    constexpr int WARPS = PAIR ? PAIR_CELLS : 4;          // cells per block
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long cell = (long long)blockIdx.x * WARPS + warp;
+    const int half = PAIR ? (warp & 1) : 0;
+    const int slot = PAIR ? (warp >> 1) : warp;            // cell slot inside the block
+    const long long cell = (long long)blockIdx.x * WARPS + slot;
 
     // shared layout: tables | per warp { CellSpecies | scratch | [y psi zb] }
     DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
@@ -276,20 +343,31 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
-    const size_t state_doubles = (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>()) + (SMEM ? (size_t)2 * nxm * NB : 0);
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
-                            (size_t)(scratch_doubles<NB, ST>() + state_doubles) * sizeof(double);
-    unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
+    // per cell: CellSpecies | per warp {scratch | ring} | [y zb] | pair exchange (xch block, norms)
+    constexpr size_t RINGD = (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    constexpr size_t WARPD = scratch_doubles<NB, ST>() + RINGD;          // doubles private to one warp
+    constexpr int WPC = PAIR ? 2 : 1;                                     // warps per cell
+    const size_t cell_doubles = WPC * WARPD + (SMEM ? (size_t)2 * nxm * NB : 0) +
+                                (PAIR ? (size_t)NB * padded<NB, ST>() + 4 : 0);
+    const size_t per_cell = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + cell_doubles * sizeof(double);
+    unsigned char* mine = smem_raw + off + (size_t)slot * per_cell;
     if (cell >= P.n_cells) return;
 
     const long long t_kernel0 = clock64();
     WarpState<NB, ST> ws;
     ws.lane = lane;
+    ws.bar_id = slot + 1;
+    ws.vlane = lane + 32 * half;
+    ws.vstride = 32 * WPC;
     ws.tb = tb;
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
     ws.sp = sp;
-    ws.scratch = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
-    load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
+    double* cellbase = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
+    ws.scratch = cellbase + (size_t)half * WARPD;
+    if (half == 0) load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
+    pair_sync<PAIR>(ws.bar_id);
+    if (PAIR && half == 1)             // scalars only: the species table was filled by warp 0
+        load_cell_scalars(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, ws.cs);
     const int n = ws.cs.n;
     const int N = n * NB;
     ws.N = N;
@@ -301,16 +379,21 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
     ws.psi = g;                g += align4((size_t)nxm * NB);
-    double* sdyn = ws.scratch + scratch_doubles<NB, ST>();
-    ws.ring = sdyn;            sdyn += (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    ws.ring = ws.scratch + scratch_doubles<NB, ST>();
+    double* sdyn = cellbase + (size_t)WPC * WARPD;
     if constexpr (SMEM) {
         ws.y = sdyn; ws.zb = sdyn + (size_t)nxm * NB;
+        sdyn += (size_t)2 * nxm * NB;
     } else {
         ws.y = g; ws.zb = g + align4((size_t)nxm * NB);
     }
+    double* xch = sdyn;                                   // PAIR: W^b block handed to the coupling node
+    double* xn = sdyn + (size_t)NB * NBP;                 // PAIR: norm / flag exchange
+    const int mid = n / 2;                                // coupling node of the twisted sweeps
+    const int vlane = ws.vlane, vstride = ws.vstride;
 
     // ---- initial state: y0 (or bulk) with the consistent field --------------
-    for (int idx = lane; idx < N; idx += 32) {
+    for (int idx = vlane; idx < N; idx += vstride) {
         const int i = idx / NB, r = idx - i * NB;
         double v = 0.0;
         if (r < S) v = P.y0 ? P.y0[((size_t)cell * nxm + i) * S + r] : sp->cb[r];
@@ -318,13 +401,15 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         ws.psi[idx] = 0.0;
     }
     __syncwarp();
-    consistent_field<NB, ST>(ws, ws.y);
+    pair_sync<PAIR>(ws.bar_id);
+    if (half == 0) consistent_field<NB, ST>(ws, ws.y);
+    pair_sync<PAIR>(ws.bar_id);
 
     const double rtol = P.rtol, atol = P.atol;
 
     // zn[0]=y, zn[1]=h*f(y) (mass rows), ewt; first step size from the initial rate of change
     double fnorm = 0.0;
-    for (int idx = lane; idx < N; idx += 32) {
+    for (int idx = vlane; idx < N; idx += vstride) {
         const int i = idx / NB, r = idx - i * NB;
         const bool mass = r < S && i < n - 1;
         const double F = mass ? row_residual<NB, ST>(ws, ws.y, i, r) : 0.0;
@@ -336,7 +421,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         if (mass) fnorm = fmax(fnorm, fabs(F) * w);
     }
     __syncwarp();
-    fnorm = warp_max(fnorm);
+    fnorm = pair_max<PAIR>(fnorm, xn, half, lane, ws.bar_id);
 
     Bdf<NB, ST> B;
     B.q = 1; B.qwait = 2; B.nst = 0; B.t = 0.0; B.etamax = ETAMX1; B.saved_tq5 = 0.0;
@@ -348,8 +433,9 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         h0 = fmin(h0, 1e-3 * (t_end > 0.0 ? t_end : 1.0));
     }
     B.h = B.hscale = h0;
-    for (int idx = lane; idx < N; idx += 32) ws.zn[(size_t)N + idx] *= h0;
+    for (int idx = vlane; idx < N; idx += vstride) ws.zn[(size_t)N + idx] *= h0;
     __syncwarp();
+    pair_sync<PAIR>(ws.bar_id);
 
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // factor, residual, forward, backward, norms, history, correction, other
     const bool prof_on = P.prof != nullptr;
@@ -382,7 +468,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             B.t = saved_t + B.h;
             set_bdf<NB, ST>(B);
             const double rl1 = 1.0 / B.l[1];
-            { CATINT_TIC; history_pass<NB, ST>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true); CATINT_TOC(5); }
+            { CATINT_TIC; history_pass<NB, ST>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+              pair_sync<PAIR>(ws.bar_id); CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
 
@@ -398,13 +485,21 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 bool jcur = false;
                 if (pass == 1) {
                     // stale factors did not converge: restart the corrector from the prediction
-                    for (int idx = lane; idx < N; idx += 32) ws.y[idx] = ws.zn[idx];
+                    for (int idx = vlane; idx < N; idx += vstride) ws.y[idx] = ws.zn[idx];
                     __syncwarp();
+                    pair_sync<PAIR>(ws.bar_id);
                     call_setup = true;
                 }
                 if (call_setup) {
                     CATINT_TIC;
-                    const bool ok = factor_sweep<NB, ST>(ws, inv_gamma);
+                    bool ok;
+                    if constexpr (PAIR) {
+                        ok = (half == 0) ? factor_sweep<NB, ST>(ws, inv_gamma, mid, xch)
+                                         : factor_bottom<NB, ST>(ws, inv_gamma, mid, xch);
+                        ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
+                    } else {
+                        ok = factor_sweep<NB, ST>(ws, inv_gamma);
+                    }
                     CATINT_TOC(0);
                     ++nsetups;
                     have_factors = ok;
@@ -418,10 +513,9 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 double crate = 1.0, delp = 0.0;
                 bool bad = false;
                 for (int m = 0; m < MAXCOR; ++m) {
-                    { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); CATINT_TOC(1); }
-                    { CATINT_TIC; forward_solve<NB, ST>(ws); CATINT_TOC(2); }
-                    double del, acn;
-                    { CATINT_TIC; backward_solve<NB, ST>(ws, dscale, del, acn, 0, 0.0, 0.0); CATINT_TOC(3); }
+                    { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); pair_sync<PAIR>(ws.bar_id); CATINT_TOC(1); }
+                    double del = 0.0, acn = 0.0;
+                    newton_solve<NB, ST, PAIR>(ws, dscale, mid, half, xn, del, acn, 0, 0.0, 0.0, pc, prof_on);
                     ++nni;
                     if (!(del <= 1e300)) { bad = true; break; }
                     if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
@@ -465,14 +559,16 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 pend_undo = false;
                 B.h *= ETAMIN; B.hscale = B.h;
                 B.qwait = LONG_WAIT;
-                for (int idx = lane; idx < N; idx += 32) ws.y[idx] = ws.zn[idx];
+                for (int idx = vlane; idx < N; idx += vstride) ws.y[idx] = ws.zn[idx];
                 __syncwarp();
-                for (int idx = lane; idx < N; idx += 32) {
+                pair_sync<PAIR>(ws.bar_id);
+                for (int idx = vlane; idx < N; idx += vstride) {
                     const int i = idx / NB, r = idx - i * NB;
                     const bool mass = r < S && i < n - 1;
                     ws.zn[(size_t)N + idx] = mass ? B.h * row_residual<NB, ST>(ws, ws.y, i, r) : 0.0;
                 }
                 __syncwarp();
+                pair_sync<PAIR>(ws.bar_id);
             }
         }
         if (!accepted) break;
@@ -500,11 +596,11 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             for (int j = 0; j < LMAX; ++j) lreg[j] = B.l[j];
             double* __restrict__ zn = ws.zn;
             double* __restrict__ ewt = ws.ewt;
-            for (int base = lane; base < N; base += 64) {
+            for (int base = vlane; base < N; base += 2 * vstride) {
                 int idx[2]; bool has[2]; double yv[2], w[2], z0[2], zq[2], zj[2][LMAX];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    idx[u] = base + 32 * u;
+                    idx[u] = base + vstride * u;
                     has[u] = idx[u] < N;
                     const int ii = has[u] ? idx[u] : base;
                     yv[u] = ws.y[ii];
@@ -538,6 +634,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             }
         }
         __syncwarp();
+        ddn = pair_max<PAIR>(ddn, xn, half, lane, ws.bar_id);      // also the pair barrier that ends the correction pass
+        dup = pair_max<PAIR>(dup, xn, half, lane, ws.bar_id);
         if (prof_on) pc[6] += clock64() - tic_corr;
         if (save_acor) B.saved_tq5 = B.tq[5];
 
@@ -552,8 +650,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 eta = etaq;
             } else {
                 B.qwait = 2;
-                ddn = warp_max(ddn) * B.tq[1];
-                dup = warp_max(dup) * B.tq[3];
+                ddn = ddn * B.tq[1];
+                dup = dup * B.tq[3];
                 double etaqm1 = 0.0, etaqp1 = 0.0;
                 if (q > 1) etaqm1 = 1.0 / (pow(BIAS1 * ddn, 1.0 / q) + ADDON);
                 if (want_up) etaqp1 = 1.0 / (pow(BIAS3 * dup, 1.0 / (q + 2)) + ADDON);
@@ -574,7 +672,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             const bool last = (iout == P.n_out - 1);
             double* co = P.c_out + ((size_t)iout * P.n_cells + cell) * nxm * S;
             double* go = P.g_out ? P.g_out + ((size_t)iout * P.n_cells + cell) * nxm : nullptr;
-            for (int idx = lane; idx < N; idx += 32) {
+            for (int idx = vlane; idx < N; idx += vstride) {
                 const int i = idx / NB, r = idx - i * NB;
                 double v = 0.0;
 #pragma unroll
@@ -588,7 +686,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 }
             }
             __syncwarp();
-            if (!ST && !last && P.phi_out && go && lane == 0) {
+            pair_sync<PAIR>(ws.bar_id);
+            if (!ST && !last && P.phi_out && go && lane == 0 && half == 0) {
                 // potential of an intermediate output: forward cumulative sum of the g just written
                 double* po2 = P.phi_out + ((size_t)iout * P.n_cells + cell) * nxm;
                 double v = ws.cs.phi_wall, vm1 = v, vm2 = v;
@@ -621,13 +720,19 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         double del_prev = 0.0;
         for (int it = 0; it < P.polish_max_iter && !done; ++it) {
             // true Newton on the steady residual: inv_gamma = 0 removes the mass term
-            const bool ok = factor_sweep<NB, ST>(ws, 0.0);
+            bool ok;
+            if constexpr (PAIR) {
+                ok = (half == 0) ? factor_sweep<NB, ST>(ws, 0.0, mid, xch) : factor_bottom<NB, ST>(ws, 0.0, mid, xch);
+                ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
+            } else {
+                ok = factor_sweep<NB, ST>(ws, 0.0);
+            }
             ++nsetups;
             if (!ok) break;
             residual_pass<NB, ST>(ws, 0.0);
-            forward_solve<NB, ST>(ws);
-            double del, acn;
-            backward_solve<NB, ST>(ws, 1.0, del, acn, 1, P.polish_rtol, patol);
+            pair_sync<PAIR>(ws.bar_id);
+            double del = 0.0, acn = 0.0;
+            newton_solve<NB, ST, PAIR>(ws, 1.0, mid, half, xn, del, acn, 1, P.polish_rtol, patol, pc, false);
             ++nni;
             if (!(del <= 1e300)) break;
             // converged, or stagnating at the rounding floor of the linear solve with an update that is
@@ -644,8 +749,9 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         double* co = P.c_out + ((size_t)io * P.n_cells + cell) * nxm * S;
         double* go = P.g_out ? P.g_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
         double* po = P.phi_out ? P.phi_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
+        pair_sync<PAIR>(ws.bar_id);
         if (P.mode == CATINT_PNP_MODE_STEADY || status != CATINT_PNP_CELL_CONVERGED) {
-            for (int idx = lane; idx < N; idx += 32) {
+            for (int idx = vlane; idx < N; idx += vstride) {
                 const int i = idx / NB, r = idx - i * NB;
                 const double v = ws.y[idx];
                 if (r < S) co[(size_t)i * S + r] = v;
@@ -654,9 +760,10 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
             }
         }
         __syncwarp();
+        pair_sync<PAIR>(ws.bar_id);
         // potential by the forward cumulative sum of the reference (calculator_old.py:798-800);
         // in Stern mode phi is an unknown of the state and has been written above
-        if (!ST && po && lane == 0) {
+        if (!ST && po && lane == 0 && half == 0) {
             double v = ws.cs.phi_wall;
             po[0] = v;
             double vm1 = v, vm2 = v;
@@ -672,13 +779,13 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 po[n - 1] = vm1 + (vm1 - vm2) * ratio;
             }
         }
-        if (P.flux_out && lane < S) {
+        if (P.flux_out && lane < S && half == 0) {
             const WallCoef w = wall_coef(ws.cs);
             const double bq = tb->use_migration ? sp->bq[lane] : 0.0;
             P.flux_out[(size_t)cell * S + lane] =
                 -sp->D[lane] * ((ws.y[2 * NB + lane] - ws.y[lane]) * w.w0 + bq * ws.y[NB + lane] * ws.y[NB + S]);
         }
-        if (lane == 0) {
+        if (lane == 0 && half == 0) {
             P.status[cell] = status;
             P.n_steps[cell] = B.nst;
             P.n_newton[cell] = nni;
@@ -795,25 +902,38 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
 namespace catint {
 template <int NB, bool ST>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
-    const int WARPS = 4;
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp_fixed = ((sizeof(CellSpecies) + 15) & ~size_t(15)) +
-                                  (size_t)(scratch_doubles<NB, ST>() + RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>())) * sizeof(double);
-    const size_t state = (size_t)2 * P.tb.nx_max * NB * sizeof(double);
+    const size_t species = ((sizeof(CellSpecies) + 15) & ~size_t(15));
+    const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    const size_t state = (size_t)2 * P.tb.nx_max * NB;
     int dev = 0; cudaGetDevice(&dev);
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const size_t smem_state = base + WARPS * (per_warp_fixed + state);
-    const unsigned grid = (unsigned)((P.n_cells + WARPS - 1) / WARPS);
-    if (smem_state <= (size_t)max_optin) {
+    // (1) warp pair per cell (twisted sweeps), EXPERIMENTAL, only with CATINT_PNP_PAIR=1: correct (same parity
+    //     tests) but measured slower than (2) on the 1024-cell C2 batch (0.91-1.5 s vs 0.65 s per launch): at
+    //     12-14 warps/SM the kernel is limited to 128 registers/thread and spills ~4.8 KB/thread into an L1
+    //     that the 186 KB of shared state leaves almost empty.  Needs a leaner factor sweep first (round 2).
+    const size_t smem_pair = base + PAIR_CELLS * (species + (2 * warpd + state + (size_t)NB * padded<NB, ST>() + 4) * sizeof(double));
+    const char* env = getenv("CATINT_PNP_PAIR");
+    const bool want_pair = (env && env[0] == '1') && P.tb.nx_max >= 12;
+    // (2) one warp per cell, four cells per block, state in shared memory; (3) state in the workspace
+    const size_t smem_single = base + 4 * (species + (warpd + state) * sizeof(double));
+    if (want_pair && smem_pair <= (size_t)max_optin) {
         P.state_in_smem = 1;
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_state);
-        pnp_bdf_kernel<NB, ST, true><<<grid, WARPS * 32, smem_state, st>>>(P);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair);
+        const unsigned grid = (unsigned)((P.n_cells + PAIR_CELLS - 1) / PAIR_CELLS);
+        pnp_bdf_kernel<NB, ST, true, true><<<grid, 64 * PAIR_CELLS, smem_pair, st>>>(P);
+    } else if (smem_single <= (size_t)max_optin) {
+        P.state_in_smem = 1;
+        const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single);
+        pnp_bdf_kernel<NB, ST, true, false><<<grid, 128, smem_single, st>>>(P);
     } else {
         P.state_in_smem = 0;
-        const size_t smem = base + WARPS * per_warp_fixed;
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pnp_bdf_kernel<NB, ST, false><<<grid, WARPS * 32, smem, st>>>(P);
+        const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
+        const size_t smem = base + 4 * (species + warpd * sizeof(double));
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pnp_bdf_kernel<NB, ST, false, false><<<grid, 128, smem, st>>>(P);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }

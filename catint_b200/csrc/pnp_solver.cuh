@@ -41,7 +41,14 @@ struct WarpState {
     CellScalars cs;
     int N;          // n*NB
     int lane;
+    int vlane, vstride;   // element-wise passes: first index and stride (a warp pair splits them)
+    int bar_id;           // named barrier of the warp pair (PAIR mode)
 };
+
+// barrier of the two warps that share a cell (64 threads, hardware barrier bar_id)
+__device__ __forceinline__ void pair_barrier(int bar_id) {
+    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+}
 
 template <int NB, bool ST>
 __host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }
@@ -53,7 +60,7 @@ __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 // doubles per node of the stored factors: inverse block (padded rows) + 4 coefficients per row
 template <int NB, bool ST>
 __host__ __device__ constexpr int fac_rec() { return NB * padded<NB, ST>() + NB * 4; }
-constexpr int RING = 8;   // node records in flight in the solve sweeps
+constexpr int RING = 8;   // node records in flight in the solve sweeps (power of two)
 
 // ---------------------------------------------------------------------------
 // Gauss-Jordan elimination with threshold partial pivoting; lane j owns column j
@@ -244,8 +251,11 @@ __device__ __forceinline__ void interior_diag_column(const WarpState<NB, ST>& ws
 // Factorisation sweep.  Lanes: D = 0..NB-1 (columns of A_D'), I = NB..2NB-1 (identity ->
 // inverse), G = 2NB (g-column of A_U -> W[:,g]).  Stores inv_i (all nodes), the sparse
 // coefficients of A_L/A_U (la), V_0 and the dense W_1.
+// One-warp mode: all nodes top-down (mid < 0).  Twisted mode (warp pair): this is the TOP half, nodes
+// 0..mid; at the coupling node `mid` the Schur complement of the bottom half arrives through the
+// shared block xch = W^b_{mid+1} (written by factor_bottom, separated by a block barrier).
 template <int NB, bool ST>
-__device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
+__device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma, int mid = -1, const double* xch = nullptr) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
     const int lane = ws.lane;
@@ -264,7 +274,8 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
     bool ok = true;
     const double* y = ws.y;
 
-    const int n_fac = ST ? n : n - 1;      // Stern mode: the bulk node couples phi_{n-1} to phi_{n-2}
+    // Stern mode: the bulk node couples phi_{n-1} to phi_{n-2} and is eliminated like any other node
+    const int n_fac = (mid >= 0) ? mid + 1 : (ST ? n : n - 1);
     for (int i = 0; i < n_fac; ++i) {
         __syncwarp();
         node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
@@ -324,6 +335,8 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
 
         // ---- interior node: column j of [A_D' | I | u_g] ----
         double Dsave[NB];
+        const bool couple = (i == mid);
+        if (couple) pair_barrier(ws.bar_id);   // the bottom half has published W^b_{mid+1}
         if (isD) {
             if (!bulk) {
                 interior_diag_column<NB, ST>(ws, yi, j, k, inv_gamma, sg, A);
@@ -339,6 +352,14 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
 #pragma unroll
             for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;     // A_D - A_L*W_{i-1}
             if (ST) A[NB - 1] += sl[NB - 1] * Wp[NB - 1];                       // phi row: A_L = -1 on the diagonal
+            if (couple) {
+                // - A_U * W^b_{mid+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
+                const double* xc = xch + j;
+                const double xg = xc[S * NBP];
+#pragma unroll
+                for (int r = 0; r < S; ++r) A[r] += sud[r] * xc[r * NBP] + sua[r] * xg;
+                A[S] += sud[S] * sg * xg;
+            }
             if (i == 1) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r) Dsave[r] = A[r];
@@ -401,13 +422,106 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma) {
         for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
     }
     // bulk node (default Poisson BCs): identity rows, no coupling
-    if (!ST) {
+    if (!ST && mid < 0) {
         const int i = n - 1;
         double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
         for (int e = lane; e < NB * NBP; e += 32) rec[e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
         if (lane < NB) reinterpret_cast<double4*>(rec + NB * NBP)[lane] = make_double4(0, 0, 0, 0);
     }
     __syncwarp();
+    return __all_sync(FULL, ok);
+}
+
+// ---------------------------------------------------------------------------
+// BOTTOM half of the twisted factorisation (second warp of a pair): nodes n-1 down to mid+1 are
+// eliminated upwards,  A_D'_i = A_D,i - A_U,i * W^b_{i+1},  W^b_i = inv_i * A_L,i  with
+// A_L = -(diag l + a e_g^T).  Same lane roles and node records as factor_sweep.  Publishes
+// W^b_{mid+1} in xch for the coupling node and joins the block barrier.
+template <int NB, bool ST>
+__device__ bool factor_bottom(WarpState<NB, ST>& ws, double inv_gamma, int mid, double* xch) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
+    const int lane = ws.lane;
+    const int n = ws.cs.n;
+    const bool mig = ws.tb->use_migration;
+    double* pivbuf = ws.scratch;
+    double* sl = ws.scratch + 2 * (NB + 2);
+    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
+    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
+    const int j = isD ? lane : lane - NB;
+    const int wsrc = isD ? (j != S ? lane + NB : 2 * NB) : lane;
+    double A[NB], Wp[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+    bool ok = true;
+    const double* y = ws.y;
+    for (int i = n - 1; i > mid; --i) {
+        __syncwarp();
+        node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
+        __syncwarp();
+        const double* yi = y + (size_t)i * NB;
+        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
+        double* invcol = rec + j;
+        const bool bulk = (i == n - 1);
+        const NodeCoef k = bulk ? interior_coef(ws.cs, i - 1) : interior_coef(ws.cs, i);
+        const double sg = (!bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
+        if (lane < NB) {
+            double4 v;
+            v.x = sl[lane]; v.y = sa[lane];
+            v.z = (lane == S) ? sud[lane] * sg : sud[lane];
+            v.w = sua[lane];
+            reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < NB; ++r) A[r] = 0.0;
+        if (isD) {
+            if (!bulk) {
+                interior_diag_column<NB, ST>(ws, yi, j, k, inv_gamma, sg, A);
+                // - A_U * W^b_{i+1}
+                const double wg = Wp[S];
+#pragma unroll
+                for (int r = 0; r < S; ++r) A[r] += sud[r] * Wp[r] + sua[r] * wg;
+                A[S] += sud[S] * sg * wg;
+            } else {
+#pragma unroll
+                for (int r = 0; r < S; ++r)
+                    if (r == j) A[r] = 1.0;
+                if (!ST) {
+                    if (j == S) A[S] = 1.0;
+                } else {
+                    if (j == S) A[NB - 1] = -k.hi;
+                    if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
+                }
+            }
+        } else if (isI) {
+#pragma unroll
+            for (int r = 0; r < NB; ++r)
+                if (r == j) A[r] = 1.0;
+        } else if (isG) {
+            // g-column of A_L: -a_r on the transport rows
+#pragma unroll
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -sa[r] : 0.0;
+        }
+        ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
+        double Wc[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) Wc[r] = A[r];
+        if (isI) {
+            const double lj = -sl[j];
+#pragma unroll
+            for (int r = 0; r < NB; ++r) {
+                invcol[r * NBP] = A[r];
+                if (j != S) Wc[r] = A[r] * lj;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
+    }
+    if (isD) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
+    }
+    pair_barrier(ws.bar_id);
     return __all_sync(FULL, ok);
 }
 
@@ -420,7 +534,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     const int n = ws.cs.n;
     const DevTables& tb = *ws.tb;
     const double* y = ws.y;
-    for (int i = ws.lane; i < n; i += 32) {
+    for (int i = ws.vlane; i < n; i += ws.vstride) {
         const double* y0 = y + (size_t)i * NB;
         double* out = ws.zb + (size_t)i * NB;
         if (i == 0 || i == n - 1) {
@@ -468,10 +582,14 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     }
     __syncwarp();
     if (inv_gamma != 0.0) {
-        // mass term of the BDF corrector, psi streamed from global memory (coalesced)
-        for (int idx = ws.lane; idx < ws.N; idx += 32) {
-            const int i = idx / NB, r = idx - i * NB;
-            if (r < S && i < n - 1) ws.zb[idx] -= (y[idx] + ws.psi[idx]) * inv_gamma;
+        // mass term of the BDF corrector, psi streamed from global memory; every lane finishes the
+        // node records it produced above (no cross-lane dependency, hence no barrier in between)
+        for (int i = ws.vlane; i < n - 1; i += ws.vstride) {
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const size_t idx = (size_t)i * NB + r;
+                ws.zb[idx] -= (y[idx] + ws.psi[idx]) * inv_gamma;
+            }
         }
         __syncwarp();
     }
@@ -481,21 +599,15 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
 // Solve sweeps with the stored factors.  The node records stream from global memory (L2/HBM)
 // into a shared-memory ring by cp.async, RING-1 nodes ahead of use, so that the sequential
 // chain over the nodes never waits for DRAM.  Lane r (< NB) owns row r.
-template <int NB, bool ST>
-__device__ __forceinline__ void ring_issue(const WarpState<NB, ST>& ws, int i, int slot) {
-    constexpr int REC = fac_rec<NB, ST>();
-    if (i >= 0 && i < ws.cs.n) {
-        const double* src = ws.fac + (size_t)i * REC;
-        double* dst = ws.ring + (size_t)slot * REC;
-        for (int c = ws.lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
-    }
-    __pipeline_commit();
-}
-
+//
+// All sweeps take a node range and a direction so that the same code serves the one-warp
+// elimination (top-down over all nodes) and the twisted elimination of a warp pair: the "top"
+// warp eliminates nodes 0..m-1 downwards, the "bottom" warp nodes n-1..m+1 upwards, node m
+// couples the two halves (see pnp_kernels.cuh, PAIR).
 template <int NB, bool ST>
 struct FactorRow {
     double v[NB];
-    double4 co;      // l, a, ud, ua of this row
+    double4 co;      // l, a (A_L) and ud, ua (A_U) of this row
 };
 
 template <int NB, bool ST>
@@ -523,67 +635,88 @@ __device__ __forceinline__ double row_dot(const FactorRow<NB, ST>& f, const doub
     return s0 + s1;
 }
 
-// forward substitution:  z_i = inv_i*(rhs_i - A_L z_{i-1}), zb <- z.
+// elimination of the right-hand side over `count` nodes starting at `first` in direction dir:
+//   dir=+1:  z_i = inv_i*(rhs_i - A_L z_{i-1})      (the first node of the range has no predecessor
+//   dir=-1:  z_i = inv_i*(rhs_i - A_U z_{i+1})       inside the range: its coupling term is skipped)
+// zb <- z.
 template <int NB, bool ST>
-__device__ void forward_solve(WarpState<NB, ST>& ws) {
+__device__ void forward_solve(WarpState<NB, ST>& ws, int first, int count, int dir) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int REC = fac_rec<NB, ST>();
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;           // 2*NB doubles (the pivot buffer is free here)
+    auto issue = [&](int k) {
+        const int i = first + dir * k;
+        if (k < count && i >= 0 && i < n) {
+            const double* src = ws.fac + (size_t)i * REC;
+            double* dst = ws.ring + (size_t)(k & (RING - 1)) * REC;
+            for (int c = lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+        }
+        __pipeline_commit();
+    };
 #pragma unroll
-    for (int p = 0; p < RING - 1; ++p) ring_issue<NB, ST>(ws, p, p);
+    for (int p = 0; p < RING - 1; ++p) issue(p);
     double zprev = 0.0;
-    for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < count; ++k) {
+        const int i = first + dir * k;
         __pipeline_wait_prior(RING - 2);
         __syncwarp();
         FactorRow<NB, ST> f;
         double z = 0.0;
         if (act) {
-            ring_row<NB, ST>(ws, i & (RING - 1), r, f);
+            ring_row<NB, ST>(ws, k & (RING - 1), r, f);
             double t = ws.zb[(size_t)i * NB + r];
-            if (i > 0) {
-                const double zs = ws.zb[(size_t)(i - 1) * NB + S];
-                t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
+            if (k > 0) {
+                const double zs = ws.zb[(size_t)(i - dir) * NB + S];
+                if (dir > 0) t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
+                else t = fma(f.co.z, zprev, fma(f.co.w, zs, t));              // rhs - A_U z_{i+1}
             }
-            tbuf[(i & 1) * NB + r] = t;
+            tbuf[(k & 1) * NB + r] = t;
         }
         __syncwarp();
         if (act) {
-            z = row_dot<NB, ST>(f, tbuf + (i & 1) * NB);
+            z = row_dot<NB, ST>(f, tbuf + (k & 1) * NB);
             ws.zb[(size_t)i * NB + r] = z;
         }
         zprev = z;
-        ring_issue<NB, ST>(ws, i + RING - 1, (i + RING - 1) & (RING - 1));
+        issue(k + RING - 1);
     }
     __pipeline_wait_prior(0);
     __syncwarp();
 }
 
-// Backward substitution  d_i = z_i - inv_i*(A_U d_{i+1})  (node 1: dense W_1; node 0: extra
-// wall block V_0);  y += scale*d, zb <- d.  Fused with the weighted max norms of the Newton
-// update (|scale*d|*w) and of the accumulated correction (|y-zn0|*w) over the error-controlled
-// unknowns (concentrations of nodes 0..n-2): the weights and zn0 of each node ride in a second
-// cp.async ring.  wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
+// Back substitution over `count` nodes starting at `first` in direction dir, the solution of the
+// node before `first` (first-dir) being final already in zb:
+//   dir=-1:  d_i = z_i - inv_i*(A_U d_{i+1})   (node 1: dense W_1; node 0: extra wall block V_0)
+//   dir=+1:  d_i = z_i - inv_i*(A_L d_{i-1})
+// y += scale*d, zb <- d.  Fused with the weighted max norms of the Newton update (|scale*d|*w)
+// and of the accumulated correction (|y-zn0|*w) over the error-controlled unknowns
+// (concentrations of nodes 0..n-2), accumulated into dmax/amax (per lane, reduce afterwards):
+// the weights and zn0 of each node ride in a second cp.async ring.
+// wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
 template <int NB, bool ST>
-__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnorm, double& anorm,
-                               int wmode, double prtol, double patol) {
+__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int first, int count, int dir,
+                               double& dmax, double& amax, int wmode, double prtol, double patol) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
+    constexpr int REC = fac_rec<NB, ST>();
     constexpr int R2 = 2 * NBP;                  // doubles per node in the weight ring
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool act = lane < NB;
     const int r = act ? lane : 0;
     double* tbuf = ws.scratch;
-    double* ring2 = ws.ring + (size_t)RING * fac_rec<NB, ST>();
-    double dmax = 0.0, amax = 0.0;
-    auto issue = [&](int i, int slot) {
-        if (i >= 0 && i < n) {
-            const double* src = ws.fac + (size_t)i * fac_rec<NB, ST>();
-            double* dst = ws.ring + (size_t)slot * fac_rec<NB, ST>();
-            for (int c = lane; c < fac_rec<NB, ST>() / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+    double* ring2 = ws.ring + (size_t)RING * REC;
+    auto issue = [&](int k) {
+        const int i = first + dir * k;
+        if (k < count && i >= 0 && i < n) {
+            const int slot = k & (RING - 1);
+            const double* src = ws.fac + (size_t)i * REC;
+            double* dst = ws.ring + (size_t)slot * REC;
+            for (int c = lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
             if (wmode == 0 && lane < 2 * NB) {
                 const double* s2 = (lane < NB ? ws.ewt : ws.zn - NB) + (size_t)i * NB + lane;
                 __pipeline_memcpy_async(ring2 + (size_t)slot * R2 + (lane < NB ? lane : NBP + lane - NB), s2, 8);
@@ -591,21 +724,16 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnor
         }
         __pipeline_commit();
     };
-    // sweep position k = 0,1,.. <-> node i = n-2-k
 #pragma unroll
-    for (int p = 0; p < RING - 1; ++p) issue(n - 2 - p, p);
-    if (act) {   // bulk node: d = z (not error controlled)
-        const size_t idx = (size_t)(n - 1) * NB + r;
-        ws.y[idx] += ws.zb[idx] * scale;
-    }
-    for (int k = 0; k <= n - 2; ++k) {
-        const int i = n - 2 - k;
+    for (int p = 0; p < RING - 1; ++p) issue(p);
+    for (int k = 0; k < count; ++k) {
+        const int i = first + dir * k;
         __pipeline_wait_prior(RING - 2);
         __syncwarp();
         const int slot = k & (RING - 1);
         FactorRow<NB, ST> f;
         double d = 0.0;
-        if (i == 1) {
+        if (dir < 0 && i == 1) {
             if (act) {
                 const double* dn = ws.zb + 2 * NB;
                 const double* Wr = ws.W1 + (size_t)r * NBP;
@@ -617,15 +745,16 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnor
         } else {
             if (act) {
                 ring_row<NB, ST>(ws, slot, r, f);
-                const double* dn = ws.zb + (size_t)(i + 1) * NB;
-                // t = A_U d_{i+1}: diag -ud, g column -ua (g row: -ud*sg, ua = 0)
-                const double t = -(f.co.z * dn[r] + (r < S ? f.co.w * dn[S] : 0.0));
+                const double* dn = ws.zb + (size_t)(i - dir) * NB;       // final solution of the neighbour
+                double t;
+                if (dir < 0) t = -(f.co.z * dn[r] + f.co.w * dn[S]);      // A_U d_{i+1} (ua = 0 off the c rows)
+                else t = -(f.co.x * dn[r] + f.co.y * dn[S]);              // A_L d_{i-1}
                 tbuf[(k & 1) * NB + r] = t;
             }
             __syncwarp();
             if (act) {
                 d = ws.zb[(size_t)i * NB + r] - row_dot<NB, ST>(f, tbuf + (k & 1) * NB);
-                if (i == 0) {
+                if (dir < 0 && i == 0) {
                     const double* d2 = ws.zb + 2 * NB;
                     const double* Vr = ws.V0 + (size_t)r * NBP;
                     double s = 0.0;
@@ -641,7 +770,7 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnor
             const double ds = d * scale;
             const double yn = ws.y[idx] + ds;
             ws.y[idx] = yn;
-            if (r < S) {
+            if (r < S && i < n - 1) {
                 double w, z0 = 0.0;
                 if (wmode == 0) { w = ring2[(size_t)slot * R2 + r]; z0 = ring2[(size_t)slot * R2 + NBP + r]; }
                 else w = 1.0 / (prtol * fabs(yn) + patol);
@@ -651,12 +780,64 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, double& dnor
                 if (wmode == 0) amax = fmax(amax, fabs(yn - z0) * w);
             }
         }
-        issue(n - 2 - (k + RING - 1), (k + RING - 1) & (RING - 1));
+        issue(k + RING - 1);
     }
     __pipeline_wait_prior(0);
     __syncwarp();
-    dnorm = warp_max(dmax);
-    anorm = warp_max(amax);
+}
+
+// update of one node whose solution d already sits in zb (the bulk node of the one-warp sweep,
+// the coupling node of the twisted sweep): y += scale*d and the norms.
+template <int NB, bool ST>
+__device__ void apply_node(WarpState<NB, ST>& ws, double scale, int i, double& dmax, double& amax,
+                           int wmode, double prtol, double patol) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    const int r = ws.lane;
+    if (r < NB) {
+        const size_t idx = (size_t)i * NB + r;
+        const double ds = ws.zb[idx] * scale;
+        const double yn = ws.y[idx] + ds;
+        ws.y[idx] = yn;
+        if (r < S && i < ws.cs.n - 1) {
+            const double w = (wmode == 0) ? ws.ewt[idx] : 1.0 / (prtol * fabs(yn) + patol);
+            double ad = fabs(ds) * w;
+            if (!(ad <= 1e300)) ad = INFINITY;
+            dmax = fmax(dmax, ad);
+            if (wmode == 0) amax = fmax(amax, fabs(yn - ws.zn[idx]) * w);
+        }
+    }
+    __syncwarp();
+}
+
+// solution of the coupling node m of the twisted sweep (done by the top warp):
+//   d_m = inv_m*(rhs_m - A_L z_{m-1} - A_U z_{m+1}),  zb[m] <- d_m
+template <int NB, bool ST>
+__device__ void solve_middle(WarpState<NB, ST>& ws, int m) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
+    const int lane = ws.lane;
+    const bool act = lane < NB;
+    const int r = act ? lane : 0;
+    double* tbuf = ws.scratch;
+    const double* rec = ws.fac + (size_t)m * fac_rec<NB, ST>();
+    double row[NB];
+    double4 co = make_double4(0, 0, 0, 0);
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) row[c] = rec[r * NBP + c];
+        co = reinterpret_cast<const double4*>(rec + NB * NBP)[r];
+        const double* zm = ws.zb + (size_t)(m - 1) * NB;
+        const double* zp = ws.zb + (size_t)(m + 1) * NB;
+        tbuf[r] = ws.zb[(size_t)m * NB + r] + co.x * zm[r] + co.y * zm[S] + co.z * zp[r] + co.w * zp[S];
+    }
+    __syncwarp();
+    if (act) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) s = fma(row[c], tbuf[c], s);
+        ws.zb[(size_t)m * NB + r] = s;
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------
