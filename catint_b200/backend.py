@@ -120,6 +120,7 @@ class CellBatch(object):
         self.mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.int32)
         self.mesh_xi = None if mesh_xi is None else np.ascontiguousarray(mesh_xi, dtype=np.float64)
         self.species = list(species) if species is not None else None
+        self.origin = np.arange(self.B)          # cell indices in the batch this one was selected from
         if self.S > MAX_SPECIES or self.R > MAX_REACTIONS:
             raise ValueError('at most %d species and %d reactions' % (MAX_SPECIES, MAX_REACTIONS))
 
@@ -153,6 +154,11 @@ class CellBatch(object):
     def select(self, idx):
         """sub-batch (used for sharding cells over ranks)."""
         idx = np.asarray(idx)
+        sub = self._select(idx)
+        sub.origin = self.origin[idx]
+        return sub
+
+    def _select(self, idx):
         return CellBatch(self.z, self.reactions, self.nu, self.par[idx], self.nx[idx], nx_max=self.nx_max,
                          use_migration=self.use_migration, poisson_bc=self.poisson_bc,
                          mesh_id=None if self.mesh_id is None else self.mesh_id[idx], mesh_xi=self.mesh_xi,

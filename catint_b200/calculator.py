@@ -235,20 +235,51 @@ class Calculator():
             ts = [float(self.tp.tmax)]
         return ts
 
-    def solve_batch(self, batch, backend=None, pinned=None):
+    def solve_batch(self, batch, backend=None, pinned=None, y0=None):
         """host CellBatch -> host result dict (numpy).  Host->device copies, the
-        solve and the device->host copies all happen here."""
+        solve and the device->host copies all happen here.  y0: optional initial
+        concentrations [B,nx_max,S] (default: bulk everywhere, the reference's c0)."""
         import torch
         if backend is None:
             backend = _be.PnpBackend(self.device)
         db = backend.upload(batch, pinned=pinned)
         mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT
+        y0_dev = None
+        if y0 is not None:
+            y0_dev = torch.as_tensor(np.ascontiguousarray(y0, dtype=np.float64)).to(backend.device)
         out = backend.solve(db, self.output_times(), mode=mode, rtol=self.rtol, atol=self.atol,
-                            max_steps=self.max_steps)
+                            max_steps=self.max_steps, y0=y0_dev)
         host = {k: v.cpu().numpy() for k, v in out.items()}
-        host['h2d_bytes'] = db.h2d_bytes
+        host['h2d_bytes'] = db.h2d_bytes + (0 if y0 is None else int(y0_dev.numel() * 8))
         host['d2h_bytes'] = sum(int(v.numel() * v.element_size()) for v in out.values())
         return host
+
+    def initial_state_from_folder(self, batch):
+        """system['init_folder'] (reference: calculator.py:303-309, a previous results folder) -> initial
+        concentrations of every cell from that run's alldata (warm start / continuation of a sweep).
+        The restart folder must use the same descriptor grid and mesh (reference: calculator.py:242-251)."""
+        tp = self.tp
+        folder = tp.system.get('init_folder', None)
+        if folder is None:
+            return None
+        from .catint_io import load_obj
+        alldata = load_obj('alldata', folder)
+        names = list(tp.species)
+        if len(alldata) != batch.B:
+            tp.logger.error('| CI | -- | init_folder {} holds {} cells, the current descriptor grid {}'.format(
+                folder, len(alldata), batch.B))
+            sys.exit()
+        y0 = np.zeros((batch.B, batch.nx_max, batch.S))
+        for c in range(batch.B):
+            n = int(batch.nx[c])
+            for k, sp in enumerate(names):
+                conc = np.asarray(alldata[c]['species'][sp]['concentration'], dtype=float)
+                if len(conc) != n:
+                    tp.logger.error('| CI | -- | init_folder cell {} has {} nodes, expected {}'.format(c, len(conc), n))
+                    sys.exit()
+                y0[c, :n, k] = conc
+        tp.logger.info('| CI | -- | Initialised {} cells from {}'.format(batch.B, folder))
+        return y0
 
     def run(self):
         tp = self.tp
@@ -262,7 +293,11 @@ class Calculator():
         tp.logger.info('| CI | -- | Starting batched calculation of {} cells ({} x {})'.format(
             batch.B, len(tp.descriptors[keys[0]]), len(tp.descriptors[keys[1]])))
         from . import distributed as _dist
-        res = _dist.solve_sharded(self, batch)
+        y0 = self.initial_state_from_folder(batch)
+        if y0 is None:
+            res = _dist.solve_sharded(self, batch)
+        else:
+            res = _dist.solve_sharded(self, batch, solve_fn=lambda sub: self.solve_batch(sub, y0=y0[sub.origin]))
         t1 = time.time()
         if res is not None:
             self.scatter_results(batch, models, res)

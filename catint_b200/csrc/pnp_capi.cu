@@ -110,11 +110,11 @@ static int block_size_of(const CatintPnpShared* sh) {
 
 static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
     const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
-    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1[NB][NBP] + (y,psi,zb)[N] (used only when the state
+    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1,Wb[NB][NBP] + (y,psi,zb)[N] (used only when the state
     // does not fit in shared memory, always reserved so that the size query is stateless)
     const size_t NBP = NB + (NB & 1);
     const size_t REC = NB * NBP + NB * 4;
-    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 2 * align4(NB * NBP) +
+    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 3 * align4(NB * NBP) +
                3 * align4(nxm * NB);
     return (d + 15) & ~size_t(15);
 }

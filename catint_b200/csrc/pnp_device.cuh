@@ -48,6 +48,7 @@ struct CellScalars {
     double phi_wall, g_bulk, cstern;
     const double* xi;   // normalised mesh row (non-uniform) or nullptr
     double u_am, u_ac;  // cached uniform-mesh stencil weights 1/dx^2, 1/(2dx)
+    double u_sg;        // cached uniform-mesh g-row scale eps/(dx*F)
 };
 
 // Per-cell, per-species parameters in shared memory (one copy per warp).
@@ -60,50 +61,64 @@ struct NodeCoef {
     double hi, him;      // h_i = x_{i+1}-x_i ; h_{i-1}
 };
 
-__device__ __forceinline__ NodeCoef interior_coef(const CellScalars& cs, int i) {
+// graded mesh: three fp64 divisions per node.  Kept out of line: the division sequences would
+// otherwise be replicated at every call site (instruction-cache footprint).
+static __device__ __noinline__ NodeCoef graded_coef(const double* xi, double dx, int i) {
     NodeCoef k;
-    if (cs.uniform) {
-        k.am = cs.u_am; k.ap = cs.u_am; k.ac = cs.u_ac; k.hi = cs.dx; k.him = cs.dx;
-    } else {
-        const double xm = cs.dx * cs.xi[i - 1], x0 = cs.dx * cs.xi[i], xp = cs.dx * cs.xi[i + 1];
-        const double hm = x0 - xm, hp = xp - x0;
-        k.am = 2.0 / (hm * (hm + hp));
-        k.ap = 2.0 / (hp * (hm + hp));
-        k.ac = 1.0 / (hm + hp);
-        k.hi = hp;
-        k.him = hm;
-    }
+    const double xm = dx * xi[i - 1], x0 = dx * xi[i], xp = dx * xi[i + 1];
+    const double hm = x0 - xm, hp = xp - x0;
+    k.am = 2.0 / (hm * (hm + hp));
+    k.ap = 2.0 / (hp * (hm + hp));
+    k.ac = 1.0 / (hm + hp);
+    k.hi = hp;
+    k.him = hm;
     return k;
+}
+
+__device__ __forceinline__ NodeCoef interior_coef(const CellScalars& cs, int i) {
+    if (cs.uniform) {
+        NodeCoef k;
+        k.am = cs.u_am; k.ap = cs.u_am; k.ac = cs.u_ac; k.hi = cs.dx; k.him = cs.dx;
+        return k;
+    }
+    return graded_coef(cs.xi, cs.dx, i);
 }
 
 struct WallCoef { double w0, ih0, ext; };   // 1/(h0+h1), 1/h0, h0/h1
 
-__device__ __forceinline__ WallCoef wall_coef(const CellScalars& cs) {
+static __device__ __noinline__ WallCoef graded_wall_coef(const double* xi, double dx) {
     WallCoef w;
+    const double h0 = dx * (xi[1] - xi[0]), h1 = dx * (xi[2] - xi[1]);
+    w.w0 = 1.0 / (h0 + h1);
+    w.ih0 = 1.0 / h0;
+    w.ext = h0 / h1;
+    return w;
+}
+
+__device__ __forceinline__ WallCoef wall_coef(const CellScalars& cs) {
     if (cs.uniform) {
+        WallCoef w;
         w.w0 = cs.u_ac;
         w.ih0 = 2.0 * cs.u_ac;
         w.ext = 1.0;
-    } else {
-        const double h0 = cs.dx * (cs.xi[1] - cs.xi[0]), h1 = cs.dx * (cs.xi[2] - cs.xi[1]);
-        w.w0 = 1.0 / (h0 + h1);
-        w.ih0 = 1.0 / h0;
-        w.ext = h0 / h1;
+        return w;
     }
-    return w;
+    return graded_wall_coef(cs.xi, cs.dx);
 }
 
 // scale of the algebraic g-row of an interior node: eps/(h_i*F) turns the charge entries
 // q_j*h/eps (~1e8) into the integer charges z_j, so that partial pivoting rarely swaps
 __device__ __forceinline__ double grow_scale(const CellScalars& cs, double hi) {
-    return cs.eps / (hi * UNIT_F);
+    return cs.uniform ? cs.u_sg : cs.eps / (hi * UNIT_F);
 }
 
 // net rate of reaction r at a node whose concentrations are c[0..S)
 __device__ __forceinline__ double net_rate(const DevTables& tb, int r, const double* c) {
     double f = tb.kf[r];
+#pragma unroll 1
     for (int e = 0; e < tb.ned[r]; ++e) f *= c[tb.ed[r][e]];
     double b = tb.kr[r];
+#pragma unroll 1
     for (int e = 0; e < tb.npr[r]; ++e) b *= c[tb.pr[r][e]];
     return f - b;
 }
@@ -126,6 +141,7 @@ __device__ __forceinline__ void load_cell_scalars(const DevTables& tb, const dou
     cs.dx = p[3 * S + 5];
     cs.u_am = 1.0 / (cs.dx * cs.dx);
     cs.u_ac = 1.0 / (2.0 * cs.dx);
+    cs.u_sg = cs.eps / (cs.dx * UNIT_F);
 }
 
 // cell set-up shared by all kernels
@@ -147,6 +163,7 @@ __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par
     cs.dx = p[3 * S + 5];
     cs.u_am = 1.0 / (cs.dx * cs.dx);
     cs.u_ac = 1.0 / (2.0 * cs.dx);
+    cs.u_sg = cs.eps / (cs.dx * UNIT_F);
     if (lane < S) {
         sp->cb[lane] = p[lane];
         sp->J[lane] = p[S + lane];
@@ -159,10 +176,14 @@ __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par
     __syncwarp();
 }
 
+// max over the warp of NON-NEGATIVE values (norms): IEEE doubles with a clear sign bit order like
+// their bit patterns, so two integer warp reductions (REDUX) replace five shuffle+max rounds; +Inf
+// and NaN patterns sort above every finite value, i.e. a poisoned norm stays poisoned.
 __device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 }  // namespace catint

@@ -294,18 +294,24 @@ __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid, int h
                              long long* pc, bool prof_on) {
     const int n = ws.cs.n;
     double dmax = 0.0, amax = 0.0;
+    const Chain none = {0, 0, 1};
     if constexpr (!PAIR) {
-        { long long t0 = prof_on ? clock64() : 0; forward_solve<NB, ST>(ws, 0, n, +1); if (prof_on) pc[2] += clock64() - t0; }
+        // one warp, twisted factors: both chains advance in the two halves of the warp
         long long t0 = prof_on ? clock64() : 0;
-        apply_node<NB, ST>(ws, scale, n - 1, dmax, amax, wmode, prtol, patol);        // bulk node: d = z
-        backward_solve<NB, ST>(ws, scale, n - 2, n - 1, -1, dmax, amax, wmode, prtol, patol);
+        forward_solve<NB, ST>(ws, Chain{0, mid, +1}, Chain{n - 1, n - 1 - mid, -1});
+        solve_middle<NB, ST>(ws, mid);
+        if (prof_on) pc[2] += clock64() - t0;
+        t0 = prof_on ? clock64() : 0;
+        apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
+        backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, Chain{mid + 1, n - 1 - mid, +1},
+                               dmax, amax, wmode, prtol, patol);
         del = warp_max(dmax);
         acn = warp_max(amax);
         if (prof_on) pc[3] += clock64() - t0;
     } else {
         long long t0 = prof_on ? clock64() : 0;
-        if (half == 0) forward_solve<NB, ST>(ws, 0, mid, +1);
-        else forward_solve<NB, ST>(ws, n - 1, n - 1 - mid, -1);
+        if (half == 0) forward_solve<NB, ST>(ws, Chain{0, mid, +1}, none);
+        else forward_solve<NB, ST>(ws, Chain{n - 1, n - 1 - mid, -1}, none);
         pair_barrier(ws.bar_id);
         if (half == 0) {
             solve_middle<NB, ST>(ws, mid);
@@ -314,8 +320,8 @@ __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid, int h
         pair_barrier(ws.bar_id);
         if (prof_on) pc[2] += clock64() - t0;
         t0 = prof_on ? clock64() : 0;
-        if (half == 0) backward_solve<NB, ST>(ws, scale, mid - 1, mid, -1, dmax, amax, wmode, prtol, patol);
-        else backward_solve<NB, ST>(ws, scale, mid + 1, n - 1 - mid, +1, dmax, amax, wmode, prtol, patol);
+        if (half == 0) backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, none, dmax, amax, wmode, prtol, patol);
+        else backward_solve<NB, ST>(ws, scale, Chain{mid + 1, n - 1 - mid, +1}, none, dmax, amax, wmode, prtol, patol);
         del = pair_max<PAIR>(dmax, xn, half, ws.lane, ws.bar_id);
         acn = pair_max<PAIR>(amax, xn, half, ws.lane, ws.bar_id);
         if (prof_on) pc[3] += clock64() - t0;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     const long long t_kernel0 = clock64();
     WarpState<NB, ST> ws;
     ws.lane = lane;
-    ws.bar_id = slot + 1;
+    ws.bar_id = PAIR ? slot + 1 : 0;
     ws.vlane = lane + 32 * half;
     ws.vstride = 32 * WPC;
     ws.tb = tb;
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
     ws.psi = g;                g += align4((size_t)nxm * NB);
+    double* xch_g = g;         g += align4((size_t)NB * NBP);   // one warp per cell: coupling block W^b_{mid+1}
     ws.ring = ws.scratch + scratch_doubles<NB, ST>();
     double* sdyn = cellbase + (size_t)WPC * WARPD;
     if constexpr (SMEM) {
@@ -387,9 +394,13 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     } else {
         ws.y = g; ws.zb = g + align4((size_t)nxm * NB);
     }
-    double* xch = sdyn;                                   // PAIR: W^b block handed to the coupling node
+    double* xch = PAIR ? sdyn : xch_g;                    // W^b block handed to the coupling node
     double* xn = sdyn + (size_t)NB * NBP;                 // PAIR: norm / flag exchange
     const int mid = n / 2;                                // coupling node of the twisted sweeps
+    SmemOffsets so;                                       // shared-memory pointers as offsets (factor_nodes)
+    so.scratch = (unsigned)(reinterpret_cast<unsigned char*>(ws.scratch) - smem_raw);
+    so.sp = (unsigned)(reinterpret_cast<const unsigned char*>(sp) - smem_raw);
+    so.y = SMEM ? (unsigned)(reinterpret_cast<unsigned char*>(ws.y) - smem_raw) : 0u;
     const int vlane = ws.vlane, vstride = ws.vstride;
 
     // ---- initial state: y0 (or bulk) with the consistent field --------------
@@ -494,11 +505,10 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                     CATINT_TIC;
                     bool ok;
                     if constexpr (PAIR) {
-                        ok = (half == 0) ? factor_sweep<NB, ST>(ws, inv_gamma, mid, xch)
-                                         : factor_bottom<NB, ST>(ws, inv_gamma, mid, xch);
+                        ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid, xch, half == 0 ? FACTOR_TOP : FACTOR_BOTTOM);
                         ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
                     } else {
-                        ok = factor_sweep<NB, ST>(ws, inv_gamma);
+                        ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid, xch, FACTOR_BOTH);
                     }
                     CATINT_TOC(0);
                     ++nsetups;
@@ -722,10 +732,10 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             // true Newton on the steady residual: inv_gamma = 0 removes the mass term
             bool ok;
             if constexpr (PAIR) {
-                ok = (half == 0) ? factor_sweep<NB, ST>(ws, 0.0, mid, xch) : factor_bottom<NB, ST>(ws, 0.0, mid, xch);
+                ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid, xch, half == 0 ? FACTOR_TOP : FACTOR_BOTTOM);
                 ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
             } else {
-                ok = factor_sweep<NB, ST>(ws, 0.0);
+                ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid, xch, FACTOR_BOTH);
             }
             ++nsetups;
             if (!ok) break;

@@ -47,11 +47,12 @@ struct WarpState {
 
 // barrier of the two warps that share a cell (64 threads, hardware barrier bar_id)
 __device__ __forceinline__ void pair_barrier(int bar_id) {
-    asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+    if (bar_id > 0) asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+    else __syncwarp();          // one warp owns the whole cell: nothing to wait for
 }
 
 template <int NB, bool ST>
-__host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }
+__host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }   // >= 4*padded (sweep buffers)
 // sub-arrays of the per-cell workspace start on 32-byte boundaries
 __host__ __device__ constexpr size_t align4(size_t doubles) { return (doubles + 3) & ~size_t(3); }
 // padded row length of the stored blocks (even -> 16-byte aligned rows, double2 loads)
@@ -67,46 +68,58 @@ constexpr int RING = 8;   // node records in flight in the solve sweeps (power o
 // (columns >= NB are right-hand sides).  The pivot column travels through shared
 // memory (one writer, broadcast reads).  A row swap is a warp-uniform branch, so
 // it only costs when it happens.  Returns false on a zero/non-finite pivot.
+// Reciprocal of a pivot: hardware seed (MUFU.RCP64H, ~2^-20) + three Newton steps, no slow path.
+// Accurate to ~1 ulp for normal operands, which is all a factorisation needs (the correctly rounded
+// __drcp_rn costs ~45 dependent instructions on the critical path of every elimination step);
+// zero / denormal / huge pivots give Inf or NaN and are rejected by the caller.
+__device__ __forceinline__ double pivot_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
 template <int NB, bool ST>
 __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* pivbuf) {
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
         double* buf = pivbuf + (k & 1) * (NB + 2);
-        if (lane == k) {
-            // magnitude keys: high word of |a| with the row index in the low 4 bits
-            int best = ((__double2hiint(A[k]) & 0x7fffffff) & ~0xf) | k;
-            const int diag = best;
+        // magnitude keys: high word of |a| with the row index in the low 4 bits
+        int best = ((__double2hiint(A[k]) & 0x7fffffff) & ~0xf) | k;
+        const int diag = best;
+#pragma unroll
+        for (int r = k + 1; r < NB; ++r) {
+            const int key = ((__double2hiint(A[r]) & 0x7fffffff) & ~0xf) | r;
+            best = max(best, key);
+        }
+        // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
+        int p = best & 0xf;
+        if (diag + (3 << 20) >= best) p = k;
+        p = __shfl_sync(FULL, p, k);          // the decision of the lane that owns column k
+        if (p != k) {                          // warp-uniform: rows k and p change places
+            double ak = A[k];
 #pragma unroll
             for (int r = k + 1; r < NB; ++r) {
-                const int key = ((__double2hiint(A[r]) & 0x7fffffff) & ~0xf) | r;
-                best = max(best, key);
+                if (r == p) { const double t = A[r]; A[r] = ak; ak = t; }
             }
-            // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
-            int p = best & 0xf;
-            if (diag + (3 << 20) >= best) p = k;
+            A[k] = ak;
+        }
+        if (lane == k) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) buf[r] = A[r];
-            buf[NB] = (double)p;
         }
         __syncwarp();
-        const int p = (int)buf[NB];
         double col[NB];
 #pragma unroll
         for (int r = 0; r < NB; ++r) col[r] = buf[r];
-        if (p != k) {           // warp-uniform
-            double ck = col[k], ak = A[k];
-#pragma unroll
-            for (int r = k + 1; r < NB; ++r) {
-                if (r == p) {
-                    double t = col[r]; col[r] = ck; ck = t;
-                    t = A[r]; A[r] = ak; ak = t;
-                }
-            }
-            col[k] = ck; A[k] = ak;
-        }
         const double ck = col[k];
-        const double inv = __drcp_rn(ck);
+        const double inv = pivot_rcp(ck);
         ok = ok && (ck != 0.0) && (fabs(inv) < 1e300);
         const double ak = A[k] * inv;
         A[k] = ak;
@@ -149,6 +162,7 @@ __device__ __forceinline__ double row_residual(const WarpState<NB, ST>& ws, cons
     const double* yp = y0 + NB;
     if (r < S) {
         double R = 0.0;
+#pragma unroll 1
         for (int rr = 0; rr < tb.R; ++rr) {
             const double nu = tb.nu[rr][r];
             if (nu != 0.0) R += nu * net_rate(tb, rr, y0);
@@ -248,16 +262,40 @@ __device__ __forceinline__ void interior_diag_column(const WarpState<NB, ST>& ws
 }
 
 // ---------------------------------------------------------------------------
-// Factorisation sweep.  Lanes: D = 0..NB-1 (columns of A_D'), I = NB..2NB-1 (identity ->
-// inverse), G = 2NB (g-column of A_U -> W[:,g]).  Stores inv_i (all nodes), the sparse
-// coefficients of A_L/A_U (la), V_0 and the dense W_1.
-// One-warp mode: all nodes top-down (mid < 0).  Twisted mode (warp pair): this is the TOP half, nodes
-// 0..mid; at the coupling node `mid` the Schur complement of the bottom half arrives through the
-// shared block xch = W^b_{mid+1} (written by factor_bottom, separated by a block barrier).
-template <int NB, bool ST>
-__device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma, int mid = -1, const double* xch = nullptr) {
+// Twisted block factorisation of the Newton matrix.  Lanes: D = 0..NB-1 (columns of A_D'),
+// I = NB..2NB-1 (identity -> inverse), G = 2NB (g-column of the coupling block -> W[:,g]).
+//
+//   bottom half (FACTOR_BOTTOM): nodes n-1 down to mid+1 are eliminated upwards,
+//       A_D'_i = A_D,i - A_U,i * W^b_{i+1},   W^b_i = inv_i * A_L,i,   A_L = -(diag l + a e_g^T);
+//       W^b_{mid+1} is published in xch for the coupling node.
+//   top half (FACTOR_TOP): nodes 0..mid downwards,  A_D'_i = A_D,i - A_L,i * W_{i-1},  W_i = inv_i*A_U,i;
+//       node 0 carries the extra wall block A_E (V_0 = inv_0*A_E), which makes A_U of node 1 dense
+//       (second elimination, W_1 stored); the coupling node `mid` also subtracts A_U * W^b_{mid+1}.
+//
+// Stores inv_i and the sparse coefficients of A_L/A_U per node, V_0 and W_1.  One warp runs both halves
+// one after the other (parts = FACTOR_BOTH); a warp pair runs one half each and meets at the named
+// barrier.  Every node of either half passes through the SAME elimination code: the routine is
+// deliberately not inlined and has a single gauss_jordan instance, because the unrolled elimination
+// is the bulk of the kernel's instruction footprint (instruction cache).
+constexpr int FACTOR_TOP = 1, FACTOR_BOTTOM = 2, FACTOR_BOTH = 3;
+
+// The warp state is passed BY VALUE: handing out a reference would force the caller's copy into
+// local memory and turn every shared-memory access of the whole kernel into a generic one.  Pointers
+// that cross the call lose their address space, so the shared-memory ones are rebuilt here from
+// byte offsets into the block's dynamic shared memory (SmemOffsets) and come out as LDS/STS again.
+struct SmemOffsets { unsigned scratch, sp, y; };
+
+template <int NB, bool ST, bool SMEM>
+__device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
+                                          int mid, double* xch, int parts) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpState<NB, ST> ws = ws_in;
+    ws.scratch = reinterpret_cast<double*>(smem_raw + so.scratch);
+    ws.sp = reinterpret_cast<const CellSpecies*>(smem_raw + so.sp);
+    ws.tb = reinterpret_cast<const DevTables*>(smem_raw);
+    if constexpr (SMEM) ws.y = reinterpret_cast<double*>(smem_raw + so.y);
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
@@ -266,38 +304,60 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma, int mid = 
     double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
     const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
     const int j = isD ? lane : lane - NB;
-    // source lane of the W column that D-lane j needs for the next Schur update
-    const int wsrc = isD ? (j < S ? lane + NB : 2 * NB) : lane;
+    // source lane of the W column that D-lane j needs for the next Schur update: the scaled inverse
+    // column where the coupling block has a diagonal entry in column j, the G lane for the g column
+    const int wsrc_top = isD ? (j < S ? lane + NB : 2 * NB) : lane;
+    const int wsrc_bot = isD ? (j != S ? lane + NB : 2 * NB) : lane;
     double A[NB], Wp[NB];
 #pragma unroll
     for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
     bool ok = true;
     const double* y = ws.y;
 
-    // Stern mode: the bulk node couples phi_{n-1} to phi_{n-2} and is eliminated like any other node
-    const int n_fac = (mid >= 0) ? mid + 1 : (ST ? n : n - 1);
-    for (int i = 0; i < n_fac; ++i) {
-        __syncwarp();
-        node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
-        __syncwarp();
-        const double* yi = y + (size_t)i * NB;
+    bool bottom = (parts & FACTOR_BOTTOM) != 0;
+    int i = bottom ? n - 1 : 0;
+    int pass = 0;            // node 1 is eliminated twice (pass 1: [A_D1' | A_U1'] -> dense W_1)
+#pragma unroll 1
+    for (;;) {
+        if (bottom && i <= mid) {
+            // bottom half done: publish W^b_{mid+1}
+            if (isD) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
+            }
+            if (!(parts & FACTOR_TOP)) { pair_barrier(ws.bar_id); break; }
+            bottom = false; i = 0;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+        }
+        if (!bottom && i > mid) break;
+
+        const bool bulk = (i == n - 1);
+        const bool wall = (i == 0);
+        const bool couple = !bottom && (i == mid);
         double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
         double* invcol = rec + j;                                   // column j of inv_i (I lanes)
-        const bool bulk = (i == n - 1);
-        const NodeCoef k = bulk ? interior_coef(ws.cs, i - 1)
-                                : ((i > 0) ? interior_coef(ws.cs, i) : NodeCoef{0, 0, 0, 1, 1});
-        const double sg = (i > 0 && !bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
-        if (lane < NB) {
-            double4 v;
-            v.x = sl[lane]; v.y = sa[lane];
-            v.z = (lane == S) ? sud[lane] * sg : sud[lane];
-            v.w = sua[lane];
-            reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
+        NodeCoef k = NodeCoef{0, 0, 0, 1, 1};
+        if (!wall) k = interior_coef(ws.cs, bulk ? i - 1 : i);
+        const double sg = (!wall && !bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
+        __syncwarp();
+        if (pass == 0) {
+            node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
+            __syncwarp();
+            if (lane < NB) {
+                double4 v;
+                v.x = sl[lane]; v.y = sa[lane];
+                v.z = (lane == S && !wall) ? sud[lane] * sg : sud[lane];
+                v.w = sua[lane];
+                reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
+            }
         }
+        if (couple) pair_barrier(ws.bar_id);   // the bottom half has published W^b_{mid+1}
 #pragma unroll
         for (int r = 0; r < NB; ++r) A[r] = 0.0;
 
-        if (i == 0) {
+        // ---- column j of [A_D' | I | u_g] ----
+        if (wall) {
             // A_D0 is diag(mass*inv_gamma - sa); A_U0 = diag(-sud) + g-column(-sua); A_E = diag(-sl)
             if (isD || isI) {
 #pragma unroll
@@ -308,91 +368,12 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma, int mid = 
 #pragma unroll
                 for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r];
             }
-            ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
-            double Wc[NB];
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wc[r] = A[r];
-            if (isI) {
-                const double ud = -sud[j], ae = -sl[j];
-                double* v0col = ws.V0 + j;
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    invcol[r * NBP] = A[r];
-                    v0col[r * NBP] = A[r] * ae;
-                    if (j < S) Wc[r] = A[r] * ud;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
-            // the I lanes keep V_0 columns for the modified A_U of node 1
-            if (isI) {
-                const double ae = -sl[j];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) Wp[r] = A[r] * ae;
-            }
-            continue;
-        }
-
-        // ---- interior node: column j of [A_D' | I | u_g] ----
-        double Dsave[NB];
-        const bool couple = (i == mid);
-        if (couple) pair_barrier(ws.bar_id);   // the bottom half has published W^b_{mid+1}
-        if (isD) {
-            if (!bulk) {
-                interior_diag_column<NB, ST>(ws, yi, j, k, inv_gamma, sg, A);
-            } else {
-                // Stern bulk node: c rows identity; row S: phi_{n-1} = 0; row P: phi recursion with h_{n-2}
-#pragma unroll
-                for (int r = 0; r < S; ++r)
-                    if (r == j) A[r] = 1.0;
-                if (j == S) A[NB - 1] = -k.hi;
-                if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
-            }
-            const double wg = Wp[S];
-#pragma unroll
-            for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;     // A_D - A_L*W_{i-1}
-            if (ST) A[NB - 1] += sl[NB - 1] * Wp[NB - 1];                       // phi row: A_L = -1 on the diagonal
-            if (couple) {
-                // - A_U * W^b_{mid+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
-                const double* xc = xch + j;
-                const double xg = xc[S * NBP];
-#pragma unroll
-                for (int r = 0; r < S; ++r) A[r] += sud[r] * xc[r * NBP] + sua[r] * xg;
-                A[S] += sud[S] * sg * xg;
-            }
-            if (i == 1) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) Dsave[r] = A[r];
-            }
-        } else if (isI) {
-#pragma unroll
-            for (int r = 0; r < NB; ++r)
-                if (r == j) A[r] = 1.0;
-        } else if (isG) {
-#pragma unroll
-            for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r] * sg;
-        }
-        ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
-        double Wc[NB];
-#pragma unroll
-        for (int r = 0; r < NB; ++r) Wc[r] = A[r];
-        if (isI) {
-            const double ud = -sud[j];
-#pragma unroll
-            for (int r = 0; r < NB; ++r) {
-                invcol[r * NBP] = A[r];
-                if (j < S) Wc[r] = A[r] * ud;
-            }
-        }
-        if (i == 1) {
-            // A_U of node 1 is modified by the wall block: A_U1' = A_U1 - A_L1*V_0 (dense in
-            // general), so W_1 = inv_1*A_U1' comes from a second elimination [A_D1' | A_U1']
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < NB; ++r) A[r] = 0.0;
+        } else if (pass == 1) {
+            // node 1, second elimination: A_U1' = A_U1 - A_L1*V_0 (dense in general)
             if (isD) {
+                const double* d1 = ws.W1 + j;        // A_D1' parked there by pass 0
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = Dsave[r];
+                for (int r = 0; r < NB; ++r) A[r] = d1[r * NBP];
             } else if (isI) {
                 const double vg = Wp[S];
 #pragma unroll
@@ -405,84 +386,31 @@ __device__ bool factor_sweep(WarpState<NB, ST>& ws, double inv_gamma, int mid = 
                     A[r] = v;
                 }
             }
-            ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wc[r] = A[r];
-            if (isI) {
-                double* w1col = ws.W1 + j;
-#pragma unroll
-                for (int r = 0; r < NB; ++r) w1col[r * NBP] = A[r];
-            }
-            const int src1 = isD ? lane + NB : lane;
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], src1);
-            continue;
-        }
-#pragma unroll
-        for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
-    }
-    // bulk node (default Poisson BCs): identity rows, no coupling
-    if (!ST && mid < 0) {
-        const int i = n - 1;
-        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
-        for (int e = lane; e < NB * NBP; e += 32) rec[e] = (e / NBP == e % NBP) ? 1.0 : 0.0;
-        if (lane < NB) reinterpret_cast<double4*>(rec + NB * NBP)[lane] = make_double4(0, 0, 0, 0);
-    }
-    __syncwarp();
-    return __all_sync(FULL, ok);
-}
-
-// ---------------------------------------------------------------------------
-// BOTTOM half of the twisted factorisation (second warp of a pair): nodes n-1 down to mid+1 are
-// eliminated upwards,  A_D'_i = A_D,i - A_U,i * W^b_{i+1},  W^b_i = inv_i * A_L,i  with
-// A_L = -(diag l + a e_g^T).  Same lane roles and node records as factor_sweep.  Publishes
-// W^b_{mid+1} in xch for the coupling node and joins the block barrier.
-template <int NB, bool ST>
-__device__ bool factor_bottom(WarpState<NB, ST>& ws, double inv_gamma, int mid, double* xch) {
-    constexpr int S = NB - 1 - (ST ? 1 : 0);
-    constexpr int NBP = padded<NB, ST>();
-    const int lane = ws.lane;
-    const int n = ws.cs.n;
-    const bool mig = ws.tb->use_migration;
-    double* pivbuf = ws.scratch;
-    double* sl = ws.scratch + 2 * (NB + 2);
-    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
-    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
-    const int j = isD ? lane : lane - NB;
-    const int wsrc = isD ? (j != S ? lane + NB : 2 * NB) : lane;
-    double A[NB], Wp[NB];
-#pragma unroll
-    for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
-    bool ok = true;
-    const double* y = ws.y;
-    for (int i = n - 1; i > mid; --i) {
-        __syncwarp();
-        node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
-        __syncwarp();
-        const double* yi = y + (size_t)i * NB;
-        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
-        double* invcol = rec + j;
-        const bool bulk = (i == n - 1);
-        const NodeCoef k = bulk ? interior_coef(ws.cs, i - 1) : interior_coef(ws.cs, i);
-        const double sg = (!bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
-        if (lane < NB) {
-            double4 v;
-            v.x = sl[lane]; v.y = sa[lane];
-            v.z = (lane == S) ? sud[lane] * sg : sud[lane];
-            v.w = sua[lane];
-            reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
-        }
-#pragma unroll
-        for (int r = 0; r < NB; ++r) A[r] = 0.0;
-        if (isD) {
+        } else if (isD) {
             if (!bulk) {
-                interior_diag_column<NB, ST>(ws, yi, j, k, inv_gamma, sg, A);
-                // - A_U * W^b_{i+1}
+                interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, j, k, inv_gamma, sg, A);
                 const double wg = Wp[S];
+                if (bottom) {
+                    // - A_U * W^b_{i+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
 #pragma unroll
-                for (int r = 0; r < S; ++r) A[r] += sud[r] * Wp[r] + sua[r] * wg;
-                A[S] += sud[S] * sg * wg;
+                    for (int r = 0; r < S; ++r) A[r] += sud[r] * Wp[r] + sua[r] * wg;
+                    A[S] += sud[S] * sg * wg;
+                } else {
+                    // - A_L * W_{i-1}:  A_L = -(diag l + a e_g^T)
+#pragma unroll
+                    for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;
+                    if (ST) A[NB - 1] += sl[NB - 1] * Wp[NB - 1];                   // phi row: A_L = -1 on the diagonal
+                    if (couple) {
+                        const double* xc = xch + j;
+                        const double xg = xc[S * NBP];
+#pragma unroll
+                        for (int r = 0; r < S; ++r) A[r] += sud[r] * xc[r * NBP] + sua[r] * xg;
+                        A[S] += sud[S] * sg * xg;
+                    }
+                }
             } else {
+                // bulk node: c rows identity; default Poisson BCs: g row identity;
+                // Stern: row S: phi_{n-1} = 0; row P: phi recursion with h_{n-2}
 #pragma unroll
                 for (int r = 0; r < S; ++r)
                     if (r == j) A[r] = 1.0;
@@ -493,35 +421,75 @@ __device__ bool factor_bottom(WarpState<NB, ST>& ws, double inv_gamma, int mid, 
                     if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
                 }
             }
+            if (i == 1) {
+                // park A_D1' for the second elimination (W1 is rewritten at the end of pass 1)
+                double* d1 = ws.W1 + j;
+#pragma unroll
+                for (int r = 0; r < NB; ++r) d1[r * NBP] = A[r];
+            }
         } else if (isI) {
 #pragma unroll
             for (int r = 0; r < NB; ++r)
                 if (r == j) A[r] = 1.0;
         } else if (isG) {
-            // g-column of A_L: -a_r on the transport rows
+            if (bottom) {
+                // g-column of A_L: -a_r on the transport rows
 #pragma unroll
-            for (int r = 0; r < NB; ++r) A[r] = r < S ? -sa[r] : 0.0;
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sa[r] : 0.0;
+            } else {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r] * sg;
+            }
         }
+
         ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
-        double Wc[NB];
+
+        // ---- store the inverse, form the W columns for the next node ----
+        int src = bottom ? wsrc_bot : wsrc_top;
+        if (pass == 1) {
+            if (isI) {
+                double* w1col = ws.W1 + j;
 #pragma unroll
-        for (int r = 0; r < NB; ++r) Wc[r] = A[r];
-        if (isI) {
-            const double lj = -sl[j];
+                for (int r = 0; r < NB; ++r) w1col[r * NBP] = A[r];
+            }
+            src = isD ? lane + NB : lane;
+        } else if (isI) {
+            // scale of column j of the coupling block: top A_U = diag(-ud) (c columns), bottom
+            // A_L = diag(-l) (c and phi columns); the g column comes from the G lane
+            const bool scaled = bottom ? (j != S) : (j < S);
+            const double cj = bottom ? -sl[j] : -sud[j];
+            const double ae = -sl[j];
+            double* v0col = ws.V0 + j;
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
                 invcol[r * NBP] = A[r];
-                if (j != S) Wc[r] = A[r] * lj;
+                if (wall) v0col[r * NBP] = A[r] * ae;
+                if (scaled) A[r] *= cj;
             }
         }
+        // (between the two eliminations of node 1 the I lanes still need their V_0 columns)
+        if (!(i == 1 && pass == 0 && !bottom)) {
 #pragma unroll
-        for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, Wc[r], wsrc);
-    }
-    if (isD) {
+            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, A[r], src);
+        }
+        if (ST && !bottom && pass == 0 && isD && j == NB - 1) {
+            // A_U has no phi column: W[:,phi] = 0
 #pragma unroll
-        for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
+            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+        }
+        if (wall && isI) {
+            // the I lanes keep V_0 columns for the modified A_U of node 1
+            const double* v0col = ws.V0 + j;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) Wp[r] = v0col[r * NBP];
+        }
+
+        // ---- next task ----
+        if (bottom) --i;
+        else if (i == 1 && pass == 0) pass = 1;
+        else { ++i; pass = 0; }
     }
-    pair_barrier(ws.bar_id);
+    __syncwarp();
     return __all_sync(FULL, ok);
 }
 
@@ -538,7 +506,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
         const double* y0 = y + (size_t)i * NB;
         double* out = ws.zb + (size_t)i * NB;
         if (i == 0 || i == n - 1) {
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < NB; ++r) {
                 double v = row_residual<NB, ST>(ws, y, i, r);
                 out[r] = v;
@@ -635,61 +603,128 @@ __device__ __forceinline__ double row_dot(const FactorRow<NB, ST>& f, const doub
     return s0 + s1;
 }
 
-// elimination of the right-hand side over `count` nodes starting at `first` in direction dir:
-//   dir=+1:  z_i = inv_i*(rhs_i - A_L z_{i-1})      (the first node of the range has no predecessor
-//   dir=-1:  z_i = inv_i*(rhs_i - A_U z_{i+1})       inside the range: its coupling term is skipped)
-// zb <- z.
+// ---- asynchronous global->shared copies (LDGSTS) with explicit shared addresses ------------------
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// A sweep walks up to TWO independent chains at once, one per half warp (lanes 0..15 and 16..31, row
+// r = lane & 15): with the twisted factorisation the upper chain (wall side) and the lower chain
+// (bulk side) have no data dependence, so one warp advances both in the same instruction stream and
+// the sequential depth of a sweep halves.  A chain is (first node, number of nodes, direction).
+struct Chain { int first, count, dir; };
+
+// Feeds the node records of a sweep into the shared-memory ring: per lane the running source
+// pointers of its 16-byte chunks, one commit group per sweep iteration (both chains' records).
 template <int NB, bool ST>
-__device__ void forward_solve(WarpState<NB, ST>& ws, int first, int count, int dir) {
-    constexpr int S = NB - 1 - (ST ? 1 : 0);
-    constexpr int REC = fac_rec<NB, ST>();
-    const int lane = ws.lane;
-    const int n = ws.cs.n;
-    const bool act = lane < NB;
-    const int r = act ? lane : 0;
-    double* tbuf = ws.scratch;           // 2*NB doubles (the pivot buffer is free here)
-    auto issue = [&](int k) {
-        const int i = first + dir * k;
-        if (k < count && i >= 0 && i < n) {
-            const double* src = ws.fac + (size_t)i * REC;
-            double* dst = ws.ring + (size_t)(k & (RING - 1)) * REC;
-            for (int c = lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
-        }
-        __pipeline_commit();
-    };
-#pragma unroll
-    for (int p = 0; p < RING - 1; ++p) issue(p);
-    double zprev = 0.0;
-    for (int k = 0; k < count; ++k) {
-        const int i = first + dir * k;
-        __pipeline_wait_prior(RING - 2);
-        __syncwarp();
-        FactorRow<NB, ST> f;
-        double z = 0.0;
-        if (act) {
-            ring_row<NB, ST>(ws, k & (RING - 1), r, f);
-            double t = ws.zb[(size_t)i * NB + r];
-            if (k > 0) {
-                const double zs = ws.zb[(size_t)(i - dir) * NB + S];
-                if (dir > 0) t = fma(f.co.x, zprev, fma(f.co.y, zs, t));      // rhs - A_L z_{i-1}
-                else t = fma(f.co.z, zprev, fma(f.co.w, zs, t));              // rhs - A_U z_{i+1}
-            }
-            tbuf[(k & 1) * NB + r] = t;
-        }
-        __syncwarp();
-        if (act) {
-            z = row_dot<NB, ST>(f, tbuf + (k & 1) * NB);
-            ws.zb[(size_t)i * NB + r] = z;
-        }
-        zprev = z;
-        issue(k + RING - 1);
+struct RecordFeed {
+    static constexpr int REC = fac_rec<NB, ST>();
+    static constexpr int CH = REC / 2;                   // 16-byte chunks per record
+    static_assert(CH <= 64, "a record is copied in at most two rounds of the warp");
+    const double* s0; const double* s1;                  // this lane's first chunk of the next record, per chain
+    long long st0, st1;                                  // doubles between consecutive records (+-REC)
+    unsigned dst;                                        // shared address of this lane's first chunk in slot 0
+    int n0, n1, two;
+    bool has2;
+    __device__ __forceinline__ void init(const double* fac, const double* ring, int lane, Chain c0, Chain c1) {
+        s0 = fac + (long long)c0.first * REC + 2 * lane; st0 = (long long)c0.dir * REC;
+        s1 = fac + (long long)c1.first * REC + 2 * lane; st1 = (long long)c1.dir * REC;
+        dst = (unsigned)__cvta_generic_to_shared(ring) + 16u * lane;
+        n0 = c0.count; n1 = c1.count; two = c1.count > 0 ? 2 : 1;
+        has2 = lane + 32 < CH;
     }
-    __pipeline_wait_prior(0);
+    // records of iteration k (calls must come with k = 0, 1, 2, ...)
+    __device__ __forceinline__ void issue(int k) {
+        if (k < n0) {
+            const unsigned d = dst + (unsigned)(((two * k) & (RING - 1)) * REC * 8);
+            cp_async16(d, s0);
+            if (has2) cp_async16(d + 512u, s0 + 64);
+            s0 += st0;
+        }
+        if (k < n1) {
+            const unsigned d = dst + (unsigned)(((2 * k + 1) & (RING - 1)) * REC * 8);
+            cp_async16(d, s1);
+            if (has2) cp_async16(d + 512u, s1 + 64);
+            s1 += st1;
+        }
+    }
+};
+
+// elimination of the right-hand side along a chain:
+//   dir=+1:  z_i = inv_i*(rhs_i - A_L z_{i-1})      (the first node of a chain has no predecessor
+//   dir=-1:  z_i = inv_i*(rhs_i - A_U z_{i+1})       inside the chain: its coupling term is skipped)
+// zb <- z.  c1.count may be 0 (single chain).  Lanes without a row (r >= NB) and the shorter chain in
+// its missing last iteration run the same arithmetic on valid dummy operands and only skip the stores,
+// so the loop body is free of divergent branches.
+template <int NB, bool ST>
+__device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
+    constexpr int REC = fac_rec<NB, ST>();
+    static_assert(NB <= 16, "a chain occupies half a warp");
+    const int lane = ws.lane;
+    const int grp = lane >> 4;
+    const int r0 = lane & 15;
+    const Chain me = grp ? c1 : c0;
+    const bool rowlane = r0 < NB;
+    const int r = rowlane ? r0 : 0;
+    const bool dual = c1.count > 0;
+    const int iters = max(c0.count, c1.count);
+    const int ahead = dual ? RING / 2 - 1 : RING - 1;    // iterations of look-ahead
+    RecordFeed<NB, ST> feed;
+    feed.init(ws.fac, ws.ring, lane, c0, c1);
+    for (int p = 0; p < ahead; ++p) { feed.issue(p); cp_commit(); }
+    double* tbuf = ws.scratch + grp * 2 * NBP;           // [parity][NBP] per chain
+    const double* ringrow = ws.ring + r * NBP;
+    const double* ringco = ws.ring + NB * NBP + 4 * r;
+    const int zstep = me.dir * NB;
+    int zo = me.first * NB + r;                          // this lane's unknown of the current node
+    double zprev = 0.0;
+    for (int k = 0; k < iters; ++k) {
+        if (dual) cp_wait<RING / 2 - 2>(); else cp_wait<RING - 2>();
+        __syncwarp();
+        const bool live = k < me.count;
+        const int slot = (dual ? 2 * k + grp : k) & (RING - 1);
+        FactorRow<NB, ST> f;
+        {
+            const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
+#pragma unroll
+            for (int c = 0; c < NBP / 2; ++c) {
+                const double2 t = p[c];
+                f.v[2 * c] = t.x;
+                if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
+            }
+            f.co = *reinterpret_cast<const double4*>(ringco + slot * REC);
+        }
+        double t = ws.zb[zo];
+        if (k > 0) {
+            const double zs = ws.zb[zo - zstep + (S - r)];
+            const double ca = me.dir > 0 ? f.co.x : f.co.z;          // -A_L or -A_U: diagonal ...
+            const double cb = me.dir > 0 ? f.co.y : f.co.w;          // ... and g column
+            t = fma(ca, zprev, fma(cb, zs, t));
+        }
+        double* tt = tbuf + (k & 1) * NBP;
+        if (rowlane) tt[r] = t;
+        __syncwarp();
+        const double z = row_dot<NB, ST>(f, tt);
+        if (rowlane && live) ws.zb[zo] = z;
+        zprev = z;
+        if (k + 1 < me.count) zo += zstep;
+        feed.issue(k + ahead);
+        cp_commit();
+    }
+    cp_wait<0>();
     __syncwarp();
 }
 
-// Back substitution over `count` nodes starting at `first` in direction dir, the solution of the
-// node before `first` (first-dir) being final already in zb:
+// Back substitution along a chain, the solution of the node before its first node (first-dir) being
+// final already in zb:
 //   dir=-1:  d_i = z_i - inv_i*(A_U d_{i+1})   (node 1: dense W_1; node 0: extra wall block V_0)
 //   dir=+1:  d_i = z_i - inv_i*(A_L d_{i-1})
 // y += scale*d, zb <- d.  Fused with the weighted max norms of the Newton update (|scale*d|*w)
@@ -698,7 +733,7 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int first, int count, int d
 // the weights and zn0 of each node ride in a second cp.async ring.
 // wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
 template <int NB, bool ST>
-__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int first, int count, int dir,
+__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Chain c1,
                                double& dmax, double& amax, int wmode, double prtol, double patol) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
@@ -706,83 +741,95 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int first, i
     constexpr int R2 = 2 * NBP;                  // doubles per node in the weight ring
     const int lane = ws.lane;
     const int n = ws.cs.n;
-    const bool act = lane < NB;
-    const int r = act ? lane : 0;
-    double* tbuf = ws.scratch;
-    double* ring2 = ws.ring + (size_t)RING * REC;
+    const int grp = lane >> 4;
+    const int r0 = lane & 15;
+    const Chain me = grp ? c1 : c0;
+    const bool rowlane = r0 < NB;
+    const int r = rowlane ? r0 : 0;
+    const bool dual = c1.count > 0;
+    const int iters = max(c0.count, c1.count);
+    const int ahead = dual ? RING / 2 - 1 : RING - 1;
+    RecordFeed<NB, ST> feed;
+    feed.init(ws.fac, ws.ring, lane, c0, c1);
+    // weight ring: lanes 0..NB-1 fetch ewt, lanes NB..2NB-1 zn0 of the node, per chain
+    const double* ring2 = ws.ring + (size_t)RING * REC;
+    const bool wl = wmode == 0 && lane < 2 * NB;
+    const double* wbase = (lane < NB ? ws.ewt + lane : ws.zn + (lane - NB));
+    const double* w0 = wbase + (long long)c0.first * NB;
+    const double* w1 = wbase + (long long)c1.first * NB;
+    const unsigned wdst = (unsigned)__cvta_generic_to_shared(ring2) + 8u * (lane < NB ? lane : NBP + lane - NB);
     auto issue = [&](int k) {
-        const int i = first + dir * k;
-        if (k < count && i >= 0 && i < n) {
-            const int slot = k & (RING - 1);
-            const double* src = ws.fac + (size_t)i * REC;
-            double* dst = ws.ring + (size_t)slot * REC;
-            for (int c = lane; c < REC / 2; c += 32) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
-            if (wmode == 0 && lane < 2 * NB) {
-                const double* s2 = (lane < NB ? ws.ewt : ws.zn - NB) + (size_t)i * NB + lane;
-                __pipeline_memcpy_async(ring2 + (size_t)slot * R2 + (lane < NB ? lane : NBP + lane - NB), s2, 8);
-            }
+        feed.issue(k);
+        if (wl) {
+            if (k < c0.count) { cp_async8(wdst + (unsigned)((((dual ? 2 : 1) * k) & (RING - 1)) * R2 * 8), w0); w0 += c0.dir * NB; }
+            if (k < c1.count) { cp_async8(wdst + (unsigned)(((2 * k + 1) & (RING - 1)) * R2 * 8), w1); w1 += c1.dir * NB; }
         }
-        __pipeline_commit();
+        cp_commit();
     };
-#pragma unroll
-    for (int p = 0; p < RING - 1; ++p) issue(p);
-    for (int k = 0; k < count; ++k) {
-        const int i = first + dir * k;
-        __pipeline_wait_prior(RING - 2);
+    for (int p = 0; p < ahead; ++p) issue(p);
+    double* tbuf = ws.scratch + grp * 2 * NBP;
+    const double* ringrow = ws.ring + r * NBP;
+    const double* ringco = ws.ring + NB * NBP + 4 * r;
+    const int zstep = me.dir * NB;
+    int zo = me.first * NB + r;
+    const bool crow = rowlane && r < S;                  // this lane owns a concentration unknown
+    for (int k = 0; k < iters; ++k) {
+        if (dual) cp_wait<RING / 2 - 2>(); else cp_wait<RING - 2>();
         __syncwarp();
-        const int slot = k & (RING - 1);
+        const bool live = k < me.count;
+        const int i = me.first + me.dir * k;
+        const int slot = (dual ? 2 * k + grp : k) & (RING - 1);
         FactorRow<NB, ST> f;
-        double d = 0.0;
-        if (dir < 0 && i == 1) {
-            if (act) {
-                const double* dn = ws.zb + 2 * NB;
-                const double* Wr = ws.W1 + (size_t)r * NBP;
-                double s = ws.zb[NB + r];
+        {
+            const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s = fma(-Wr[c], dn[c], s);
-                d = s;
+            for (int c = 0; c < NBP / 2; ++c) {
+                const double2 t = p[c];
+                f.v[2 * c] = t.x;
+                if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
             }
-        } else {
-            if (act) {
-                ring_row<NB, ST>(ws, slot, r, f);
-                const double* dn = ws.zb + (size_t)(i - dir) * NB;       // final solution of the neighbour
-                double t;
-                if (dir < 0) t = -(f.co.z * dn[r] + f.co.w * dn[S]);      // A_U d_{i+1} (ua = 0 off the c rows)
-                else t = -(f.co.x * dn[r] + f.co.y * dn[S]);              // A_L d_{i-1}
-                tbuf[(k & 1) * NB + r] = t;
-            }
-            __syncwarp();
-            if (act) {
-                d = ws.zb[(size_t)i * NB + r] - row_dot<NB, ST>(f, tbuf + (k & 1) * NB);
-                if (dir < 0 && i == 0) {
-                    const double* d2 = ws.zb + 2 * NB;
-                    const double* Vr = ws.V0 + (size_t)r * NBP;
-                    double s = 0.0;
+            f.co = *reinterpret_cast<const double4*>(ringco + slot * REC);
+        }
+        double* tt = tbuf + (k & 1) * NBP;
+        {
+            const double dr = ws.zb[zo - zstep];                     // final solution of the neighbour
+            const double dg = ws.zb[zo - zstep + (S - r)];
+            const double ca = me.dir < 0 ? f.co.z : f.co.x;          // A_U (dir<0) or A_L (dir>0)
+            const double cb = me.dir < 0 ? f.co.w : f.co.y;
+            if (rowlane) tt[r] = -(ca * dr + cb * dg);
+        }
+        __syncwarp();
+        double d = ws.zb[zo] - row_dot<NB, ST>(f, tt);
+        // wall side of the upper chain (warp-uniform test): node 1 couples through the dense W_1,
+        // node 0 has the extra block V_0 towards node 2
+        const int i0 = c0.first + c0.dir * k;
+        if (c0.dir < 0 && i0 <= 1 && k < c0.count) {
+            if (grp == 0 && rowlane) {
+                const double* d2 = ws.zb + 2 * NB;
+                const double* Mr = (i0 == 1 ? ws.W1 : ws.V0) + (size_t)r * NBP;
+                double s_ = 0.0;
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) s = fma(Vr[c], d2[c], s);
-                    d -= s;
-                }
+                for (int c = 0; c < NB; ++c) s_ = fma(Mr[c], d2[c], s_);
+                d = (i0 == 1 ? ws.zb[zo] : d) - s_;
             }
         }
-        if (act) {
-            const size_t idx = (size_t)i * NB + r;
-            ws.zb[idx] = d;
-            const double ds = d * scale;
-            const double yn = ws.y[idx] + ds;
-            ws.y[idx] = yn;
-            if (r < S && i < n - 1) {
-                double w, z0 = 0.0;
-                if (wmode == 0) { w = ring2[(size_t)slot * R2 + r]; z0 = ring2[(size_t)slot * R2 + NBP + r]; }
-                else w = 1.0 / (prtol * fabs(yn) + patol);
-                double ad = fabs(ds) * w;
-                if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
-                dmax = fmax(dmax, ad);
-                if (wmode == 0) amax = fmax(amax, fabs(yn - z0) * w);
-            }
+        const double ds = d * scale;
+        const double yn = ws.y[zo] + ds;
+        if (rowlane && live) { ws.zb[zo] = d; ws.y[zo] = yn; }
+        {
+            double w, z0 = 0.0;
+            if (wmode == 0) { w = ring2[slot * R2 + r]; z0 = ring2[slot * R2 + NBP + r]; }
+            else w = 1.0 / (prtol * fabs(yn) + patol);
+            double ad = fabs(ds) * w;
+            if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
+            const bool counted = crow && live && i < n - 1;
+            dmax = fmax(dmax, counted ? ad : 0.0);
+            if (wmode == 0) amax = fmax(amax, counted ? fabs(yn - z0) * w : 0.0);
         }
-        issue(k + RING - 1);
+        if (k + 1 < me.count) zo += zstep;
+        issue(k + ahead);
     }
-    __pipeline_wait_prior(0);
+    cp_wait<0>();
     __syncwarp();
 }
 

@@ -36,6 +36,8 @@ def main():
     print('steps by cell decile:', [int(stp[i]) for i in range(0, n_cells, max(1, n_cells // 10))])
     if os.environ.get('CATINT_PHASES'):
         tot = prof[:, 7].double().cpu().numpy(); print('total cycles min/mean/max %.3g %.3g %.3g' % (tot.min(), tot.mean(), tot.max()))
+        j = int(tot.argmax()); pj = prof[j].cpu().numpy()
+        print('slowest cell %d: steps %d newton %d setups %d cycles %s' % (j, stp[j], nw[j], sts[j], [int(v) for v in pj]))
         pr = prof.double().mean(dim=0).cpu().numpy()
         names = ['factor', 'residual', 'forward', 'backward', 'norms', 'history', 'correction', 'total']
         print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})

@@ -331,3 +331,26 @@ def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
         assert np.max(np.abs(out['phi'][-1, c].cpu().numpy() - go['phi_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['phi_%d' % c]))
         assert np.max(np.abs(out['g'][-1, c].cpu().numpy() - go['g_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['g_%d' % c]))
     assert n_ok >= 2
+
+
+def test_warm_start_from_results_folder(bk, resultsdir):
+    """system['init_folder']: a previous results folder initialises every cell (reference: calculator.py:303-309);
+    restarting from the converged sweep must reproduce it with a fraction of the steps."""
+    from catint_b200 import workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import Calculator
+    kw = workloads.c2(n_potentials=6, phi_min=-0.8, phi_max=-1.1)
+    tp = Transport(resultsdir=resultsdir, model_name='first', **kw)
+    tp.set_calculator('odeint')
+    c1 = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary')
+    r1 = c1.run()
+    kw2 = workloads.c2(n_potentials=6, phi_min=-0.8, phi_max=-1.1)
+    kw2['system']['init_folder'] = tp.outputfoldername
+    tp2 = Transport(resultsdir=resultsdir, model_name='second', **kw2)
+    tp2.set_calculator('odeint')
+    c2 = Calculator(transport=tp2, dt=0.5, tmax=200, ntout=1, mode='stationary')
+    r2 = c2.run()
+    assert c2.stats['converged'] == 6
+    cs = 93.7
+    assert relerr(r2['c'][-1], r1['c'][-1], cs) < 1e-8
+    assert r2['n_steps'].max() < 0.5 * r1['n_steps'].min()
