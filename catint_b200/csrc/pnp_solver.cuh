@@ -626,31 +626,33 @@ template <int NB, bool ST>
 struct RecordFeed {
     static constexpr int REC = fac_rec<NB, ST>();
     static constexpr int CH = REC / 2;                   // 16-byte chunks per record
-    static_assert(CH <= 64, "a record is copied in at most two rounds of the warp");
+    static constexpr int ROUNDS = (CH + 31) / 32;        // rounds of the warp per record
     const double* s0; const double* s1;                  // this lane's first chunk of the next record, per chain
     long long st0, st1;                                  // doubles between consecutive records (+-REC)
     unsigned dst;                                        // shared address of this lane's first chunk in slot 0
     int n0, n1, two;
-    bool has2;
+    int lane;
     __device__ __forceinline__ void init(const double* fac, const double* ring, int lane, Chain c0, Chain c1) {
         s0 = fac + (long long)c0.first * REC + 2 * lane; st0 = (long long)c0.dir * REC;
         s1 = fac + (long long)c1.first * REC + 2 * lane; st1 = (long long)c1.dir * REC;
         dst = (unsigned)__cvta_generic_to_shared(ring) + 16u * lane;
         n0 = c0.count; n1 = c1.count; two = c1.count > 0 ? 2 : 1;
-        has2 = lane + 32 < CH;
+        this->lane = lane;
     }
     // records of iteration k (calls must come with k = 0, 1, 2, ...)
     __device__ __forceinline__ void issue(int k) {
         if (k < n0) {
             const unsigned d = dst + (unsigned)(((two * k) & (RING - 1)) * REC * 8);
-            cp_async16(d, s0);
-            if (has2) cp_async16(d + 512u, s0 + 64);
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q)
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s0 + 64 * q);
             s0 += st0;
         }
         if (k < n1) {
             const unsigned d = dst + (unsigned)(((2 * k + 1) & (RING - 1)) * REC * 8);
-            cp_async16(d, s1);
-            if (has2) cp_async16(d + 512u, s1 + 64);
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q)
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s1 + 64 * q);
             s1 += st1;
         }
     }
