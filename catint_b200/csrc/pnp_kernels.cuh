@@ -197,15 +197,62 @@ __device__ void decrease_coef(const Bdf<NB, ST>& B, double* l) {
 //   (predict) Pascal triangle
 //   y = zn[0], psi = rl1*zn[1] - zn[0]
 // q_old is the order the array currently has, q_new the order after the change.
-template <int NB, bool ST>
+// The Nordsieck array lives in global memory (L2).  The element-wise passes over it are latency
+// bound when every lane waits for its own loads, so each lane prefetches its elements of the next
+// chunks (32 consecutive unknowns per warp) into the shared-memory ring of the solve sweeps with
+// cp.async, STREAM_DEPTH chunks ahead; a lane only ever reads back what it copied itself, hence no
+// barrier.  ring_doubles<NB,ST>() is the ring's size; small blocks (ring too short) load directly.
+template <int NB, bool ST, bool PAIR>
+__host__ __device__ constexpr int ring_doubles() {
+    return (PAIR ? RING_CHAIN : RING) * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+}
+template <int NB, bool ST, bool PAIR, int NARR>
+__host__ __device__ constexpr int stream_depth() {
+    return ring_doubles<NB, ST, PAIR>() / (NARR * 32) > 8 ? 8 : ring_doubles<NB, ST, PAIR>() / (NARR * 32);
+}
+
+template <int NB, bool ST, bool PAIR>
 __device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo, double eta,
                              const double* lc, double A1, double rl1, bool predict) {
     const int N = ws.N;
     const int q_new = q_old + dq;
-    for (int idx = ws.vlane; idx < N; idx += ws.vstride) {
-        double z[LMAX];
+    constexpr int SD = stream_depth<NB, ST, PAIR, LMAX>();
+    constexpr bool STREAM = SD >= 3;
+    const int nch = (N + ws.vstride - 1) / ws.vstride;
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(ws.ring) + 8u * ws.lane;
+    const double* sring = ws.ring + ws.lane;
+    int islot = 0, ichunk = 0;
+    auto issue = [&]() {
+        const int idx = ws.vlane + ichunk * ws.vstride;
+        if (ichunk < nch && idx < N) {
+            const unsigned d = sb + (unsigned)(islot * LMAX * 256);
 #pragma unroll
-        for (int j = 0; j < LMAX; ++j) z[j] = (j <= q_old) ? ws.zn[(size_t)j * N + idx] : 0.0;
+            for (int j = 0; j < LMAX; ++j)
+                if (j <= q_old) cp_async8(d + 256u * j, ws.zn + (size_t)j * N + idx);
+        }
+        cp_commit();
+        ++ichunk;
+        islot = (islot + 1 == SD) ? 0 : islot + 1;
+    };
+    if constexpr (STREAM) {
+#pragma unroll 1
+        for (int p = 0; p < SD - 1; ++p) issue();
+    }
+    int rslot = 0;
+    for (int c = 0; c < nch; ++c) {
+        const int idx = ws.vlane + c * ws.vstride;
+        if constexpr (STREAM) cp_wait<(SD >= 3 ? SD - 2 : 0)>();
+        if (idx >= N) { if constexpr (STREAM) { issue(); rslot = (rslot + 1 == SD) ? 0 : rslot + 1; } continue; }
+        double z[LMAX];
+        if constexpr (STREAM) {
+            const double* s = sring + rslot * LMAX * 32;
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j) z[j] = (j <= q_old) ? s[j * 32] : 0.0;
+            rslot = (rslot + 1 == SD) ? 0 : rslot + 1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < LMAX; ++j) z[j] = (j <= q_old) ? ws.zn[(size_t)j * N + idx] : 0.0;
+        }
         if (undo) {
 #pragma unroll
             for (int k = 1; k <= QMAX; ++k)
@@ -251,7 +298,9 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo
             ws.y[idx] = z[0];
             ws.psi[idx] = rl1 * z[1] - z[0];
         }
+        if constexpr (STREAM) issue();
     }
+    if constexpr (STREAM) cp_wait<0>();
     __syncwarp();
 }
 
@@ -267,7 +316,7 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo
 //   Both warps execute the same (scalar) step/order control on identical norms, so they stay in
 //   lock step; a named hardware barrier (bar.sync id, 64) is the pair barrier.  Experimental, see
 //   launch_bdf.
-constexpr int PAIR_CELLS = 6;      // cells (warp pairs) per block in PAIR mode (shared memory: 6 x 35.6 KB at b=9)
+constexpr int PAIR_CELLS = 7;      // cells (warp pairs) per block in PAIR mode: 148 x 7 = 1036 cells in one wave
 
 template <bool PAIR>
 __device__ __forceinline__ void pair_sync(int bar_id) { if constexpr (PAIR) pair_barrier(bar_id); }
@@ -350,7 +399,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
     // per cell: CellSpecies | per warp {scratch | ring} | [y zb] | pair exchange (xch block, norms)
-    constexpr size_t RINGD = (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    constexpr size_t RINGD = (size_t)ring_doubles<NB, ST, PAIR>();
     constexpr size_t WARPD = scratch_doubles<NB, ST>() + RINGD;          // doubles private to one warp
     constexpr int WPC = PAIR ? 2 : 1;                                     // warps per cell
     const size_t cell_doubles = WPC * WARPD + (SMEM ? (size_t)2 * nxm * NB : 0) +
@@ -479,7 +528,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             B.t = saved_t + B.h;
             set_bdf<NB, ST>(B);
             const double rl1 = 1.0 / B.l[1];
-            { CATINT_TIC; history_pass<NB, ST>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+            { CATINT_TIC; history_pass<NB, ST, PAIR>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
               pair_sync<PAIR>(ws.bar_id); CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
@@ -565,7 +614,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 pend_eta = ETAMIN;
             } else {
                 // order 1 and still failing: restart the history from the last accepted state
-                history_pass<NB, ST>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
+                history_pass<NB, ST, PAIR>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
                 pend_undo = false;
                 B.h *= ETAMIN; B.hscale = B.h;
                 B.qwait = LONG_WAIT;
@@ -606,42 +655,68 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             for (int j = 0; j < LMAX; ++j) lreg[j] = B.l[j];
             double* __restrict__ zn = ws.zn;
             double* __restrict__ ewt = ws.ewt;
-            for (int base = vlane; base < N; base += 2 * vstride) {
-                int idx[2]; bool has[2]; double yv[2], w[2], z0[2], zq[2], zj[2][LMAX];
+            constexpr int NARR = LMAX + 1;                           // zn[0..QMAX] and the weights
+            constexpr int SD = stream_depth<NB, ST, PAIR, NARR>();
+            constexpr bool STREAM = SD >= 3;
+            const int nch = (N + vstride - 1) / vstride;
+            const unsigned sb = (unsigned)__cvta_generic_to_shared(ws.ring) + 8u * lane;
+            const double* sring = ws.ring + lane;
+            int islot = 0, ichunk = 0;
+            auto issue = [&]() {
+                const int ii = vlane + ichunk * vstride;
+                if (ichunk < nch && ii < N) {
+                    const unsigned d = sb + (unsigned)(islot * NARR * 256);
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    idx[u] = base + vstride * u;
-                    has[u] = idx[u] < N;
-                    const int ii = has[u] ? idx[u] : base;
-                    yv[u] = ws.y[ii];
-                    z0[u] = zn[ii];
-                    w[u] = ewt[ii];
-                    zq[u] = want_up ? zn[(size_t)QMAX * N + ii] : 0.0;
-#pragma unroll
-                    for (int j = 1; j <= QMAX; ++j) zj[u][j] = (j <= q) ? zn[(size_t)j * N + ii] : 0.0;
+                    for (int j = 0; j < LMAX; ++j)
+                        if (j <= q || (j == QMAX && want_up)) cp_async8(d + 256u * j, zn + (size_t)j * N + ii);
+                    cp_async8(d + 256u * LMAX, ewt + ii);
                 }
+                cp_commit();
+                ++ichunk;
+                islot = (islot + 1 == SD) ? 0 : islot + 1;
+            };
+            if constexpr (STREAM) {
+#pragma unroll 1
+                for (int p_ = 0; p_ < SD - 1; ++p_) issue();
+            }
+            int rslot = 0;
+            for (int c = 0; c < nch; ++c) {
+                const int ii = vlane + c * vstride;
+                if constexpr (STREAM) cp_wait<(SD >= 3 ? SD - 2 : 0)>();
+                if (ii < N) {
+                    double zj[LMAX], w;
+                    if constexpr (STREAM) {
+                        const double* s = sring + rslot * NARR * 32;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (!has[u]) continue;
-                    const int ii = idx[u];
+                        for (int j = 0; j < LMAX; ++j) zj[j] = (j <= q || (j == QMAX && want_up)) ? s[j * 32] : 0.0;
+                        w = s[LMAX * 32];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < LMAX; ++j)
+                            zj[j] = (j <= q || (j == QMAX && want_up)) ? zn[(size_t)j * N + ii] : 0.0;
+                        w = ewt[ii];
+                    }
+                    const double yv = ws.y[ii];
                     const int i = ii / NB, r = ii - i * NB;
                     const bool mass = r < S && i < n - 1;
-                    const double ac = yv[u] - z0[u];
-                    if (want_up && mass) dup = fmax(dup, fabs(ac - cquot * zq[u]) * w[u]);
-                    zn[ii] = yv[u];
+                    const double ac = yv - zj[0];
+                    if (want_up && mass) dup = fmax(dup, fabs(ac - cquot * zj[QMAX]) * w);
+                    zn[ii] = yv;
 #pragma unroll
                     for (int j = 1; j <= QMAX; ++j) {
                         if (j <= q) {
-                            const double v = zj[u][j] + lreg[j] * ac;
+                            const double v = zj[j] + lreg[j] * ac;
                             zn[(size_t)j * N + ii] = v;
-                            if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w[u]);
+                            if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w);
                         }
                     }
                     if (save_acor) zn[(size_t)QMAX * N + ii] = ac;
                     ws.zb[ii] = ac;
-                    ewt[ii] = 1.0 / (rtol * fabs(yv[u]) + atol);
+                    ewt[ii] = 1.0 / (rtol * fabs(yv) + atol);
                 }
+                if constexpr (STREAM) { issue(); rslot = (rslot + 1 == SD) ? 0 : rslot + 1; }
             }
+            if constexpr (STREAM) cp_wait<0>();
         }
         __syncwarp();
         ddn = pair_max<PAIR>(ddn, xn, half, lane, ws.bar_id);      // also the pair barrier that ends the correction pass
@@ -914,7 +989,8 @@ template <int NB, bool ST>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
     const size_t species = ((sizeof(CellSpecies) + 15) & ~size_t(15));
-    const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST, false>();
+    const size_t warpd_pair = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST, true>();
     const size_t state = (size_t)2 * P.tb.nx_max * NB;
     int dev = 0; cudaGetDevice(&dev);
     int max_optin = 0;
@@ -923,7 +999,7 @@ int launch_bdf(SolveParams& P, cudaStream_t st) {
     //     tests) but measured slower than (2) on the 1024-cell C2 batch (0.91-1.5 s vs 0.65 s per launch): at
     //     12-14 warps/SM the kernel is limited to 128 registers/thread and spills ~4.8 KB/thread into an L1
     //     that the 186 KB of shared state leaves almost empty.  Needs a leaner factor sweep first (round 2).
-    const size_t smem_pair = base + PAIR_CELLS * (species + (2 * warpd + state + (size_t)NB * padded<NB, ST>() + 4) * sizeof(double));
+    const size_t smem_pair = base + PAIR_CELLS * (species + (2 * warpd_pair + state + (size_t)NB * padded<NB, ST>() + 4) * sizeof(double));
     const char* env = getenv("CATINT_PNP_PAIR");
     const bool want_pair = (env && env[0] == '1') && P.tb.nx_max >= 12;
     // (2) one warp per cell, four cells per block, state in shared memory; (3) state in the workspace

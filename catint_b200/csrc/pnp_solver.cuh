@@ -61,7 +61,10 @@ __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 // doubles per node of the stored factors: inverse block (padded rows) + 4 coefficients per row
 template <int NB, bool ST>
 __host__ __device__ constexpr int fac_rec() { return NB * padded<NB, ST>() + NB * 4; }
-constexpr int RING = 8;   // node records in flight in the solve sweeps (power of two)
+// Node records in flight in the solve sweeps: four per chain (three iterations of look-ahead).  One warp
+// per cell walks two chains (8 slots), a warp of a pair one chain (4 slots).
+constexpr int RING_CHAIN = 4;
+constexpr int RING = 2 * RING_CHAIN;   // slots of the one-warp-per-cell ring
 
 // ---------------------------------------------------------------------------
 // Gauss-Jordan elimination with threshold partial pivoting; lane j owns column j
@@ -86,46 +89,45 @@ __device__ __forceinline__ double pivot_rcp(double a) {
 
 template <int NB, bool ST>
 __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* pivbuf) {
+    // ROLLED elimination: the pivot row always sits in register slot 0 and the rows rotate up by one
+    // slot per step (after NB steps every row is back in its place), so one loop body with static
+    // register indices serves all NB steps.  The fully unrolled form is ~8x larger and made the
+    // factorisation loop overflow the SM's instruction cache.  Slots 0..NB-1-k hold the
+    // rows not yet used as pivots.  The pivot column is broadcast from lane k by shuffles.
+    (void)pivbuf;
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < NB; ++k) {
-        double* buf = pivbuf + (k & 1) * (NB + 2);
-        // magnitude keys: high word of |a| with the row index in the low 4 bits
-        int best = ((__double2hiint(A[k]) & 0x7fffffff) & ~0xf) | k;
+        // magnitude keys: high word of |a| with the slot index in the low 4 bits
+        int best = (__double2hiint(A[0]) & 0x7ffffff0);
         const int diag = best;
 #pragma unroll
-        for (int r = k + 1; r < NB; ++r) {
-            const int key = ((__double2hiint(A[r]) & 0x7fffffff) & ~0xf) | r;
+        for (int r = 1; r < NB; ++r) {
+            const int key = (r < NB - k) ? ((__double2hiint(A[r]) & 0x7ffffff0) | r) : 0;
             best = max(best, key);
         }
         // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
         int p = best & 0xf;
-        if (diag + (3 << 20) >= best) p = k;
+        if (diag + (3 << 20) >= best) p = 0;
         p = __shfl_sync(FULL, p, k);          // the decision of the lane that owns column k
-        if (p != k) {                          // warp-uniform: rows k and p change places
-            double ak = A[k];
+        if (p != 0) {                          // warp-uniform: slots 0 and p change places
+            double a0 = A[0];
 #pragma unroll
-            for (int r = k + 1; r < NB; ++r) {
-                if (r == p) { const double t = A[r]; A[r] = ak; ak = t; }
+            for (int r = 1; r < NB; ++r) {
+                if (r == p) { const double t = A[r]; A[r] = a0; a0 = t; }
             }
-            A[k] = ak;
+            A[0] = a0;
         }
-        if (lane == k) {
-#pragma unroll
-            for (int r = 0; r < NB; ++r) buf[r] = A[r];
-        }
-        __syncwarp();
         double col[NB];
 #pragma unroll
-        for (int r = 0; r < NB; ++r) col[r] = buf[r];
-        const double ck = col[k];
+        for (int r = 0; r < NB; ++r) col[r] = __shfl_sync(FULL, A[r], k);
+        const double ck = col[0];
         const double inv = pivot_rcp(ck);
         ok = ok && (ck != 0.0) && (fabs(inv) < 1e300);
-        const double ak = A[k] * inv;
-        A[k] = ak;
+        const double a0 = A[0] * inv;
 #pragma unroll
-        for (int r = 0; r < NB; ++r)
-            if (r != k) A[r] = fma(-col[r], ak, A[r]);
+        for (int r = 1; r < NB; ++r) A[r - 1] = fma(-col[r], a0, A[r]);     // eliminate and rotate
+        A[NB - 1] = a0;
     }
     return ok;
 }
@@ -642,7 +644,7 @@ struct RecordFeed {
     // records of iteration k (calls must come with k = 0, 1, 2, ...)
     __device__ __forceinline__ void issue(int k) {
         if (k < n0) {
-            const unsigned d = dst + (unsigned)(((two * k) & (RING - 1)) * REC * 8);
+            const unsigned d = dst + (unsigned)(((two * k) & (RING_CHAIN * two - 1)) * REC * 8);
 #pragma unroll
             for (int q = 0; q < ROUNDS; ++q)
                 if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s0 + 64 * q);
@@ -678,7 +680,7 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
     const int r = rowlane ? r0 : 0;
     const bool dual = c1.count > 0;
     const int iters = max(c0.count, c1.count);
-    const int ahead = dual ? RING / 2 - 1 : RING - 1;    // iterations of look-ahead
+    constexpr int ahead = RING_CHAIN - 1;                // iterations of look-ahead
     RecordFeed<NB, ST> feed;
     feed.init(ws.fac, ws.ring, lane, c0, c1);
     for (int p = 0; p < ahead; ++p) { feed.issue(p); cp_commit(); }
@@ -689,10 +691,10 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
     int zo = me.first * NB + r;                          // this lane's unknown of the current node
     double zprev = 0.0;
     for (int k = 0; k < iters; ++k) {
-        if (dual) cp_wait<RING / 2 - 2>(); else cp_wait<RING - 2>();
+        cp_wait<RING_CHAIN - 2>();
         __syncwarp();
         const bool live = k < me.count;
-        const int slot = (dual ? 2 * k + grp : k) & (RING - 1);
+        const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
         FactorRow<NB, ST> f;
         {
             const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
@@ -750,11 +752,11 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
     const int r = rowlane ? r0 : 0;
     const bool dual = c1.count > 0;
     const int iters = max(c0.count, c1.count);
-    const int ahead = dual ? RING / 2 - 1 : RING - 1;
+    constexpr int ahead = RING_CHAIN - 1;
     RecordFeed<NB, ST> feed;
     feed.init(ws.fac, ws.ring, lane, c0, c1);
     // weight ring: lanes 0..NB-1 fetch ewt, lanes NB..2NB-1 zn0 of the node, per chain
-    const double* ring2 = ws.ring + (size_t)RING * REC;
+    const double* ring2 = ws.ring + (size_t)(dual ? RING : RING_CHAIN) * REC;
     const bool wl = wmode == 0 && lane < 2 * NB;
     const double* wbase = (lane < NB ? ws.ewt + lane : ws.zn + (lane - NB));
     const double* w0 = wbase + (long long)c0.first * NB;
@@ -763,7 +765,7 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
     auto issue = [&](int k) {
         feed.issue(k);
         if (wl) {
-            if (k < c0.count) { cp_async8(wdst + (unsigned)((((dual ? 2 : 1) * k) & (RING - 1)) * R2 * 8), w0); w0 += c0.dir * NB; }
+            if (k < c0.count) { cp_async8(wdst + (unsigned)((dual ? ((2 * k) & (RING - 1)) : (k & (RING_CHAIN - 1))) * R2 * 8), w0); w0 += c0.dir * NB; }
             if (k < c1.count) { cp_async8(wdst + (unsigned)(((2 * k + 1) & (RING - 1)) * R2 * 8), w1); w1 += c1.dir * NB; }
         }
         cp_commit();
@@ -776,11 +778,11 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
     int zo = me.first * NB + r;
     const bool crow = rowlane && r < S;                  // this lane owns a concentration unknown
     for (int k = 0; k < iters; ++k) {
-        if (dual) cp_wait<RING / 2 - 2>(); else cp_wait<RING - 2>();
+        cp_wait<RING_CHAIN - 2>();
         __syncwarp();
         const bool live = k < me.count;
         const int i = me.first + me.dir * k;
-        const int slot = (dual ? 2 * k + grp : k) & (RING - 1);
+        const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
         FactorRow<NB, ST> f;
         {
             const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
