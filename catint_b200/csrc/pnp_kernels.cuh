@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     so.scratch = (unsigned)(reinterpret_cast<unsigned char*>(ws.scratch) - smem_raw);
     so.sp = (unsigned)(reinterpret_cast<const unsigned char*>(sp) - smem_raw);
     so.y = SMEM ? (unsigned)(reinterpret_cast<unsigned char*>(ws.y) - smem_raw) : 0u;
+    so.ring = (unsigned)(reinterpret_cast<unsigned char*>(ws.ring) - smem_raw);
     const int vlane = ws.vlane, vstride = ws.vstride;
 
     // ---- initial state: y0 (or bulk) with the consistent field --------------

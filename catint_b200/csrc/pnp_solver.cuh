@@ -186,13 +186,10 @@ __device__ __forceinline__ double row_residual(const WarpState<NB, ST>& ws, cons
 //   interior: sl,sa = dF_r/dc_{r,i-1}, dF_r/dg_{i-1};  sud,sua = dF_r/dc_{r,i+1}, dF_r/dg_{i+1}
 //   wall:     sa = dF_r/dy_{r,0} (diagonal), sud,sua w.r.t. node 1, sl = dF_r/dy_{r,2} (extra block)
 template <int NB, bool ST>
-__device__ __forceinline__ void node_coeffs(const WarpState<NB, ST>& ws, const double* y, int i,
-                                            double* sl, double* sa, double* sud, double* sua) {
+__device__ __forceinline__ double4 node_coeff_row(const WarpState<NB, ST>& ws, const double* y, int i, int r) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
-    const int r = ws.lane;
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
-    if (r >= NB) return;
     double l = 0.0, a = 0.0, ud = 0.0, ua = 0.0;
     const double* y0 = y + (size_t)i * NB;
     if (i == 0) {
@@ -228,7 +225,16 @@ __device__ __forceinline__ void node_coeffs(const WarpState<NB, ST>& ws, const d
     } else if (ST && r == S + 1) {
         l = 1.0;                           // bulk node, phi recursion row: dF/dphi_{n-2}
     }
-    sl[r] = l; sa[r] = a; sud[r] = ud; sua[r] = ua;
+    return make_double4(l, a, ud, ua);
+}
+
+template <int NB, bool ST>
+__device__ __forceinline__ void node_coeffs(const WarpState<NB, ST>& ws, const double* y, int i,
+                                            double* sl, double* sa, double* sud, double* sua) {
+    const int r = ws.lane;
+    if (r >= NB) return;
+    const double4 c = node_coeff_row<NB, ST>(ws, y, i, r);
+    sl[r] = c.x; sa[r] = c.y; sud[r] = c.z; sua[r] = c.w;
 }
 
 // column j (< NB) of A_D = Mass*inv_gamma - dF_i/dy_i at an interior node, g-row scaled by sg
@@ -263,6 +269,61 @@ __device__ __forceinline__ void interior_diag_column(const WarpState<NB, ST>& ws
     }
 }
 
+// ---- asynchronous global->shared copies (LDGSTS) with explicit shared addresses ------------------
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// A sweep walks up to TWO independent chains at once, one per half warp (lanes 0..15 and 16..31, row
+// r = lane & 15): with the twisted factorisation the upper chain (wall side) and the lower chain
+// (bulk side) have no data dependence, so one warp advances both in the same instruction stream and
+// the sequential depth of a sweep halves.  A chain is (first node, number of nodes, direction).
+struct Chain { int first, count, dir; };
+
+// Feeds the node records of a sweep into the shared-memory ring: per lane the running source
+// pointers of its 16-byte chunks, one commit group per sweep iteration (both chains' records).
+template <int NB, bool ST>
+struct RecordFeed {
+    static constexpr int REC = fac_rec<NB, ST>();
+    static constexpr int CH = REC / 2;                   // 16-byte chunks per record
+    static constexpr int ROUNDS = (CH + 31) / 32;        // rounds of the warp per record
+    const double* s0; const double* s1;                  // this lane's first chunk of the next record, per chain
+    long long st0, st1;                                  // doubles between consecutive records (+-REC)
+    unsigned dst;                                        // shared address of this lane's first chunk in slot 0
+    int n0, n1, two;
+    int lane;
+    __device__ __forceinline__ void init(const double* fac, const double* ring, int lane, Chain c0, Chain c1) {
+        s0 = fac + (long long)c0.first * REC + 2 * lane; st0 = (long long)c0.dir * REC;
+        s1 = fac + (long long)c1.first * REC + 2 * lane; st1 = (long long)c1.dir * REC;
+        dst = (unsigned)__cvta_generic_to_shared(ring) + 16u * lane;
+        n0 = c0.count; n1 = c1.count; two = c1.count > 0 ? 2 : 1;
+        this->lane = lane;
+    }
+    // records of iteration k (calls must come with k = 0, 1, 2, ...)
+    __device__ __forceinline__ void issue(int k) {
+        if (k < n0) {
+            const unsigned d = dst + (unsigned)(((two * k) & (RING_CHAIN * two - 1)) * REC * 8);
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q)
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s0 + 64 * q);
+            s0 += st0;
+        }
+        if (k < n1) {
+            const unsigned d = dst + (unsigned)(((2 * k + 1) & (RING - 1)) * REC * 8);
+#pragma unroll
+            for (int q = 0; q < ROUNDS; ++q)
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s1 + 64 * q);
+            s1 += st1;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // Twisted block factorisation of the Newton matrix.  Lanes: D = 0..NB-1 (columns of A_D'),
 // I = NB..2NB-1 (identity -> inverse), G = 2NB (g-column of the coupling block -> W[:,g]).
@@ -285,16 +346,26 @@ constexpr int FACTOR_TOP = 1, FACTOR_BOTTOM = 2, FACTOR_BOTH = 3;
 // local memory and turn every shared-memory access of the whole kernel into a generic one.  Pointers
 // that cross the call lose their address space, so the shared-memory ones are rebuilt here from
 // byte offsets into the block's dynamic shared memory (SmemOffsets) and come out as LDS/STS again.
-struct SmemOffsets { unsigned scratch, sp, y; };
+//
+// Two phases.  ASSEMBLY: the Jacobian blocks of all nodes are independent of each other, so every
+// lane assembles one column of A_D and one row of coefficients of a different (node, unknown) pair
+// at a time, with the whole warp busy, straight into the node records in global memory.
+// ELIMINATION: the sequential sweep then only streams the records back through the cp.async ring
+// (three nodes ahead), applies the Schur update and eliminates.  Doing the assembly inside the
+// sequential sweep (one node at a time, 9 of 32 lanes busy, every load latency exposed) cost more
+// than the elimination itself.
+struct SmemOffsets { unsigned scratch, sp, y, ring; };
 
 template <int NB, bool ST, bool SMEM>
 __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
                                           int mid, double* xch, int parts) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
+    constexpr int REC = fac_rec<NB, ST>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpState<NB, ST> ws = ws_in;
     ws.scratch = reinterpret_cast<double*>(smem_raw + so.scratch);
+    ws.ring = reinterpret_cast<double*>(smem_raw + so.ring);
     ws.sp = reinterpret_cast<const CellSpecies*>(smem_raw + so.sp);
     ws.tb = reinterpret_cast<const DevTables*>(smem_raw);
     if constexpr (SMEM) ws.y = reinterpret_cast<double*>(smem_raw + so.y);
@@ -302,10 +373,29 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
     double* pivbuf = ws.scratch;
-    double* sl = ws.scratch + 2 * (NB + 2);
-    double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
     const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
     const int j = isD ? lane : lane - NB;
+    const double* y = ws.y;
+
+    // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
+    for (int item = ws.vlane; item < n * NB; item += ws.vstride) {
+        const int i = item / NB, r = item - i * NB;
+        double* rec = ws.fac + (size_t)i * REC;
+        double4 co = node_coeff_row<NB, ST>(ws, y, i, r);
+        if (i > 0 && i < n - 1) {
+            const NodeCoef k = interior_coef(ws.cs, i);
+            const double sg = mig ? grow_scale(ws.cs, k.hi) : 1.0;
+            if (r == S) co.z *= sg;                                  // g row of A_U carries the row scale
+            double C[NB];
+            interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, r, k, inv_gamma, sg, C);
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr) rec[rr * NBP + r] = C[rr];
+        }
+        reinterpret_cast<double4*>(rec + NB * NBP)[r] = co;
+    }
+    __syncwarp();
+    if (parts != FACTOR_BOTH) pair_barrier(ws.bar_id);               // the pair shares the assembly
+
     // source lane of the W column that D-lane j needs for the next Schur update: the scaled inverse
     // column where the coupling block has a diagonal entry in column j, the G lane for the g column
     const int wsrc_top = isD ? (j < S ? lane + NB : 2 * NB) : lane;
@@ -314,11 +404,16 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 #pragma unroll
     for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
     bool ok = true;
-    const double* y = ws.y;
 
     bool bottom = (parts & FACTOR_BOTTOM) != 0;
     int i = bottom ? n - 1 : 0;
     int pass = 0;            // node 1 is eliminated twice (pass 1: [A_D1' | A_U1'] -> dense W_1)
+    const Chain none = {0, 0, 1};
+    RecordFeed<NB, ST> feed;
+    int kk = 0;              // position in the current chain
+    feed.init(ws.fac, ws.ring, lane, bottom ? Chain{n - 1, n - 1 - mid, -1} : Chain{0, mid + 1, +1}, none);
+#pragma unroll 1
+    for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
 #pragma unroll 1
     for (;;) {
         if (bottom && i <= mid) {
@@ -331,44 +426,45 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
             bottom = false; i = 0;
 #pragma unroll
             for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+            cp_wait<0>();
+            __syncwarp();
+            kk = 0;
+            feed.init(ws.fac, ws.ring, lane, Chain{0, mid + 1, +1}, none);
+#pragma unroll 1
+            for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
         }
         if (!bottom && i > mid) break;
 
         const bool bulk = (i == n - 1);
         const bool wall = (i == 0);
         const bool couple = !bottom && (i == mid);
-        double* rec = ws.fac + (size_t)i * fac_rec<NB, ST>();
+        double* rec = ws.fac + (size_t)i * REC;
         double* invcol = rec + j;                                   // column j of inv_i (I lanes)
         NodeCoef k = NodeCoef{0, 0, 0, 1, 1};
-        if (!wall) k = interior_coef(ws.cs, bulk ? i - 1 : i);
-        const double sg = (!wall && !bulk && mig) ? grow_scale(ws.cs, k.hi) : 1.0;
-        __syncwarp();
-        if (pass == 0) {
-            node_coeffs<NB, ST>(ws, y, i, sl, sa, sud, sua);
-            __syncwarp();
-            if (lane < NB) {
-                double4 v;
-                v.x = sl[lane]; v.y = sa[lane];
-                v.z = (lane == S && !wall) ? sud[lane] * sg : sud[lane];
-                v.w = sua[lane];
-                reinterpret_cast<double4*>(rec + NB * NBP)[lane] = v;
-            }
-        }
+        if (bulk) k = interior_coef(ws.cs, i - 1);
+        if (pass == 0) { cp_wait<RING_CHAIN - 2>(); __syncwarp(); }
+        // the node's record in the ring: raw A_D and the coefficient rows (ud of the g row is scaled)
+        const double* rr_ = ws.ring + (size_t)(kk & (RING_CHAIN - 1)) * REC;
+        const double* cof = rr_ + NB * NBP;
+#define C_L(r_) cof[4 * (r_)]
+#define C_A(r_) cof[4 * (r_) + 1]
+#define C_UD(r_) cof[4 * (r_) + 2]
+#define C_UA(r_) cof[4 * (r_) + 3]
         if (couple) pair_barrier(ws.bar_id);   // the bottom half has published W^b_{mid+1}
 #pragma unroll
         for (int r = 0; r < NB; ++r) A[r] = 0.0;
 
         // ---- column j of [A_D' | I | u_g] ----
         if (wall) {
-            // A_D0 is diag(mass*inv_gamma - sa); A_U0 = diag(-sud) + g-column(-sua); A_E = diag(-sl)
+            // A_D0 is diag(mass*inv_gamma - a); A_U0 = diag(-ud) + g-column(-ua); A_E = diag(-l)
             if (isD || isI) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r)
-                    if (r == j) A[r] = isD ? ((j < S ? inv_gamma : 0.0) - sa[r]) : 1.0;
+                    if (r == j) A[r] = isD ? ((j < S ? inv_gamma : 0.0) - C_A(r)) : 1.0;
                 if (ST && isD && j == S) A[NB - 1] = ws.cs.eps / ws.cs.cstern;      // -dF_phi/dg_0 (Robin row)
             } else if (isG) {
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r];
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
             }
         } else if (pass == 1) {
             // node 1, second elimination: A_U1' = A_U1 - A_L1*V_0 (dense in general)
@@ -381,33 +477,34 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 #pragma unroll
                 for (int r = 0; r < NB; ++r) {
                     double v = 0.0;
-                    if (r == j) v = (r < S) ? -sud[r] : -sud[r] * sg;
-                    if (j == S && r < S) v = -sua[r];
-                    if (r < S) v += sl[r] * Wp[r] + sa[r] * vg;
-                    if (ST && r == NB - 1) v += sl[r] * Wp[r];
+                    if (r == j) v = -C_UD(r);
+                    if (j == S && r < S) v = -C_UA(r);
+                    if (r < S) v += C_L(r) * Wp[r] + C_A(r) * vg;
+                    if (ST && r == NB - 1) v += C_L(r) * Wp[r];
                     A[r] = v;
                 }
             }
         } else if (isD) {
             if (!bulk) {
-                interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, j, k, inv_gamma, sg, A);
+#pragma unroll
+                for (int r = 0; r < NB; ++r) A[r] = rr_[r * NBP + j];
                 const double wg = Wp[S];
                 if (bottom) {
                     // - A_U * W^b_{i+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
 #pragma unroll
-                    for (int r = 0; r < S; ++r) A[r] += sud[r] * Wp[r] + sua[r] * wg;
-                    A[S] += sud[S] * sg * wg;
+                    for (int r = 0; r < S; ++r) A[r] += C_UD(r) * Wp[r] + C_UA(r) * wg;
+                    A[S] += C_UD(S) * wg;
                 } else {
                     // - A_L * W_{i-1}:  A_L = -(diag l + a e_g^T)
 #pragma unroll
-                    for (int r = 0; r < S; ++r) A[r] += sl[r] * Wp[r] + sa[r] * wg;
-                    if (ST) A[NB - 1] += sl[NB - 1] * Wp[NB - 1];                   // phi row: A_L = -1 on the diagonal
+                    for (int r = 0; r < S; ++r) A[r] += C_L(r) * Wp[r] + C_A(r) * wg;
+                    if (ST) A[NB - 1] += C_L(NB - 1) * Wp[NB - 1];                  // phi row: A_L = -1 on the diagonal
                     if (couple) {
                         const double* xc = xch + j;
                         const double xg = xc[S * NBP];
 #pragma unroll
-                        for (int r = 0; r < S; ++r) A[r] += sud[r] * xc[r * NBP] + sua[r] * xg;
-                        A[S] += sud[S] * sg * xg;
+                        for (int r = 0; r < S; ++r) A[r] += C_UD(r) * xc[r * NBP] + C_UA(r) * xg;
+                        A[S] += C_UD(S) * xg;
                     }
                 }
             } else {
@@ -437,12 +534,19 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
             if (bottom) {
                 // g-column of A_L: -a_r on the transport rows
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sa[r] : 0.0;
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_A(r) : 0.0;
             } else {
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -sua[r] : -sud[r] * sg;
+                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
             }
         }
+        // scales of this lane's inverse column, read before the ring slot may be refilled
+        const int jc = (isD || isI) ? j : 0;
+        const double c_l = C_L(jc), c_ud = C_UD(jc);
+#undef C_L
+#undef C_A
+#undef C_UD
+#undef C_UA
 
         ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
 
@@ -459,8 +563,8 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
             // scale of column j of the coupling block: top A_U = diag(-ud) (c columns), bottom
             // A_L = diag(-l) (c and phi columns); the g column comes from the G lane
             const bool scaled = bottom ? (j != S) : (j < S);
-            const double cj = bottom ? -sl[j] : -sud[j];
-            const double ae = -sl[j];
+            const double cj = bottom ? -c_l : -c_ud;
+            const double ae = -c_l;
             double* v0col = ws.V0 + j;
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
@@ -487,10 +591,15 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
         }
 
         // ---- next task ----
-        if (bottom) --i;
-        else if (i == 1 && pass == 0) pass = 1;
-        else { ++i; pass = 0; }
+        if (!bottom && i == 1 && pass == 0) { pass = 1; continue; }
+        pass = 0;
+        i += bottom ? -1 : 1;
+        __syncwarp();                           // every lane is done with this node's ring slot
+        feed.issue(kk + RING_CHAIN - 1);
+        cp_commit();
+        ++kk;
     }
+    cp_wait<0>();
     __syncwarp();
     return __all_sync(FULL, ok);
 }
@@ -604,61 +713,6 @@ __device__ __forceinline__ double row_dot(const FactorRow<NB, ST>& f, const doub
     }
     return s0 + s1;
 }
-
-// ---- asynchronous global->shared copies (LDGSTS) with explicit shared addresses ------------------
-__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
-}
-__device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
-// A sweep walks up to TWO independent chains at once, one per half warp (lanes 0..15 and 16..31, row
-// r = lane & 15): with the twisted factorisation the upper chain (wall side) and the lower chain
-// (bulk side) have no data dependence, so one warp advances both in the same instruction stream and
-// the sequential depth of a sweep halves.  A chain is (first node, number of nodes, direction).
-struct Chain { int first, count, dir; };
-
-// Feeds the node records of a sweep into the shared-memory ring: per lane the running source
-// pointers of its 16-byte chunks, one commit group per sweep iteration (both chains' records).
-template <int NB, bool ST>
-struct RecordFeed {
-    static constexpr int REC = fac_rec<NB, ST>();
-    static constexpr int CH = REC / 2;                   // 16-byte chunks per record
-    static constexpr int ROUNDS = (CH + 31) / 32;        // rounds of the warp per record
-    const double* s0; const double* s1;                  // this lane's first chunk of the next record, per chain
-    long long st0, st1;                                  // doubles between consecutive records (+-REC)
-    unsigned dst;                                        // shared address of this lane's first chunk in slot 0
-    int n0, n1, two;
-    int lane;
-    __device__ __forceinline__ void init(const double* fac, const double* ring, int lane, Chain c0, Chain c1) {
-        s0 = fac + (long long)c0.first * REC + 2 * lane; st0 = (long long)c0.dir * REC;
-        s1 = fac + (long long)c1.first * REC + 2 * lane; st1 = (long long)c1.dir * REC;
-        dst = (unsigned)__cvta_generic_to_shared(ring) + 16u * lane;
-        n0 = c0.count; n1 = c1.count; two = c1.count > 0 ? 2 : 1;
-        this->lane = lane;
-    }
-    // records of iteration k (calls must come with k = 0, 1, 2, ...)
-    __device__ __forceinline__ void issue(int k) {
-        if (k < n0) {
-            const unsigned d = dst + (unsigned)(((two * k) & (RING_CHAIN * two - 1)) * REC * 8);
-#pragma unroll
-            for (int q = 0; q < ROUNDS; ++q)
-                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s0 + 64 * q);
-            s0 += st0;
-        }
-        if (k < n1) {
-            const unsigned d = dst + (unsigned)(((2 * k + 1) & (RING - 1)) * REC * 8);
-#pragma unroll
-            for (int q = 0; q < ROUNDS; ++q)
-                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s1 + 64 * q);
-            s1 += st1;
-        }
-    }
-};
 
 // elimination of the right-hand side along a chain:
 //   dir=+1:  z_i = inv_i*(rhs_i - A_L z_{i-1})      (the first node of a chain has no predecessor
