@@ -71,7 +71,7 @@ constexpr int RING = 2 * RING_CHAIN;   // slots of the one-warp-per-cell ring
 // (columns >= NB are right-hand sides).  The pivot column travels through shared
 // memory (one writer, broadcast reads).  A row swap is a warp-uniform branch, so
 // it only costs when it happens.  Returns false on a zero/non-finite pivot.
-// Reciprocal of a pivot: hardware seed (MUFU.RCP64H, ~2^-20) + three Newton steps, no slow path.
+// Reciprocal of a pivot: hardware seed (MUFU.RCP64H, ~2^-20) + two Newton steps (2^-40, 2^-80), no slow path.
 // Accurate to ~1 ulp for normal operands, which is all a factorisation needs (the correctly rounded
 // __drcp_rn costs ~45 dependent instructions on the critical path of every elimination step);
 // zero / denormal / huge pivots give Inf or NaN and are rejected by the caller.
@@ -79,8 +79,6 @@ __device__ __forceinline__ double pivot_rcp(double a) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
     double e = fma(-a, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-a, x, 1.0);
     x = fma(x, e, x);
     e = fma(-a, x, 1.0);
     x = fma(x, e, x);
@@ -342,109 +340,36 @@ struct RecordFeed {
 // is the bulk of the kernel's instruction footprint (instruction cache).
 constexpr int FACTOR_TOP = 1, FACTOR_BOTTOM = 2, FACTOR_BOTH = 3;
 
-// The warp state is passed BY VALUE: handing out a reference would force the caller's copy into
-// local memory and turn every shared-memory access of the whole kernel into a generic one.  Pointers
-// that cross the call lose their address space, so the shared-memory ones are rebuilt here from
-// byte offsets into the block's dynamic shared memory (SmemOffsets) and come out as LDS/STS again.
-//
-// Two phases.  ASSEMBLY: the Jacobian blocks of all nodes are independent of each other, so every
-// lane assembles one column of A_D and one row of coefficients of a different (node, unknown) pair
-// at a time, with the whole warp busy, straight into the node records in global memory.
-// ELIMINATION: the sequential sweep then only streams the records back through the cp.async ring
-// (three nodes ahead), applies the Schur update and eliminates.  Doing the assembly inside the
-// sequential sweep (one node at a time, 9 of 32 lanes busy, every load latency exposed) cost more
-// than the elimination itself.
-struct SmemOffsets { unsigned scratch, sp, y, ring; };
+// Elimination of one node of the factorisation sweep (see factor_nodes).  SPECIAL = false is the
+// compact body of the interior nodes; the wall node, node 1 (two passes), the bulk node and the
+// coupling node take the SPECIAL = true instance, which keeps their rarely executed code out of the
+// hot loop's instruction footprint.
+struct FactorLane { bool isD, isI, isG; int j, wsrc_top, wsrc_bot; };
 
-template <int NB, bool ST, bool SMEM>
-__device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
-                                          int mid, double* xch, int parts) {
+template <int NB, bool ST, bool SPECIAL>
+__device__ __forceinline__ bool eliminate_node(const WarpState<NB, ST>& ws, const FactorLane fl, double (&Wp)[NB],
+                                               int i, int pass, bool bottom, int mid, int slot, double inv_gamma,
+                                               double* xch) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
     constexpr int REC = fac_rec<NB, ST>();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpState<NB, ST> ws = ws_in;
-    ws.scratch = reinterpret_cast<double*>(smem_raw + so.scratch);
-    ws.ring = reinterpret_cast<double*>(smem_raw + so.ring);
-    ws.sp = reinterpret_cast<const CellSpecies*>(smem_raw + so.sp);
-    ws.tb = reinterpret_cast<const DevTables*>(smem_raw);
-    if constexpr (SMEM) ws.y = reinterpret_cast<double*>(smem_raw + so.y);
     const int lane = ws.lane;
     const int n = ws.cs.n;
-    const bool mig = ws.tb->use_migration;
-    double* pivbuf = ws.scratch;
-    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
-    const int j = isD ? lane : lane - NB;
-    const double* y = ws.y;
-
-    // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
-    for (int item = ws.vlane; item < n * NB; item += ws.vstride) {
-        const int i = item / NB, r = item - i * NB;
-        double* rec = ws.fac + (size_t)i * REC;
-        double4 co = node_coeff_row<NB, ST>(ws, y, i, r);
-        if (i > 0 && i < n - 1) {
-            const NodeCoef k = interior_coef(ws.cs, i);
-            const double sg = mig ? grow_scale(ws.cs, k.hi) : 1.0;
-            if (r == S) co.z *= sg;                                  // g row of A_U carries the row scale
-            double C[NB];
-            interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, r, k, inv_gamma, sg, C);
-#pragma unroll
-            for (int rr = 0; rr < NB; ++rr) rec[rr * NBP + r] = C[rr];
-        }
-        reinterpret_cast<double4*>(rec + NB * NBP)[r] = co;
-    }
-    __syncwarp();
-    if (parts != FACTOR_BOTH) pair_barrier(ws.bar_id);               // the pair shares the assembly
-
-    // source lane of the W column that D-lane j needs for the next Schur update: the scaled inverse
-    // column where the coupling block has a diagonal entry in column j, the G lane for the g column
-    const int wsrc_top = isD ? (j < S ? lane + NB : 2 * NB) : lane;
-    const int wsrc_bot = isD ? (j != S ? lane + NB : 2 * NB) : lane;
-    double A[NB], Wp[NB];
-#pragma unroll
-    for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
-    bool ok = true;
-
-    bool bottom = (parts & FACTOR_BOTTOM) != 0;
-    int i = bottom ? n - 1 : 0;
-    int pass = 0;            // node 1 is eliminated twice (pass 1: [A_D1' | A_U1'] -> dense W_1)
-    const Chain none = {0, 0, 1};
-    RecordFeed<NB, ST> feed;
-    int kk = 0;              // position in the current chain
-    feed.init(ws.fac, ws.ring, lane, bottom ? Chain{n - 1, n - 1 - mid, -1} : Chain{0, mid + 1, +1}, none);
-#pragma unroll 1
-    for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
-#pragma unroll 1
-    for (;;) {
-        if (bottom && i <= mid) {
-            // bottom half done: publish W^b_{mid+1}
-            if (isD) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
-            }
-            if (!(parts & FACTOR_TOP)) { pair_barrier(ws.bar_id); break; }
-            bottom = false; i = 0;
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
-            cp_wait<0>();
-            __syncwarp();
-            kk = 0;
-            feed.init(ws.fac, ws.ring, lane, Chain{0, mid + 1, +1}, none);
-#pragma unroll 1
-            for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
-        }
-        if (!bottom && i > mid) break;
-
-        const bool bulk = (i == n - 1);
-        const bool wall = (i == 0);
-        const bool couple = !bottom && (i == mid);
+    const bool isD = fl.isD, isI = fl.isI, isG = fl.isG;
+    const int j = fl.j, wsrc_top = fl.wsrc_top, wsrc_bot = fl.wsrc_bot;
+    double A[NB];
+    {
+        const bool bulk = SPECIAL && (i == n - 1);
+        const bool wall = SPECIAL && (i == 0);
+        const bool couple = SPECIAL && !bottom && (i == mid);
+        const bool node1 = SPECIAL && (i == 1);
+        if (!SPECIAL) pass = 0;
         double* rec = ws.fac + (size_t)i * REC;
         double* invcol = rec + j;                                   // column j of inv_i (I lanes)
         NodeCoef k = NodeCoef{0, 0, 0, 1, 1};
         if (bulk) k = interior_coef(ws.cs, i - 1);
-        if (pass == 0) { cp_wait<RING_CHAIN - 2>(); __syncwarp(); }
         // the node's record in the ring: raw A_D and the coefficient rows (ud of the g row is scaled)
-        const double* rr_ = ws.ring + (size_t)(kk & (RING_CHAIN - 1)) * REC;
+        const double* rr_ = ws.ring + (size_t)slot * REC;
         const double* cof = rr_ + NB * NBP;
 #define C_L(r_) cof[4 * (r_)]
 #define C_A(r_) cof[4 * (r_) + 1]
@@ -520,7 +445,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
                     if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
                 }
             }
-            if (i == 1) {
+            if (node1) {
                 // park A_D1' for the second elimination (W1 is rewritten at the end of pass 1)
                 double* d1 = ws.W1 + j;
 #pragma unroll
@@ -548,7 +473,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 #undef C_UD
 #undef C_UA
 
-        ok = gauss_jordan<NB, ST>(A, lane, pivbuf) && ok;
+        bool ok = gauss_jordan<NB, ST>(A, lane, ws.scratch);
 
         // ---- store the inverse, form the W columns for the next node ----
         int src = bottom ? wsrc_bot : wsrc_top;
@@ -574,7 +499,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
             }
         }
         // (between the two eliminations of node 1 the I lanes still need their V_0 columns)
-        if (!(i == 1 && pass == 0 && !bottom)) {
+        if (!(node1 && pass == 0 && !bottom)) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, A[r], src);
         }
@@ -589,6 +514,110 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 #pragma unroll
             for (int r = 0; r < NB; ++r) Wp[r] = v0col[r * NBP];
         }
+
+        return ok;
+    }
+}
+
+// The warp state is passed BY VALUE: handing out a reference would force the caller's copy into
+// local memory and turn every shared-memory access of the whole kernel into a generic one.  Pointers
+// that cross the call lose their address space, so the shared-memory ones are rebuilt here from
+// byte offsets into the block's dynamic shared memory (SmemOffsets) and come out as LDS/STS again.
+//
+// Two phases.  ASSEMBLY: the Jacobian blocks of all nodes are independent of each other, so every
+// lane assembles one column of A_D and one row of coefficients of a different (node, unknown) pair
+// at a time, with the whole warp busy, straight into the node records in global memory.
+// ELIMINATION: the sequential sweep then only streams the records back through the cp.async ring
+// (three nodes ahead), applies the Schur update and eliminates.  Doing the assembly inside the
+// sequential sweep (one node at a time, 9 of 32 lanes busy, every load latency exposed) cost more
+// than the elimination itself.
+struct SmemOffsets { unsigned scratch, sp, y, ring; };
+
+template <int NB, bool ST, bool SMEM>
+__device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
+                                          int mid, double* xch, int parts) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    constexpr int NBP = padded<NB, ST>();
+    constexpr int REC = fac_rec<NB, ST>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpState<NB, ST> ws = ws_in;
+    ws.scratch = reinterpret_cast<double*>(smem_raw + so.scratch);
+    ws.ring = reinterpret_cast<double*>(smem_raw + so.ring);
+    ws.sp = reinterpret_cast<const CellSpecies*>(smem_raw + so.sp);
+    ws.tb = reinterpret_cast<const DevTables*>(smem_raw);
+    if constexpr (SMEM) ws.y = reinterpret_cast<double*>(smem_raw + so.y);
+    const int lane = ws.lane;
+    const int n = ws.cs.n;
+    const bool mig = ws.tb->use_migration;
+    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
+    const int j = isD ? lane : lane - NB;
+    const double* y = ws.y;
+
+    // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
+    for (int item = ws.vlane; item < n * NB; item += ws.vstride) {
+        const int i = item / NB, r = item - i * NB;
+        double* rec = ws.fac + (size_t)i * REC;
+        double4 co = node_coeff_row<NB, ST>(ws, y, i, r);
+        if (i > 0 && i < n - 1) {
+            const NodeCoef k = interior_coef(ws.cs, i);
+            const double sg = mig ? grow_scale(ws.cs, k.hi) : 1.0;
+            if (r == S) co.z *= sg;                                  // g row of A_U carries the row scale
+            double C[NB];
+            interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, r, k, inv_gamma, sg, C);
+#pragma unroll
+            for (int rr = 0; rr < NB; ++rr) rec[rr * NBP + r] = C[rr];
+        }
+        reinterpret_cast<double4*>(rec + NB * NBP)[r] = co;
+    }
+    __syncwarp();
+    if (parts != FACTOR_BOTH) pair_barrier(ws.bar_id);               // the pair shares the assembly
+
+    // source lane of the W column that D-lane j needs for the next Schur update: the scaled inverse
+    // column where the coupling block has a diagonal entry in column j, the G lane for the g column
+    FactorLane fl;
+    fl.isD = isD; fl.isI = isI; fl.isG = isG; fl.j = j;
+    fl.wsrc_top = isD ? (j < S ? lane + NB : 2 * NB) : lane;
+    fl.wsrc_bot = isD ? (j != S ? lane + NB : 2 * NB) : lane;
+    double Wp[NB];
+#pragma unroll
+    for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+    bool ok = true;
+
+    bool bottom = (parts & FACTOR_BOTTOM) != 0;
+    int i = bottom ? n - 1 : 0;
+    int pass = 0;            // node 1 is eliminated twice (pass 1: [A_D1' | A_U1'] -> dense W_1)
+    const Chain none = {0, 0, 1};
+    RecordFeed<NB, ST> feed;
+    int kk = 0;              // position in the current chain
+    feed.init(ws.fac, ws.ring, lane, bottom ? Chain{n - 1, n - 1 - mid, -1} : Chain{0, mid + 1, +1}, none);
+#pragma unroll 1
+    for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
+#pragma unroll 1
+    for (;;) {
+        if (bottom && i <= mid) {
+            // bottom half done: publish W^b_{mid+1}
+            if (isD) {
+#pragma unroll
+                for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
+            }
+            if (!(parts & FACTOR_TOP)) { pair_barrier(ws.bar_id); break; }
+            bottom = false; i = 0;
+#pragma unroll
+            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
+            cp_wait<0>();
+            __syncwarp();
+            kk = 0;
+            feed.init(ws.fac, ws.ring, lane, Chain{0, mid + 1, +1}, none);
+#pragma unroll 1
+            for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
+        }
+        if (!bottom && i > mid) break;
+
+        const bool special = (i <= 1) || (i == n - 1) || (!bottom && i == mid);
+        if (pass == 0) { cp_wait<RING_CHAIN - 2>(); __syncwarp(); }
+        const int slot = kk & (RING_CHAIN - 1);
+        if (special) ok = eliminate_node<NB, ST, true>(ws, fl, Wp, i, pass, bottom, mid, slot, inv_gamma, xch) && ok;
+        else ok = eliminate_node<NB, ST, false>(ws, fl, Wp, i, pass, bottom, mid, slot, inv_gamma, xch) && ok;
 
         // ---- next task ----
         if (!bottom && i == 1 && pass == 0) { pass = 1; continue; }
