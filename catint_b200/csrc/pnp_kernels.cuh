@@ -5,6 +5,7 @@
 //   K3  pnp_bdf_kernel       per-cell BDF/Newton integrator with fused assembly +
 //                            block-Thomas solve (see pnp_solver.cuh)
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -211,10 +212,17 @@ __host__ __device__ constexpr int stream_depth() {
     return ring_doubles<NB, ST, PAIR>() / (NARR * 32) > 8 ? 8 : ring_doubles<NB, ST, PAIR>() / (NARR * 32);
 }
 
-template <int NB, bool ST, bool PAIR>
-__device__ void history_pass(WarpState<NB, ST>& ws, int q_old, int dq, bool undo, double eta,
-                             const double* lc, double A1, double rl1, bool predict) {
+// QF > 0: instance specialised for the common case "order QF kept, nothing to undo, predict": all
+// order tests fold at compile time and the loop body shrinks to the loads, the rescaling, the
+// Pascal additions and the stores of exactly QF+1 arrays.  QF = 0: general run-time version.
+template <int NB, bool ST, bool PAIR, int QF>
+__device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, bool undo_rt, double eta,
+                             const double* lc, double A1, double rl1, bool predict_rt) {
     const int N = ws.N;
+    const int q_old = QF ? QF : q_old_rt;
+    const int dq = QF ? 0 : dq_rt;
+    const bool undo = QF ? false : undo_rt;
+    const bool predict = QF ? true : predict_rt;
     const int q_new = q_old + dq;
     constexpr int SD = stream_depth<NB, ST, PAIR, LMAX>();
     constexpr bool STREAM = SD >= 3;
@@ -529,7 +537,18 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             B.t = saved_t + B.h;
             set_bdf<NB, ST>(B);
             const double rl1 = 1.0 / B.l[1];
-            { CATINT_TIC; history_pass<NB, ST, PAIR>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+            { CATINT_TIC;
+              if (!pend_undo && pend_dq == 0) {
+                  switch (q_old) {
+                      case 1: history_pass<NB, ST, PAIR, 1>(ws, 1, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 2: history_pass<NB, ST, PAIR, 2>(ws, 2, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 3: history_pass<NB, ST, PAIR, 3>(ws, 3, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 4: history_pass<NB, ST, PAIR, 4>(ws, 4, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      default: history_pass<NB, ST, PAIR, 5>(ws, 5, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                  }
+              } else {
+                  history_pass<NB, ST, PAIR, 0>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+              }
               pair_sync<PAIR>(ws.bar_id); CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
@@ -615,7 +634,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 pend_eta = ETAMIN;
             } else {
                 // order 1 and still failing: restart the history from the last accepted state
-                history_pass<NB, ST, PAIR>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
+                history_pass<NB, ST, PAIR, 0>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
                 pend_undo = false;
                 B.h *= ETAMIN; B.hscale = B.h;
                 B.qwait = LONG_WAIT;
@@ -650,7 +669,10 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
         // correction pass: zn[j] += l[j]*acor, norms for the order selection, new weights.
         // Two elements per lane and iteration, loads grouped ahead of the stores (memory-level
         // parallelism; the history array streams from L2/HBM).
-        {
+        auto correction = [&](auto qf_) {
+            // QF > 0: instance specialised for order QF (all order tests fold); QF = 0: run-time order
+            constexpr int QF = decltype(qf_)::value;
+            const int q = QF ? QF : B.q;
             double lreg[LMAX];
 #pragma unroll
             for (int j = 0; j < LMAX; ++j) lreg[j] = B.l[j];
@@ -718,6 +740,14 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 if constexpr (STREAM) { issue(); rslot = (rslot + 1 == SD) ? 0 : rslot + 1; }
             }
             if constexpr (STREAM) cp_wait<0>();
+        };
+        switch (q) {
+            case 1: correction(std::integral_constant<int, 1>()); break;
+            case 2: correction(std::integral_constant<int, 2>()); break;
+            case 3: correction(std::integral_constant<int, 3>()); break;
+            case 4: correction(std::integral_constant<int, 4>()); break;
+            case 5: correction(std::integral_constant<int, 5>()); break;
+            default: correction(std::integral_constant<int, 0>()); break;
         }
         __syncwarp();
         ddn = pair_max<PAIR>(ddn, xn, half, lane, ws.bar_id);      // also the pair barrier that ends the correction pass
