@@ -52,6 +52,17 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same workload), or None."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.isfile(p):
+        d = json.load(open(p)).get(kernel)
+        if d:
+            return float(d['dram_bytes_read']) + float(d['dram_bytes_write'])
+    return None
+
+
 def c2_batch(rank=0, world=1, n_cells=CELLS_PER_GPU):
     """the rank's sweep as a host CellBatch (model tables from the fixture-verified Transport)."""
     import tempfile
@@ -227,7 +238,7 @@ def rhs_roofline(bk, batch, dev, n_cells=131072, reps=10):
     peak, which = measured_peaks()
     ach = nbytes / (ms * 1e-3) / 1e9
     return {'bound': 'hbm', 'kernel': 'pnp_rhs_kernel', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-            'frac': ach / peak, 'traffic': None, 'peak_source': which, 'cells': n_cells,
+            'frac': ach / peak, 'traffic': ncu_traffic('pnp_rhs_kernel'), 'peak_source': which, 'cells': n_cells,
             'algorithmic_bytes_per_launch': nbytes, 'ms_per_launch': ms,
             'note': 'input+output 2x%.0f MB per launch (> 126 MB L2), back-to-back launches' % (nbytes / 2e6)}
 
@@ -333,8 +344,8 @@ def run_gpu(args):
         launch_s = dev_ms * 1e-3 / args.steps
         peak, which = measured_peaks()
         achieved = algo_bytes / launch_s / 1e9                                  # this rank's launch
-        roofline = {'bound': 'hbm', 'kernel': 'pnp_bdf_kernel<9,true>', 'achieved': achieved, 'peak': peak,
-                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': which,
+        roofline = {'bound': 'hbm', 'kernel': 'pnp_bdf_kernel<9,false,true,false>', 'achieved': achieved, 'peak': peak,
+                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic('pnp_bdf_kernel'), 'peak_source': which,
                     'algorithmic_bytes_per_launch': algo_bytes,
                     'newton_iterations_per_launch': newton_total, 'factorisations_per_launch': setups_total,
                     'bdf_steps_per_launch': steps_total,
@@ -342,7 +353,8 @@ def run_gpu(args):
                     'bytes_per_bdf_step': bytes_step,
                     'fp64_tflops_algorithmic': flops / launch_s / 1e12,
                     'note': 'one warp per cell, 1024 cells = 7 warps/SM: the kernel is bound by the dependency '
-                            'latency of the sequential block sweeps, not by HBM (see DESIGN.md 6)'}
+                            'latency of the sequential block sweeps, not by HBM; traffic = DRAM bytes of one launch '
+                            '(ncu, L2 absorbs the rest of the algorithmic bytes), see DESIGN.md 6'}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'cells/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

@@ -302,12 +302,13 @@ def test_thousand_node_grid_uses_global_state(bk, resultsdir):
     assert np.max(np.abs(st['phi'][-1, 0].cpu().numpy() - go['phi'])) < RTOL_PROFILE * np.max(np.abs(go['phi']))
 
 
-@pytest.mark.parametrize('nn', [201])
+@pytest.mark.parametrize('nn', [201, 1001])
 def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
     """C3-type cells: Stern-layer (Robin) Poisson boundary, phi carried as an unknown (block size S+2),
     geometric mesh with a 0.05 nm first interval; phiM x bulk_pH corner cells against the CPU BDF oracle +
     Newton root of the same discrete system (extension beyond the reference FD code).  A cell
-    whose discrete ODE blows up in finite time in the oracle must be reported as failed by the GPU too."""
+    whose discrete ODE blows up in finite time in the oracle must be reported as failed by the GPU too.
+    nn=1001 runs through the global-state kernel variant (the iterate does not fit in shared memory)."""
     from catint_b200 import backend as be, workloads
     from catint_b200.transport import Transport
     from catint_b200.calculator import build_cell_batch
