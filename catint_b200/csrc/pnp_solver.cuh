@@ -758,24 +758,31 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
     const int lane = ws.lane;
     const int grp = lane >> 4;
     const int r0 = lane & 15;
-    const Chain me = grp ? c1 : c0;
+    const bool dual = c1.count > 0;
+    const Chain me = (grp && dual) ? c1 : c0;       // one chain: the upper half warp shadows the lower one
     const bool rowlane = r0 < NB;
     const int r = rowlane ? r0 : 0;
-    const bool dual = c1.count > 0;
     const int iters = max(c0.count, c1.count);
     constexpr int ahead = RING_CHAIN - 1;                // iterations of look-ahead
     RecordFeed<NB, ST> feed;
     feed.init(ws.fac, ws.ring, lane, c0, c1);
+#pragma unroll 1
     for (int p = 0; p < ahead; ++p) { feed.issue(p); cp_commit(); }
     double* tbuf = ws.scratch + grp * 2 * NBP;           // [parity][NBP] per chain
     const double* ringrow = ws.ring + r * NBP;
     const double* ringco = ws.ring + NB * NBP + 4 * r;
     const int zstep = me.dir * NB;
+    const int gsrc = (lane & 16) + S;                    // lane that owns the g component of my chain
     int zo = me.first * NB + r;                          // this lane's unknown of the current node
-    double zprev = 0.0;
+    double zprev = 0.0, zs = 0.0;                        // my row / the g row of the previous node (none at k = 0)
+    cp_wait<RING_CHAIN - 2>();
+    __syncwarp();                                        // record 0 is visible to every lane
+    // One warp barrier per iteration: it publishes the right-hand sides tt, makes the NEXT record (whose
+    // copies every lane has just waited for) visible, and tells that all lanes are done with the
+    // previous one.  The predecessor's solution travels in registers (own row) and by shuffle (g row).
     for (int k = 0; k < iters; ++k) {
-        cp_wait<RING_CHAIN - 2>();
-        __syncwarp();
+        feed.issue(k + ahead);                           // refills the slot of record k-1
+        cp_commit();
         const bool live = k < me.count;
         const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
         FactorRow<NB, ST> f;
@@ -790,21 +797,20 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
             f.co = *reinterpret_cast<const double4*>(ringco + slot * REC);
         }
         double t = ws.zb[zo];
-        if (k > 0) {
-            const double zs = ws.zb[zo - zstep + (S - r)];
+        {
             const double ca = me.dir > 0 ? f.co.x : f.co.z;          // -A_L or -A_U: diagonal ...
             const double cb = me.dir > 0 ? f.co.y : f.co.w;          // ... and g column
             t = fma(ca, zprev, fma(cb, zs, t));
         }
         double* tt = tbuf + (k & 1) * NBP;
         if (rowlane) tt[r] = t;
+        cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 have landed
         __syncwarp();
         const double z = row_dot<NB, ST>(f, tt);
         if (rowlane && live) ws.zb[zo] = z;
         zprev = z;
+        zs = __shfl_sync(FULL, z, gsrc);
         if (k + 1 < me.count) zo += zstep;
-        feed.issue(k + ahead);
-        cp_commit();
     }
     cp_wait<0>();
     __syncwarp();
@@ -830,39 +836,48 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
     const int n = ws.cs.n;
     const int grp = lane >> 4;
     const int r0 = lane & 15;
-    const Chain me = grp ? c1 : c0;
+    const bool dual = c1.count > 0;
+    const Chain me = (grp && dual) ? c1 : c0;       // one chain: the upper half warp shadows the lower one
     const bool rowlane = r0 < NB;
     const int r = rowlane ? r0 : 0;
-    const bool dual = c1.count > 0;
     const int iters = max(c0.count, c1.count);
     constexpr int ahead = RING_CHAIN - 1;
     RecordFeed<NB, ST> feed;
     feed.init(ws.fac, ws.ring, lane, c0, c1);
-    // weight ring: lanes 0..NB-1 fetch ewt, lanes NB..2NB-1 zn0 of the node, per chain
+    // weight ring: every row lane fetches the weight and zn0 of its own unknown and reads them back
+    // itself (its own wait_group is all the synchronisation that needs)
     const double* ring2 = ws.ring + (size_t)(dual ? RING : RING_CHAIN) * REC;
-    const bool wl = wmode == 0 && lane < 2 * NB;
-    const double* wbase = (lane < NB ? ws.ewt + lane : ws.zn + (lane - NB));
-    const double* w0 = wbase + (long long)c0.first * NB;
-    const double* w1 = wbase + (long long)c1.first * NB;
-    const unsigned wdst = (unsigned)__cvta_generic_to_shared(ring2) + 8u * (lane < NB ? lane : NBP + lane - NB);
+    const bool wl = wmode == 0 && rowlane;
+    const double* wsrc = ws.ewt + (long long)me.first * NB + r;
+    const double* zsrc = ws.zn + (long long)me.first * NB + r;
+    const unsigned wdst = (unsigned)__cvta_generic_to_shared(ring2) + 8u * r;
+    const int wstep = me.dir * NB;
     auto issue = [&](int k) {
         feed.issue(k);
-        if (wl) {
-            if (k < c0.count) { cp_async8(wdst + (unsigned)((dual ? ((2 * k) & (RING - 1)) : (k & (RING_CHAIN - 1))) * R2 * 8), w0); w0 += c0.dir * NB; }
-            if (k < c1.count) { cp_async8(wdst + (unsigned)(((2 * k + 1) & (RING - 1)) * R2 * 8), w1); w1 += c1.dir * NB; }
+        if (wl && k < me.count) {
+            const int rs = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
+            cp_async8(wdst + (unsigned)(rs * R2 * 8), wsrc);
+            cp_async8(wdst + (unsigned)((rs * R2 + NBP) * 8), zsrc);
+            wsrc += wstep; zsrc += wstep;
         }
         cp_commit();
     };
+#pragma unroll 1
     for (int p = 0; p < ahead; ++p) issue(p);
     double* tbuf = ws.scratch + grp * 2 * NBP;
     const double* ringrow = ws.ring + r * NBP;
     const double* ringco = ws.ring + NB * NBP + 4 * r;
     const int zstep = me.dir * NB;
+    const int gsrc = (lane & 16) + S;
     int zo = me.first * NB + r;
     const bool crow = rowlane && r < S;                  // this lane owns a concentration unknown
-    for (int k = 0; k < iters; ++k) {
-        cp_wait<RING_CHAIN - 2>();
-        __syncwarp();
+    // final solution of the node before the chain (the coupling node): my row and its g row
+    double dprev = ws.zb[zo - zstep];
+    double dg = ws.zb[zo - zstep + (S - r)];
+    cp_wait<RING_CHAIN - 2>();
+    __syncwarp();                                        // record 0 is visible to every lane
+    for (int k = 0; k < iters; ++k) {                    // one warp barrier per iteration, see forward_solve
+        issue(k + ahead);
         const bool live = k < me.count;
         const int i = me.first + me.dir * k;
         const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
@@ -879,19 +894,18 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
         }
         double* tt = tbuf + (k & 1) * NBP;
         {
-            const double dr = ws.zb[zo - zstep];                     // final solution of the neighbour
-            const double dg = ws.zb[zo - zstep + (S - r)];
             const double ca = me.dir < 0 ? f.co.z : f.co.x;          // A_U (dir<0) or A_L (dir>0)
             const double cb = me.dir < 0 ? f.co.w : f.co.y;
-            if (rowlane) tt[r] = -(ca * dr + cb * dg);
+            if (rowlane) tt[r] = -(ca * dprev + cb * dg);
         }
+        cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 (and my weights of node k)
         __syncwarp();
         double d = ws.zb[zo] - row_dot<NB, ST>(f, tt);
         // wall side of the upper chain (warp-uniform test): node 1 couples through the dense W_1,
         // node 0 has the extra block V_0 towards node 2
         const int i0 = c0.first + c0.dir * k;
         if (c0.dir < 0 && i0 <= 1 && k < c0.count) {
-            if (grp == 0 && rowlane) {
+            if ((grp == 0 || !dual) && rowlane) {        // (a shadowing half warp must take the same path)
                 const double* d2 = ws.zb + 2 * NB;
                 const double* Mr = (i0 == 1 ? ws.W1 : ws.V0) + (size_t)r * NBP;
                 double s_ = 0.0;
@@ -903,6 +917,8 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
         const double ds = d * scale;
         const double yn = ws.y[zo] + ds;
         if (rowlane && live) { ws.zb[zo] = d; ws.y[zo] = yn; }
+        dprev = d;
+        dg = __shfl_sync(FULL, d, gsrc);
         {
             double w, z0 = 0.0;
             if (wmode == 0) { w = ring2[slot * R2 + r]; z0 = ring2[slot * R2 + NBP + r]; }
@@ -914,7 +930,6 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
             if (wmode == 0) amax = fmax(amax, counted ? fabs(yn - z0) * w : 0.0);
         }
         if (k + 1 < me.count) zo += zstep;
-        issue(k + ahead);
     }
     cp_wait<0>();
     __syncwarp();
