@@ -211,6 +211,50 @@ def test_steady_state_is_a_root_of_the_rhs_kernel(bk):
     assert int(out['n_steps'].max()) < 5000
 
 
+@pytest.mark.parametrize('S', [1, 2, 3, 5])
+def test_small_block_sizes(bk, S):
+    """block sizes 2..6 (one kernel instantiation each): reaction-free electrolytes with 1..5 species on a
+    ragged pair of cells; the converged state must be a root of K1's dc/dt, carry the imposed wall fluxes and
+    agree with the CPU Newton root of the same discrete system (oracle/pnp_local.py)."""
+    import torch
+    from catint_b200 import backend as be
+    from oracle.pnp_local import LocalForm
+    su = load_golden('ref_c1.npz')
+    zs = {1: [0.0], 2: [1.0, -1.0], 3: [1.0, -1.0, 0.0], 5: [1.0, -1.0, 0.0, 2.0, -1.0]}[S]
+    cb = {1: [30.0], 2: [100.0, 100.0], 3: [100.0, 100.0, 30.0], 5: [100.0, 140.0, 30.0, 20.0, 0.0]}[S]
+    cb = np.array(cb); z = np.array(zs)
+    if S == 5:
+        cb[4] = 0.0; cb[1] = 100.0 + 2 * 20.0          # electroneutral: 100 + 2*20 = 140
+    J = np.zeros(S); J[0] = -2e-5                       # species 0 consumed at the wall
+    if S >= 3: J[2] = +2e-5                             # neutral product released
+    D = np.array(su['D'][:S], dtype=float)
+    B = 2
+    par = np.zeros((B, be.npar(S)))
+    for c in range(B):
+        par[c, 0:S] = cb; par[c, S:2 * S] = J * (1 + c); par[c, 2 * S:3 * S] = D
+        par[c, 3 * S + 0] = su['beta']; par[c, 3 * S + 1] = su['eps']; par[c, 3 * S + 2] = su['phi_wall']
+        par[c, 3 * S + 3] = su['g_bulk']; par[c, 3 * S + 4] = 0.2; par[c, 3 * S + 5] = su['dx']
+    nx = np.array([41, 38], dtype=np.int32)
+    mig = S > 1
+    batch = be.CellBatch(z, [], be.stoichiometry(S, [], 'summed'), par, nx, use_migration=mig,
+                         species=['s%d' % k for k in range(S)])
+    assert batch.b == S + 1
+    db = bk.upload(batch)
+    out = bk.solve(db, [50.0], mode=be.MODE_STEADY)
+    assert out['status'].tolist() == [0, 0]
+    c = out['c'][-1].contiguous()
+    dcdt, _, _ = bk.rhs(db, c)
+    for k in range(B):
+        n = int(nx[k])
+        scale = float((c[k, :n].abs().amax(dim=0) * torch.tensor(D, device=c.device)).max()) / float(su['dx']) ** 2
+        assert float(dcdt[k, :n].abs().max()) < 5e-10 * scale
+        assert np.max(np.abs(out['flux'][k].cpu().numpy() - par[k, S:2 * S])) <= 1e-9 * np.max(np.abs(par[k, S:2 * S]))
+        lf = LocalForm(oracle_system_of_cell(batch, k))
+        yr, info = lf.solve_steady(y0=lf.y_from_c(c[k, :n].cpu().numpy().T), pure_newton=True)
+        assert info['converged']
+        assert relerr(c[k, :n].cpu().numpy().T, lf.unpack(yr)[0], np.max(cb)) < RTOL_PROFILE
+
+
 def test_calculator_run_end_to_end(bk, resultsdir):
     """the reference-facing call: Transport -> set_calculator -> Calculator.run() on a small sweep."""
     from catint_b200 import workloads
