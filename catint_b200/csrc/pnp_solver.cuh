@@ -780,11 +780,16 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
     // One warp barrier per iteration: it publishes the right-hand sides tt, makes the NEXT record (whose
     // copies every lane has just waited for) visible, and tells that all lanes are done with the
     // previous one.  The predecessor's solution travels in registers (own row) and by shuffle (g row).
+    // The coupling coefficients and the right-hand side of the next node are fetched right after the
+    // barrier, so that no shared-memory latency sits at the head of the next iteration's dependency chain.
+    auto slot_of = [&](int k) { return dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1)); };
+    double4 co = *reinterpret_cast<const double4*>(ringco + slot_of(0) * REC);
+    double rhs = ws.zb[zo];
     for (int k = 0; k < iters; ++k) {
         feed.issue(k + ahead);                           // refills the slot of record k-1
         cp_commit();
         const bool live = k < me.count;
-        const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
+        const int slot = slot_of(k);
         FactorRow<NB, ST> f;
         {
             const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
@@ -794,23 +799,22 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
                 f.v[2 * c] = t.x;
                 if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
             }
-            f.co = *reinterpret_cast<const double4*>(ringco + slot * REC);
         }
-        double t = ws.zb[zo];
-        {
-            const double ca = me.dir > 0 ? f.co.x : f.co.z;          // -A_L or -A_U: diagonal ...
-            const double cb = me.dir > 0 ? f.co.y : f.co.w;          // ... and g column
-            t = fma(ca, zprev, fma(cb, zs, t));
-        }
+        const double ca = me.dir > 0 ? co.x : co.z;                  // -A_L or -A_U: diagonal ...
+        const double cb = me.dir > 0 ? co.y : co.w;                  // ... and g column
+        const double t = fma(ca, zprev, fma(cb, zs, rhs));
         double* tt = tbuf + (k & 1) * NBP;
         if (rowlane) tt[r] = t;
         cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 have landed
         __syncwarp();
+        const int zo_now = zo;
+        if (k + 1 < me.count) zo += zstep;
+        co = *reinterpret_cast<const double4*>(ringco + slot_of(k + 1) * REC);
+        rhs = ws.zb[zo];
         const double z = row_dot<NB, ST>(f, tt);
-        if (rowlane && live) ws.zb[zo] = z;
+        if (rowlane && live) ws.zb[zo_now] = z;
         zprev = z;
         zs = __shfl_sync(FULL, z, gsrc);
-        if (k + 1 < me.count) zo += zstep;
     }
     cp_wait<0>();
     __syncwarp();
@@ -876,11 +880,14 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
     double dg = ws.zb[zo - zstep + (S - r)];
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
+    auto slot_of = [&](int k) { return dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1)); };
+    double4 co = *reinterpret_cast<const double4*>(ringco + slot_of(0) * REC);
+    double zcur = ws.zb[zo];                             // forward-eliminated value of the current node
     for (int k = 0; k < iters; ++k) {                    // one warp barrier per iteration, see forward_solve
         issue(k + ahead);
         const bool live = k < me.count;
         const int i = me.first + me.dir * k;
-        const int slot = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
+        const int slot = slot_of(k);
         FactorRow<NB, ST> f;
         {
             const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
@@ -890,17 +897,23 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
                 f.v[2 * c] = t.x;
                 if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
             }
-            f.co = *reinterpret_cast<const double4*>(ringco + slot * REC);
         }
         double* tt = tbuf + (k & 1) * NBP;
         {
-            const double ca = me.dir < 0 ? f.co.z : f.co.x;          // A_U (dir<0) or A_L (dir>0)
-            const double cb = me.dir < 0 ? f.co.w : f.co.y;
+            const double ca = me.dir < 0 ? co.z : co.x;              // A_U (dir<0) or A_L (dir>0)
+            const double cb = me.dir < 0 ? co.w : co.y;
             if (rowlane) tt[r] = -(ca * dprev + cb * dg);
         }
         cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 (and my weights of node k)
         __syncwarp();
-        double d = ws.zb[zo] - row_dot<NB, ST>(f, tt);
+        const int zo_now = zo;
+        if (k + 1 < me.count) zo += zstep;
+        co = *reinterpret_cast<const double4*>(ringco + slot_of(k + 1) * REC);
+        const double znext = ws.zb[zo];
+        const double yold = ws.y[zo_now];
+        double w = 0.0, z0 = 0.0;
+        if (wmode == 0) { w = ring2[slot * R2 + r]; z0 = ring2[slot * R2 + NBP + r]; }
+        double d = zcur - row_dot<NB, ST>(f, tt);
         // wall side of the upper chain (warp-uniform test): node 1 couples through the dense W_1,
         // node 0 has the extra block V_0 towards node 2
         const int i0 = c0.first + c0.dir * k;
@@ -911,25 +924,23 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
                 double s_ = 0.0;
 #pragma unroll
                 for (int c = 0; c < NB; ++c) s_ = fma(Mr[c], d2[c], s_);
-                d = (i0 == 1 ? ws.zb[zo] : d) - s_;
+                d = (i0 == 1 ? zcur : d) - s_;
             }
         }
         const double ds = d * scale;
-        const double yn = ws.y[zo] + ds;
-        if (rowlane && live) { ws.zb[zo] = d; ws.y[zo] = yn; }
+        const double yn = yold + ds;
+        if (rowlane && live) { ws.zb[zo_now] = d; ws.y[zo_now] = yn; }
         dprev = d;
         dg = __shfl_sync(FULL, d, gsrc);
+        zcur = znext;
         {
-            double w, z0 = 0.0;
-            if (wmode == 0) { w = ring2[slot * R2 + r]; z0 = ring2[slot * R2 + NBP + r]; }
-            else w = 1.0 / (prtol * fabs(yn) + patol);
+            if (wmode != 0) w = 1.0 / (prtol * fabs(yn) + patol);
             double ad = fabs(ds) * w;
             if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
             const bool counted = crow && live && i < n - 1;
             dmax = fmax(dmax, counted ? ad : 0.0);
             if (wmode == 0) amax = fmax(amax, counted ? fabs(yn - z0) * w : 0.0);
         }
-        if (k + 1 < me.count) zo += zstep;
     }
     cp_wait<0>();
     __syncwarp();
