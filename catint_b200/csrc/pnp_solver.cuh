@@ -634,7 +634,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 }
 
 // ---------------------------------------------------------------------------
-// rhs = F(y) - Mass*(y+psi)*inv_gamma for every unknown; one lane per node.
+// rhs = F(y) - Mass*(y+psi)*inv_gamma for every unknown; one lane per node (mass term fused).
 // The g-row of interior nodes carries the same scale as in factor_sweep.
 template <int NB, bool ST>
 __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
@@ -645,10 +645,16 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     for (int i = ws.vlane; i < n; i += ws.vstride) {
         const double* y0 = y + (size_t)i * NB;
         double* out = ws.zb + (size_t)i * NB;
+        // mass term of the BDF corrector: psi streams from global memory, loaded first so that its
+        // latency hides behind the stencil arithmetic
+        double ps[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) ps[r] = (inv_gamma != 0.0 && i < n - 1) ? ws.psi[(size_t)i * NB + r] : 0.0;
         if (i == 0 || i == n - 1) {
 #pragma unroll 1
             for (int r = 0; r < NB; ++r) {
                 double v = row_residual<NB, ST>(ws, y, i, r);
+                if (inv_gamma != 0.0 && r < S && i == 0) v -= (y0[r] + ws.psi[r]) * inv_gamma;
                 out[r] = v;
             }
             continue;
@@ -664,6 +670,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
             const double cm = ym[r], c0 = y0[r], cp = yp[r];
             F[r] = ws.sp->D[r] * (k.am * cm - (k.am + k.ap) * c0 + k.ap * cp
                                   + ws.sp->bq[r] * k.ac * (cp * gp - cm * gm));
+            F[r] = fma(-(c0 + ps[r]), inv_gamma, F[r]);
             rho = fma(ws.sp->qe[r], c0, rho);
         }
         for (int rr = 0; rr < tb.R; ++rr) {
@@ -689,18 +696,6 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
         if (ST) out[NB - 1] = -(y0[NB - 1] - ym[NB - 1] - y0[S] * k.him);
     }
     __syncwarp();
-    if (inv_gamma != 0.0) {
-        // mass term of the BDF corrector, psi streamed from global memory; every lane finishes the
-        // node records it produced above (no cross-lane dependency, hence no barrier in between)
-        for (int i = ws.vlane; i < n - 1; i += ws.vstride) {
-#pragma unroll
-            for (int r = 0; r < S; ++r) {
-                const size_t idx = (size_t)i * NB + r;
-                ws.zb[idx] -= (y[idx] + ws.psi[idx]) * inv_gamma;
-            }
-        }
-        __syncwarp();
-    }
 }
 
 // ---------------------------------------------------------------------------
