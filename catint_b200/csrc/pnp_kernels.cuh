@@ -2,8 +2,8 @@
 //
 //   K1  pnp_rhs_kernel       dc/dt of the reference ODE (streaming stencil, HBM bound)
 //   K2  pnp_jacobian_kernel  residual + block-tridiagonal Jacobian blocks (parity/debug)
-//   K3  pnp_bdf_kernel       per-cell BDF/Newton integrator with fused assembly +
-//                            block-Thomas solve (see pnp_solver.cuh)
+//   K3  pnp_bdf_kernel       per-cell variable-order BDF / modified-Newton integrator on the twisted
+//                            block factorisation of pnp_solver.cuh, one warp per cell
 #pragma once
 #include <type_traits>
 #include <cuda_runtime.h>

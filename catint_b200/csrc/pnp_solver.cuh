@@ -1,21 +1,23 @@
 // pnp_solver.cuh -- per-cell linear algebra of the implicit integrator (K2+K3 building blocks).
 //
 // One warp owns one cell.  The Newton matrix  A = Mass/gamma - dF/dy  is block
-// tridiagonal (+ one wall block); it is FACTORED by a block-Thomas sweep with
-// partial pivoting inside the NB x NB blocks and the factors are kept in global
-// memory (L2) so that the modified-Newton iterations of the following steps only
-// run the cheap SOLVE sweeps (VODE/CVODE re-use policy):
+// tridiagonal (+ one wall block).  It is FACTORED by a twisted block elimination (from both
+// ends towards the coupling node n/2) with threshold pivoting inside the NB x NB blocks, and
+// the factors are kept in global memory (L2) so that the modified-Newton iterations of the
+// following steps only run the cheap SOLVE sweeps (VODE/CVODE re-use policy):
 //
-//   factor_sweep   lane j owns one column of the augmented block row
-//                  [A_D' | I | u_g]  (2*NB+1 <= 32 columns, NB registers per lane);
-//                  Gauss-Jordan with row pivoting turns it into [I | inv_i | W_i[:,g]];
-//                  inv_i = A_D'^{-1}, W_i = inv_i*A_U (A_U = diag + one column (g)),
-//                  both go to global memory; W columns are handed to the A_D lanes of
-//                  the next node by warp shuffles for the Schur update A_D' = A_D - A_L*W.
+//   factor_nodes   phase 1, all lanes: assembly of every node's record [A_D | l,a,ud,ua] (one
+//                  (node, unknown) pair per lane at a time);
+//                  phase 2, sequential: records stream back through the cp.async ring; lane j owns
+//                  one column of [A_D' | I | u_g] (2*NB+1 <= 32 columns, NB registers per lane);
+//                  a rolled Gauss-Jordan turns it into [I | inv_i | W_i[:,g]]; inv_i = A_D'^{-1}
+//                  goes to global memory, the W columns (inv_i*A_U top-down, inv_i*A_L bottom-up)
+//                  are handed to the A_D lanes of the next node by warp shuffles for the Schur
+//                  update A_D' = A_D - A_L*W (resp. A_U*W^b).
 //   residual_pass  lane per node: rhs = F(y) - Mass*(y+psi)/gamma  (K1 arithmetic on the
 //                  shared-memory state)
-//   forward_solve  lane r owns row r:  z_i = inv_i*(rhs_i - A_L z_{i-1})
-//   backward_sweep lane r owns row r:  d_i = z_i - W_i d_{i+1};  y += d; weighted max norms
+//   forward_solve  two chains, one per half warp, lane = row:  z_i = inv_i*(rhs_i - A_L z_{i-1})
+//   backward_solve same mapping:  d_i = z_i - inv_i*(A_U d_{i+1});  y += d; weighted max norms
 //
 // No tensor cores: the blocks are 9..13 wide and the chain over nodes is sequential.
 #pragma once
@@ -34,7 +36,7 @@ struct WarpState {
     double* fac;    // per node record [ inv_i: NB x NBP | per row l, a (A_L), ud, ua (A_U): NB x 4 ]  (global)
     double* W1;     // inv_1*A_U1' (dense because of the wall block)   [NB][NBP]
     double* V0;     // inv_0*A_E                           [NB][NBP]
-    double* ring;   // shared: RING node records staged by cp.async ahead of the solve sweeps
+    double* ring;   // shared: node records staged by cp.async ahead of the sweeps (+ weights, history chunks)
     double* scratch;            // shared, per warp
     const CellSpecies* sp;      // shared, per warp
     const DevTables* tb;        // shared, per block
