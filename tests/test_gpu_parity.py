@@ -319,6 +319,42 @@ def test_ten_species_ragged_sweep_cells(bk, resultsdir):
     assert n_ok == 13
 
 
+def test_c4_sweep_4096_cells_properties(bk, resultsdir):
+    """size-independent properties on a 64 x 64 C4-type sweep (10 species, block size 11, ragged 101/102
+    nodes, several launch waves): every cell is either converged or carries a failure status (thin layers
+    whose discrete ODE blows up in finite time, as in the CPU oracle); every converged cell zeroes K1's
+    dc/dt and carries exactly the imposed wall fluxes."""
+    import torch
+    from catint_b200 import backend as be, workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import build_cell_batch
+    tp = Transport(resultsdir=resultsdir, **workloads.c4(n_pH=64, n_L=64))
+    batch, _ = build_cell_batch(tp)
+    assert batch.B == 4096 and batch.b == 11
+    db = bk.upload(batch)
+    out = bk.solve(db, [200.0], mode=be.MODE_STEADY, max_steps=20000)
+    status = out['status'].cpu().numpy()
+    ok = status == 0
+    assert ok.sum() >= 0.6 * batch.B, int(ok.sum())
+    assert set(np.unique(status[~ok])) <= {1, 2, 3, 4, 5, 6}
+    c = out['c'][-1].contiguous()
+    dcdt, _, _ = bk.rhs(db, c)
+    S = batch.S
+    D = torch.tensor(batch.par[:, 2 * S:3 * S], device=c.device)
+    dx = torch.tensor(batch.par[:, 3 * S + 5], device=c.device)
+    scale = (c.abs().amax(dim=1) * D / dx[:, None] ** 2).amax(dim=1)
+    ratio = (dcdt.abs().amax(dim=(1, 2)) / scale).cpu().numpy()
+    # (measured: median 3e-11, max 1.3e-8 of the size of the cancelling stencil terms)
+    assert np.all(ratio[ok] < 1e-7), float(ratio[ok].max())
+    assert float(np.median(ratio[ok])) < 1e-9
+    flux = out['flux'].cpu().numpy()
+    J = batch.par[:, S:2 * S]
+    assert np.max(np.abs(flux[ok] - J[ok])) <= 1e-8 * np.max(np.abs(J))
+    # the failures are the thinnest layers only
+    dxs = batch.par[:, 3 * S + 5]
+    assert dxs[~ok].max() < 2.5e-7 and dxs[ok].max() > 1.5e-6
+
+
 def test_thousand_node_grid_uses_global_state(bk, resultsdir):
     """1001 nodes: the Newton iterate no longer fits in shared memory (workspace path).  Transient
     outputs against the CPU BDF oracle at the same rtol/atol, steady state against its Newton root."""
