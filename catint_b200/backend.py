@@ -20,7 +20,10 @@ MODE_TRANSIENT = 0
 MODE_STEADY = 1
 
 CELL_STATUS = {0: 'converged', 1: 'max_steps', 2: 'corrector_failed', 3: 'error_test_failed',
-               4: 'not_finite', 5: 'polish_failed', 6: 'step_underflow'}
+               4: 'not_finite', 5: 'polish_failed', 6: 'step_underflow', 7: 'bad_input'}
+MAX_BLOCK = 13          # unknowns per node handled by catint_pnp_solve_batch / _jacobian_batch
+MIN_NODES = 6           # CATINT_PNP_MIN_NODES
+MAX_OUTPUT_TIMES = 4096
 
 _LIB_NAME = 'libcatint_pnp.so'
 _lib = None
@@ -123,6 +126,20 @@ class CellBatch(object):
         self.origin = np.arange(self.B)          # cell indices in the batch this one was selected from
         if self.S > MAX_SPECIES or self.R > MAX_REACTIONS:
             raise ValueError('at most %d species and %d reactions' % (MAX_SPECIES, MAX_REACTIONS))
+        if self.B and (int(self.nx.min()) < MIN_NODES or int(self.nx.max()) > self.nx_max):
+            raise ValueError('every cell needs %d <= nx <= nx_max = %d nodes (got %d..%d)'
+                             % (MIN_NODES, self.nx_max, int(self.nx.min()), int(self.nx.max())))
+        if self.mesh_id is not None:
+            if self.mesh_xi is None or self.mesh_xi.ndim != 2 or self.mesh_xi.shape[1] < self.nx_max:
+                raise ValueError('mesh_xi must be [n_mesh, >= nx_max]')
+            if self.B and int(self.mesh_id.max()) >= self.mesh_xi.shape[0]:
+                raise ValueError('mesh_id out of range')
+
+    def check_solvable(self):
+        """limits of the integrator / Jacobian kernels (the RHS kernel takes up to MAX_SPECIES species)"""
+        if not 2 <= self.b <= MAX_BLOCK:
+            raise ValueError('catint_pnp_solve_batch handles 2..%d unknowns per node (S+1, or S+2 with the Stern '
+                             'boundary); got %d' % (MAX_BLOCK, self.b))
 
     @property
     def b(self):
@@ -271,6 +288,7 @@ class PnpBackend(object):
         torch = self.torch
         b = dbatch.batch
         nb = b.b
+        b.check_solvable()
         assert y.shape == (b.B, b.nx_max, nb) and y.dtype == torch.float64 and y.is_contiguous()
         F = torch.zeros_like(y)
         blocks = [torch.zeros((b.B, b.nx_max, nb, nb), dtype=torch.float64, device=self.device) for _ in range(3)]
@@ -306,6 +324,9 @@ class PnpBackend(object):
         b = dbatch.batch
         t_out = np.ascontiguousarray(np.atleast_1d(np.asarray(t_out, dtype=np.float64)))
         n_out = len(t_out)
+        b.check_solvable()
+        if n_out > MAX_OUTPUT_TIMES:
+            raise ValueError('at most %d output times per solve' % MAX_OUTPUT_TIMES)
         dev = self.device
         if out is None:
             out = self.alloc_outputs(dbatch, n_out)

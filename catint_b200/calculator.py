@@ -235,13 +235,12 @@ class Calculator():
             ts = [float(self.tp.tmax)]
         return ts
 
-    def solve_batch(self, batch, backend=None, pinned=None, y0=None):
-        """host CellBatch -> host result dict (numpy).  Host->device copies, the
-        solve and the device->host copies all happen here.  y0: optional initial
-        concentrations [B,nx_max,S] (default: bulk everywhere, the reference's c0)."""
+    def solve_batch_device(self, batch, backend=None, pinned=None, y0=None):
+        """host CellBatch -> result dict of DEVICE tensors (plus the host->device byte count): upload of the
+        cell parameters and the solve.  The sharded driver gathers these on the device."""
         import torch
         if backend is None:
-            backend = _be.PnpBackend(self.device)
+            backend = self._backend()
         db = backend.upload(batch, pinned=pinned)
         mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT
         y0_dev = None
@@ -249,10 +248,23 @@ class Calculator():
             y0_dev = torch.as_tensor(np.ascontiguousarray(y0, dtype=np.float64)).to(backend.device)
         out = backend.solve(db, self.output_times(), mode=mode, rtol=self.rtol, atol=self.atol,
                             max_steps=self.max_steps, y0=y0_dev)
-        host = {k: v.cpu().numpy() for k, v in out.items()}
-        host['h2d_bytes'] = db.h2d_bytes + (0 if y0 is None else int(y0_dev.numel() * 8))
-        host['d2h_bytes'] = sum(int(v.numel() * v.element_size()) for v in out.values())
+        out = dict(out)
+        out['h2d_bytes'] = db.h2d_bytes + (0 if y0 is None else int(y0_dev.numel() * 8))
+        return out
+
+    def solve_batch(self, batch, backend=None, pinned=None, y0=None):
+        """host CellBatch -> host result dict (numpy).  Host->device copies, the
+        solve and the device->host copies all happen here.  y0: optional initial
+        concentrations [B,nx_max,S] (default: bulk everywhere, the reference's c0)."""
+        out = self.solve_batch_device(batch, backend=backend, pinned=pinned, y0=y0)
+        host = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items()}
+        host['d2h_bytes'] = sum(int(v.numel() * v.element_size()) for v in out.values() if hasattr(v, 'numel'))
         return host
+
+    def _backend(self):
+        if getattr(self, '_bk', None) is None:
+            self._bk = _be.PnpBackend(self.device)
+        return self._bk
 
     def initial_state_from_folder(self, batch):
         """system['init_folder'] (reference: calculator.py:303-309, a previous results folder) -> initial
@@ -297,7 +309,8 @@ class Calculator():
         if y0 is None:
             res = _dist.solve_sharded(self, batch)
         else:
-            res = _dist.solve_sharded(self, batch, solve_fn=lambda sub: self.solve_batch(sub, y0=y0[sub.origin]))
+            res = _dist.solve_sharded(self, batch,
+                                      solve_fn=lambda sub: self.solve_batch_device(sub, y0=y0[sub.origin]))
         t1 = time.time()
         if res is not None:
             self.scatter_results(batch, models, res)
@@ -314,48 +327,62 @@ class Calculator():
     # ------------------------------------------------------------------
     def scatter_results(self, batch, models, res):
         """fill tp.cout/potential/efield/total_charge (last cell, like the serial
-        reference loop would leave them) and tp.alldata[i] for every cell."""
+        reference loop would leave them) and tp.alldata[i] for every cell.  Per-cell
+        quantities are computed for the whole batch at once (numpy); the per-cell loop only
+        hands out views (64k-cell sweeps: seconds, not minutes)."""
         tp = self.tp
         names = list(tp.species)
         S = len(names)
         c_all = res['c']          # [n_out,B,nx_max,S]
+        cfin_all = c_all[-1]      # [B,nx_max,S]
+        g_all, phi_all = res['g'][-1], res['phi'][-1]
         q = np.array([tp.species[s]['charge'] for s in names]) * unit_F
-        for c in range(batch.B):
-            n = int(batch.nx[c])
-            m = models[c]
-            cfin = c_all[-1, c, :n, :]                 # [n,S]
-            g = res['g'][-1, c, :n]
-            phi = res['phi'][-1, c, :n]
-            ad = tp.alldata[c]
-            for k, sp in enumerate(names):
-                d = ad['species'].setdefault(sp, {})
-                d['concentration'] = list(cfin[:, k])
-                d['surface_concentration'] = float(cfin[0, k])
-                d['electrode_flux'] = float(res['flux'][c, k])
-                if m.electrode_reactions is not None and sp in m.electrode_reactions:
-                    er = m.electrode_reactions[sp]
+        rho_all = cfin_all @ q    # [B,nx_max]
+        with np.errstate(invalid='ignore', divide='ignore'):
+            if 'H+' in names:
+                ph_all = -np.log10(cfin_all[:, :, names.index('H+')] / 1000.)
+            elif 'OH-' in names:
+                ph_all = 14 + np.log10(cfin_all[:, :, names.index('OH-')] / 1000.)
+            else:
+                ph_all = None
+        # current density = flux*nel*F/nprod/10 mA/cm^2 (comsol_reader.py:243-246); one factor per species
+        m0 = models[0]
+        cd_factor = {}
+        if m0.electrode_reactions is not None:
+            for sp in names:
+                if sp in m0.electrode_reactions:
+                    er = m0.electrode_reactions[sp]
                     nprod = len([a for a in er['reaction'][1] if a == sp])
-                    d['electrode_current_density'] = d['electrode_flux'] * er['nel'] * unit_F / nprod / 10.
+                    cd_factor[sp] = er['nel'] * unit_F / nprod / 10.
+        flux = res['flux']
+        status = res['status']
+        nxs = batch.nx
+        for c in range(batch.B):
+            n = int(nxs[c])
+            ad = tp.alldata[c]
+            spd = ad['species']
+            cf = cfin_all[c, :n]
+            for k, sp in enumerate(names):
+                d = spd.setdefault(sp, {})
+                d['concentration'] = cf[:, k]
+                d['surface_concentration'] = float(cf[0, k])
+                fl = float(flux[c, k])
+                d['electrode_flux'] = fl
+                if sp in cd_factor:
+                    d['electrode_current_density'] = fl * cd_factor[sp]
             sysd = ad['system']
-            sysd['potential'] = list(phi)
-            sysd['efield'] = list(-g)
-            sysd['charge_density'] = list(cfin @ q)
-            sysd['surface_potential'] = float(phi[0])
-            with np.errstate(invalid='ignore', divide='ignore'):
-                if 'H+' in names:
-                    ph = -np.log10(cfin[:, names.index('H+')] / 1000.)
-                elif 'OH-' in names:
-                    ph = 14 + np.log10(cfin[:, names.index('OH-')] / 1000.)
-                else:
-                    ph = None
-            if ph is not None:
-                sysd['pH'] = list(ph)
-                if np.isfinite(ph[0]):
-                    sysd['surface_pH'] = float(ph[0])
+            sysd['potential'] = phi_all[c, :n]
+            sysd['efield'] = -g_all[c, :n]
+            sysd['charge_density'] = rho_all[c, :n]
+            sysd['surface_potential'] = float(phi_all[c, 0])
+            if ph_all is not None:
+                sysd['pH'] = ph_all[c, :n]
+                if np.isfinite(ph_all[c, 0]):
+                    sysd['surface_pH'] = float(ph_all[c, 0])
                 else:
                     tp.logger.warning('| CI | -- | negative surface concentration, surface pH cannot be evaluated '
                                       'for cell {}'.format(c))
-            sysd['status'] = _be.CELL_STATUS.get(int(res['status'][c]), int(res['status'][c]))
+            sysd['status'] = _be.CELL_STATUS.get(int(status[c]), int(status[c]))
         # containers of the serial FD path (calculator_old.py:816-818, 966-973): last cell
         last = batch.B - 1
         n = int(batch.nx[last])

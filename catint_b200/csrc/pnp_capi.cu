@@ -30,7 +30,7 @@ static int fail(int code, const char* fmt, const char* a = "") {
     return code;
 }
 
-static long long* g_prof = nullptr;      // debug hook, see catint_pnp_debug_profile_buffer
+static thread_local long long* g_prof = nullptr;      // debug hook (per host thread), see catint_pnp_debug_profile_buffer
 extern "C" int catint_pnp_version(void) { return 101; }
 extern "C" void catint_pnp_debug_profile_buffer(void* dev_ptr) { g_prof = reinterpret_cast<long long*>(dev_ptr); }
 extern "C" const char* catint_pnp_last_error(void) { return g_err; }
@@ -110,18 +110,18 @@ static int block_size_of(const CatintPnpShared* sh) {
 
 static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
     const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
-    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1,Wb[NB][NBP] + (y,psi,zb)[N] (used only when the state
+    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1[NB][NBP] + (y,psi,zb)[N] (used only when the state
     // does not fit in shared memory, always reserved so that the size query is stateless)
     const size_t NBP = NB + (NB & 1);
     const size_t REC = NB * NBP + NB * 4;
-    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 3 * align4(NB * NBP) +
+    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 2 * align4(NB * NBP) +
                3 * align4(nxm * NB);
     return (d + 15) & ~size_t(15);
 }
 
 extern "C" size_t catint_pnp_workspace_bytes(const CatintPnpShared* sh, int64_t n_cells) {
     if (!sh || n_cells <= 0) return 0;
-    return ws_doubles_per_cell(sh) * sizeof(double) * (size_t)n_cells + 64 * sizeof(double);
+    return ws_doubles_per_cell(sh) * sizeof(double) * (size_t)n_cells + CATINT_PNP_MAX_OUTPUT_TIMES * sizeof(double);
 }
 
 static int check_cuda(const char* what) {
@@ -156,6 +156,14 @@ static int check_common(const CatintPnpShared* sh, const CatintPnpCells* cells, 
     if (!cells->par || !cells->nx) return fail(CATINT_PNP_EINVAL, "cells->par / cells->nx are NULL");
     if (sh->n_mesh > 0 && !cells->mesh_xi) return fail(CATINT_PNP_EINVAL, "mesh table missing");
     if (catint_pnp_device_count() <= 0) return fail(CATINT_PNP_ENODEV, "no sm_100 CUDA device visible");
+    // the kernels are sm_100a code: the CURRENT device (the one the caller's stream and pointers live on) must be one
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CATINT_PNP_ECUDA, "cannot query the current CUDA device");
+    }
+    if (major != 10) return fail(CATINT_PNP_ENODEV, "the current CUDA device is not sm_100");
     return CATINT_PNP_OK;
 }
 
@@ -210,6 +218,7 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
                                       void* workspace, size_t workspace_bytes, void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
+    if (sh->nx_max < CATINT_PNP_MIN_NODES) return fail(CATINT_PNP_EINVAL, "nx_max must be >= CATINT_PNP_MIN_NODES");
     if (!ctl || !ctl->t_out || ctl->n_out < 1) return fail(CATINT_PNP_EINVAL, "control / t_out missing");
     if (!c_out || !status || !n_steps || !n_newton) return fail(CATINT_PNP_EINVAL, "output pointers are NULL");
     if (!(ctl->rtol >= 0.0) || !(ctl->atol > 0.0)) return fail(CATINT_PNP_EINVAL, "need rtol >= 0 and atol > 0");
@@ -218,7 +227,8 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
             return fail(CATINT_PNP_EINVAL, "t_out must be positive and increasing");
     const size_t need = catint_pnp_workspace_bytes(sh, n_cells);
     if (!workspace || workspace_bytes < need) return fail(CATINT_PNP_ENOMEM, "workspace too small");
-    if (ctl->n_out > 60) return fail(CATINT_PNP_EINVAL, "at most 60 output times per call");
+    if (ctl->n_out > CATINT_PNP_MAX_OUTPUT_TIMES)
+        return fail(CATINT_PNP_EINVAL, "too many output times per call (CATINT_PNP_MAX_OUTPUT_TIMES)");
 
     SolveParams P;
     rc = build_tables(sh, P.tb);

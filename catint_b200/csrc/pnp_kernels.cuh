@@ -20,6 +20,15 @@ namespace catint {
 constexpr int QMAX = 5;
 constexpr int LMAX = QMAX + 1;     // Nordsieck vectors zn[0..QMAX]
 
+// The step/order control below (set_bdf, increase_coef, decrease_coef, the step-attempt loop of
+// pnp_bdf_kernel and these constants) restates the published variable-coefficient Nordsieck BDF scheme
+// of VODE / SUNDIALS CVODE -- cvSetBDF, cvIncreaseBDF, cvDecreaseBDF, cvNls/cvDoErrorTest/cvPrepareNextStep
+// and CVODE's constant names -- from P. N. Brown, G. D. Byrne, A. C. Hindmarsh, "VODE: a variable-coefficient
+// ODE solver", SIAM J. Sci. Stat. Comput. 10 (1989) 1038-1051, and A. C. Hindmarsh et al., "SUNDIALS: suite of
+// nonlinear and differential/algebraic equation solvers", ACM TOMS 31 (2005) 363-396 (the ODEPACK family
+// that scipy.integrate.odeint = LSODA, the reference's integrator at catint/calculator_old.py:947, belongs
+// to).  It is a third-party algorithm restated from its publications, not code taken from SUNDIALS;
+// oracle/bdf_local.py is the CPU prototype of the same control flow.
 // integrator constants (VODE/CVODE family)
 constexpr double ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
 constexpr double ETAMX1 = 1e4, ETAMX2 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1, ETACF = 0.25, THRESH = 1.5;
@@ -203,19 +212,19 @@ __device__ void decrease_coef(const Bdf<NB, ST>& B, double* l) {
 // chunks (32 consecutive unknowns per warp) into the shared-memory ring of the solve sweeps with
 // cp.async, STREAM_DEPTH chunks ahead; a lane only ever reads back what it copied itself, hence no
 // barrier.  ring_doubles<NB,ST>() is the ring's size; small blocks (ring too short) load directly.
-template <int NB, bool ST, bool PAIR>
+template <int NB, bool ST>
 __host__ __device__ constexpr int ring_doubles() {
-    return (PAIR ? RING_CHAIN : RING) * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    return RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
 }
-template <int NB, bool ST, bool PAIR, int NARR>
+template <int NB, bool ST, int NARR>
 __host__ __device__ constexpr int stream_depth() {
-    return ring_doubles<NB, ST, PAIR>() / (NARR * 32) > 8 ? 8 : ring_doubles<NB, ST, PAIR>() / (NARR * 32);
+    return ring_doubles<NB, ST>() / (NARR * 32) > 8 ? 8 : ring_doubles<NB, ST>() / (NARR * 32);
 }
 
 // QF > 0: instance specialised for the common case "order QF kept, nothing to undo, predict": all
 // order tests fold at compile time and the loop body shrinks to the loads, the rescaling, the
 // Pascal additions and the stores of exactly QF+1 arrays.  QF = 0: general run-time version.
-template <int NB, bool ST, bool PAIR, int QF>
+template <int NB, bool ST, int QF>
 __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, bool undo_rt, double eta,
                              const double* lc, double A1, double rl1, bool predict_rt) {
     const int N = ws.N;
@@ -224,14 +233,14 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
     const bool undo = QF ? false : undo_rt;
     const bool predict = QF ? true : predict_rt;
     const int q_new = q_old + dq;
-    constexpr int SD = stream_depth<NB, ST, PAIR, LMAX>();
+    constexpr int SD = stream_depth<NB, ST, LMAX>();
     constexpr bool STREAM = SD >= 3;
-    const int nch = (N + ws.vstride - 1) / ws.vstride;
+    const int nch = (N + 32 - 1) / 32;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(ws.ring) + 8u * ws.lane;
     const double* sring = ws.ring + ws.lane;
     int islot = 0, ichunk = 0;
     auto issue = [&]() {
-        const int idx = ws.vlane + ichunk * ws.vstride;
+        const int idx = ws.lane + ichunk * 32;
         if (ichunk < nch && idx < N) {
             const unsigned d = sb + (unsigned)(islot * LMAX * 256);
 #pragma unroll
@@ -248,7 +257,7 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
     }
     int rslot = 0;
     for (int c = 0; c < nch; ++c) {
-        const int idx = ws.vlane + c * ws.vstride;
+        const int idx = ws.lane + c * 32;
         if constexpr (STREAM) cp_wait<(SD >= 3 ? SD - 2 : 0)>();
         if (idx >= N) { if constexpr (STREAM) { issue(); rslot = (rslot + 1 == SD) ? 0 : rslot + 1; } continue; }
         double z[LMAX];
@@ -315,84 +324,40 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
 // SMEM = true: the Newton iterate, psi and the rhs/update vector live in shared memory and are
 // addressed with LDS/STS (a generic pointer would queue these critical-path accesses behind the
 // global prefetch loads in the L1TEX pipeline); SMEM = false: large grids, state in the workspace.
-//
-// PAIR = false: one warp per cell, four cells per block.
-// PAIR = true : one block of two warps per cell (twisted block elimination).  Warp 0 eliminates the
-//   nodes 0..m-1 downwards and owns the coupling node m = n/2, warp 1 eliminates n-1..m+1 upwards;
-//   both halves of every sweep run concurrently, which halves the sequential depth of the factor and
-//   solve sweeps; the element-wise passes over the Nordsieck history are split between the warps.
-//   Both warps execute the same (scalar) step/order control on identical norms, so they stay in
-//   lock step; a named hardware barrier (bar.sync id, 64) is the pair barrier.  Experimental, see
-//   launch_bdf.
-constexpr int PAIR_CELLS = 7;      // cells (warp pairs) per block in PAIR mode: 148 x 7 = 1036 cells in one wave
-
-template <bool PAIR>
-__device__ __forceinline__ void pair_sync(int bar_id) { if constexpr (PAIR) pair_barrier(bar_id); }
-
-// max over the two warps of a pair (xn: two shared doubles)
-template <bool PAIR>
-__device__ __forceinline__ double pair_max(double v, double* xn, int half, int lane, int bar_id) {
-    v = warp_max(v);
-    if constexpr (PAIR) {
-        if (lane == 0) xn[half] = v;
-        pair_barrier(bar_id);
-        v = fmax(xn[0], xn[1]);
-        pair_barrier(bar_id);
-    }
-    return v;
-}
+// One warp per cell, four cells per block.  (A variant with two warps per cell, one per half of the
+// twisted elimination, was measured slower in round 1 -- register cap and issue-slot contention --
+// and has been removed; both halves now run in the two half warps of the one warp.)
 
 // One linear solve with the stored factors + update of the iterate:  zb holds the rhs on entry and the
 // (unscaled) update on exit, y += scale*update; returns the weighted max norms of the scaled update
 // and of the accumulated correction (identical on both warps of a pair).
-template <int NB, bool ST, bool PAIR>
-__device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid, int half, double* xn,
+template <int NB, bool ST>
+__device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid,
                              double& del, double& acn, int wmode, double prtol, double patol,
                              long long* pc, bool prof_on) {
     const int n = ws.cs.n;
     double dmax = 0.0, amax = 0.0;
-    const Chain none = {0, 0, 1};
-    if constexpr (!PAIR) {
-        // one warp, twisted factors: both chains advance in the two halves of the warp
-        long long t0 = prof_on ? clock64() : 0;
-        forward_solve<NB, ST>(ws, Chain{0, mid, +1}, Chain{n - 1, n - 1 - mid, -1});
-        solve_middle<NB, ST>(ws, mid);
-        if (prof_on) pc[2] += clock64() - t0;
-        t0 = prof_on ? clock64() : 0;
-        apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
-        backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, Chain{mid + 1, n - 1 - mid, +1},
-                               dmax, amax, wmode, prtol, patol);
-        del = warp_max(dmax);
-        acn = warp_max(amax);
-        if (prof_on) pc[3] += clock64() - t0;
-    } else {
-        long long t0 = prof_on ? clock64() : 0;
-        if (half == 0) forward_solve<NB, ST>(ws, Chain{0, mid, +1}, none);
-        else forward_solve<NB, ST>(ws, Chain{n - 1, n - 1 - mid, -1}, none);
-        pair_barrier(ws.bar_id);
-        if (half == 0) {
-            solve_middle<NB, ST>(ws, mid);
-            apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
-        }
-        pair_barrier(ws.bar_id);
-        if (prof_on) pc[2] += clock64() - t0;
-        t0 = prof_on ? clock64() : 0;
-        if (half == 0) backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, none, dmax, amax, wmode, prtol, patol);
-        else backward_solve<NB, ST>(ws, scale, Chain{mid + 1, n - 1 - mid, +1}, none, dmax, amax, wmode, prtol, patol);
-        del = pair_max<PAIR>(dmax, xn, half, ws.lane, ws.bar_id);
-        acn = pair_max<PAIR>(amax, xn, half, ws.lane, ws.bar_id);
-        if (prof_on) pc[3] += clock64() - t0;
-    }
+    // twisted factors: both chains advance in the two halves of the warp
+    long long t0 = prof_on ? clock64() : 0;
+    forward_solve<NB, ST>(ws, Chain{0, mid, +1}, Chain{n - 1, n - 1 - mid, -1});
+    solve_middle<NB, ST>(ws, mid);
+    if (prof_on) pc[2] += clock64() - t0;
+    t0 = prof_on ? clock64() : 0;
+    apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
+    backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, Chain{mid + 1, n - 1 - mid, +1},
+                           dmax, amax, wmode, prtol, patol);
+    del = warp_max(dmax);
+    acn = warp_max(amax);
+    if (prof_on) pc[3] += clock64() - t0;
 }
 
-template <int NB, bool ST, bool SMEM, bool PAIR>
-__global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pnp_bdf_kernel(SolveParams P) {
+template <int NB, bool ST, bool SMEM>
+__global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
-    constexpr int WARPS = PAIR ? PAIR_CELLS : 4;          // cells per block
+    constexpr int WARPS = 4;                               // cells per block
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int half = PAIR ? (warp & 1) : 0;
-    const int slot = PAIR ? (warp >> 1) : warp;            // cell slot inside the block
+    const int slot = warp;                                 // cell slot inside the block
     const long long cell = (long long)blockIdx.x * WARPS + slot;
 
     // shared layout: tables | per warp { CellSpecies | scratch | [y psi zb] }
@@ -406,12 +371,10 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
-    // per cell: CellSpecies | per warp {scratch | ring} | [y zb] | pair exchange (xch block, norms)
-    constexpr size_t RINGD = (size_t)ring_doubles<NB, ST, PAIR>();
-    constexpr size_t WARPD = scratch_doubles<NB, ST>() + RINGD;          // doubles private to one warp
-    constexpr int WPC = PAIR ? 2 : 1;                                     // warps per cell
-    const size_t cell_doubles = WPC * WARPD + (SMEM ? (size_t)2 * nxm * NB : 0) +
-                                (PAIR ? (size_t)NB * padded<NB, ST>() + 4 : 0);
+    // per cell: CellSpecies | scratch | ring | [y zb]
+    constexpr size_t RINGD = (size_t)ring_doubles<NB, ST>();
+    constexpr size_t WARPD = scratch_doubles<NB, ST>() + RINGD;          // doubles private to the warp
+    const size_t cell_doubles = WARPD + (SMEM ? (size_t)2 * nxm * NB : 0);
     const size_t per_cell = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + cell_doubles * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)slot * per_cell;
     if (cell >= P.n_cells) return;
@@ -419,19 +382,21 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     const long long t_kernel0 = clock64();
     WarpState<NB, ST> ws;
     ws.lane = lane;
-    ws.bar_id = PAIR ? slot + 1 : 0;
-    ws.vlane = lane + 32 * half;
-    ws.vstride = 32 * WPC;
     ws.tb = tb;
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
     ws.sp = sp;
     double* cellbase = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
-    ws.scratch = cellbase + (size_t)half * WARPD;
-    if (half == 0) load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
-    pair_sync<PAIR>(ws.bar_id);
-    if (PAIR && half == 1)             // scalars only: the species table was filled by warp 0
-        load_cell_scalars(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, ws.cs);
+    ws.scratch = cellbase;
+    load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
     const int n = ws.cs.n;
+    if (n < CATINT_PNP_MIN_NODES || n > nxm) {           // bad nx[cell]: report, touch nothing else
+        if (lane == 0) {
+            P.status[cell] = CATINT_PNP_CELL_BAD_INPUT;
+            P.n_steps[cell] = 0; P.n_newton[cell] = 0;
+            if (P.n_setups) P.n_setups[cell] = 0;
+        }
+        return;
+    }
     const int N = n * NB;
     ws.N = N;
     double* g = P.ws + (size_t)cell * P.ws_stride;
@@ -442,24 +407,22 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
     ws.psi = g;                g += align4((size_t)nxm * NB);
-    double* xch_g = g;         g += align4((size_t)NB * NBP);   // one warp per cell: coupling block W^b_{mid+1}
     ws.ring = ws.scratch + scratch_doubles<NB, ST>();
-    double* sdyn = cellbase + (size_t)WPC * WARPD;
+    double* sdyn = cellbase + WARPD;
     if constexpr (SMEM) {
         ws.y = sdyn; ws.zb = sdyn + (size_t)nxm * NB;
         sdyn += (size_t)2 * nxm * NB;
     } else {
         ws.y = g; ws.zb = g + align4((size_t)nxm * NB);
     }
-    double* xch = PAIR ? sdyn : xch_g;                    // W^b block handed to the coupling node
-    double* xn = sdyn + (size_t)NB * NBP;                 // PAIR: norm / flag exchange
     const int mid = n / 2;                                // coupling node of the twisted sweeps
     SmemOffsets so;                                       // shared-memory pointers as offsets (factor_nodes)
     so.scratch = (unsigned)(reinterpret_cast<unsigned char*>(ws.scratch) - smem_raw);
     so.sp = (unsigned)(reinterpret_cast<const unsigned char*>(sp) - smem_raw);
     so.y = SMEM ? (unsigned)(reinterpret_cast<unsigned char*>(ws.y) - smem_raw) : 0u;
     so.ring = (unsigned)(reinterpret_cast<unsigned char*>(ws.ring) - smem_raw);
-    const int vlane = ws.vlane, vstride = ws.vstride;
+    constexpr int vstride = 32;
+    const int vlane = lane;
 
     // ---- initial state: y0 (or bulk) with the consistent field --------------
     for (int idx = vlane; idx < N; idx += vstride) {
@@ -470,9 +433,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
         ws.psi[idx] = 0.0;
     }
     __syncwarp();
-    pair_sync<PAIR>(ws.bar_id);
-    if (half == 0) consistent_field<NB, ST>(ws, ws.y);
-    pair_sync<PAIR>(ws.bar_id);
+    consistent_field<NB, ST>(ws, ws.y);
 
     const double rtol = P.rtol, atol = P.atol;
 
@@ -490,7 +451,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
         if (mass) fnorm = fmax(fnorm, fabs(F) * w);
     }
     __syncwarp();
-    fnorm = pair_max<PAIR>(fnorm, xn, half, lane, ws.bar_id);
+    fnorm = warp_max(fnorm);
 
     Bdf<NB, ST> B;
     B.q = 1; B.qwait = 2; B.nst = 0; B.t = 0.0; B.etamax = ETAMX1; B.saved_tq5 = 0.0;
@@ -504,7 +465,6 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
     B.h = B.hscale = h0;
     for (int idx = vlane; idx < N; idx += vstride) ws.zn[(size_t)N + idx] *= h0;
     __syncwarp();
-    pair_sync<PAIR>(ws.bar_id);
 
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // factor, residual, forward, backward, norms, history, correction, other
     const bool prof_on = P.prof != nullptr;
@@ -540,16 +500,15 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             { CATINT_TIC;
               if (!pend_undo && pend_dq == 0) {
                   switch (q_old) {
-                      case 1: history_pass<NB, ST, PAIR, 1>(ws, 1, 0, false, pend_eta, lc, A1c, rl1, true); break;
-                      case 2: history_pass<NB, ST, PAIR, 2>(ws, 2, 0, false, pend_eta, lc, A1c, rl1, true); break;
-                      case 3: history_pass<NB, ST, PAIR, 3>(ws, 3, 0, false, pend_eta, lc, A1c, rl1, true); break;
-                      case 4: history_pass<NB, ST, PAIR, 4>(ws, 4, 0, false, pend_eta, lc, A1c, rl1, true); break;
-                      default: history_pass<NB, ST, PAIR, 5>(ws, 5, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 1: history_pass<NB, ST, 1>(ws, 1, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 2: history_pass<NB, ST, 2>(ws, 2, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 3: history_pass<NB, ST, 3>(ws, 3, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      case 4: history_pass<NB, ST, 4>(ws, 4, 0, false, pend_eta, lc, A1c, rl1, true); break;
+                      default: history_pass<NB, ST, 5>(ws, 5, 0, false, pend_eta, lc, A1c, rl1, true); break;
                   }
               } else {
-                  history_pass<NB, ST, PAIR, 0>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
-              }
-              pair_sync<PAIR>(ws.bar_id); CATINT_TOC(5); }
+                  history_pass<NB, ST, 0>(ws, q_old, pend_dq, pend_undo, pend_eta, lc, A1c, rl1, true);
+              } CATINT_TOC(5); }
             pend_dq = 0; pend_undo = false; pend_eta = 1.0;
             const double inv_gamma = B.l[1] / B.h;
 
@@ -567,18 +526,12 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                     // stale factors did not converge: restart the corrector from the prediction
                     for (int idx = vlane; idx < N; idx += vstride) ws.y[idx] = ws.zn[idx];
                     __syncwarp();
-                    pair_sync<PAIR>(ws.bar_id);
                     call_setup = true;
                 }
                 if (call_setup) {
                     CATINT_TIC;
                     bool ok;
-                    if constexpr (PAIR) {
-                        ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid, xch, half == 0 ? FACTOR_TOP : FACTOR_BOTTOM);
-                        ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
-                    } else {
-                        ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid, xch, FACTOR_BOTH);
-                    }
+                    ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid);
                     CATINT_TOC(0);
                     ++nsetups;
                     have_factors = ok;
@@ -592,9 +545,9 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 double crate = 1.0, delp = 0.0;
                 bool bad = false;
                 for (int m = 0; m < MAXCOR; ++m) {
-                    { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); pair_sync<PAIR>(ws.bar_id); CATINT_TOC(1); }
+                    { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); CATINT_TOC(1); }
                     double del = 0.0, acn = 0.0;
-                    newton_solve<NB, ST, PAIR>(ws, dscale, mid, half, xn, del, acn, 0, 0.0, 0.0, pc, prof_on);
+                    newton_solve<NB, ST>(ws, dscale, mid, del, acn, 0, 0.0, 0.0, pc, prof_on);
                     ++nni;
                     if (!(del <= 1e300)) { bad = true; break; }
                     if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
@@ -634,20 +587,18 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 pend_eta = ETAMIN;
             } else {
                 // order 1 and still failing: restart the history from the last accepted state
-                history_pass<NB, ST, PAIR, 0>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
+                history_pass<NB, ST, 0>(ws, B.q, 0, true, 1.0, lc, 0.0, 1.0, false);
                 pend_undo = false;
                 B.h *= ETAMIN; B.hscale = B.h;
                 B.qwait = LONG_WAIT;
                 for (int idx = vlane; idx < N; idx += vstride) ws.y[idx] = ws.zn[idx];
                 __syncwarp();
-                pair_sync<PAIR>(ws.bar_id);
                 for (int idx = vlane; idx < N; idx += vstride) {
                     const int i = idx / NB, r = idx - i * NB;
                     const bool mass = r < S && i < n - 1;
                     ws.zn[(size_t)N + idx] = mass ? B.h * row_residual<NB, ST>(ws, ws.y, i, r) : 0.0;
                 }
                 __syncwarp();
-                pair_sync<PAIR>(ws.bar_id);
             }
         }
         if (!accepted) break;
@@ -679,7 +630,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             double* __restrict__ zn = ws.zn;
             double* __restrict__ ewt = ws.ewt;
             constexpr int NARR = LMAX + 1;                           // zn[0..QMAX] and the weights
-            constexpr int SD = stream_depth<NB, ST, PAIR, NARR>();
+            constexpr int SD = stream_depth<NB, ST, NARR>();
             constexpr bool STREAM = SD >= 3;
             const int nch = (N + vstride - 1) / vstride;
             const unsigned sb = (unsigned)__cvta_generic_to_shared(ws.ring) + 8u * lane;
@@ -750,8 +701,8 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             default: correction(std::integral_constant<int, 0>()); break;
         }
         __syncwarp();
-        ddn = pair_max<PAIR>(ddn, xn, half, lane, ws.bar_id);      // also the pair barrier that ends the correction pass
-        dup = pair_max<PAIR>(dup, xn, half, lane, ws.bar_id);
+        ddn = warp_max(ddn);
+        dup = warp_max(dup);
         if (prof_on) pc[6] += clock64() - tic_corr;
         if (save_acor) B.saved_tq5 = B.tq[5];
 
@@ -802,8 +753,7 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 }
             }
             __syncwarp();
-            pair_sync<PAIR>(ws.bar_id);
-            if (!ST && !last && P.phi_out && go && lane == 0 && half == 0) {
+            if (!ST && !last && P.phi_out && go && lane == 0) {
                 // potential of an intermediate output: forward cumulative sum of the g just written
                 double* po2 = P.phi_out + ((size_t)iout * P.n_cells + cell) * nxm;
                 double v = ws.cs.phi_wall, vm1 = v, vm2 = v;
@@ -837,18 +787,12 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
         for (int it = 0; it < P.polish_max_iter && !done; ++it) {
             // true Newton on the steady residual: inv_gamma = 0 removes the mass term
             bool ok;
-            if constexpr (PAIR) {
-                ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid, xch, half == 0 ? FACTOR_TOP : FACTOR_BOTTOM);
-                ok = pair_max<PAIR>(ok ? 0.0 : 1.0, xn, half, lane, ws.bar_id) == 0.0;
-            } else {
-                ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid, xch, FACTOR_BOTH);
-            }
+            ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid);
             ++nsetups;
             if (!ok) break;
             residual_pass<NB, ST>(ws, 0.0);
-            pair_sync<PAIR>(ws.bar_id);
             double del = 0.0, acn = 0.0;
-            newton_solve<NB, ST, PAIR>(ws, 1.0, mid, half, xn, del, acn, 1, P.polish_rtol, patol, pc, false);
+            newton_solve<NB, ST>(ws, 1.0, mid, del, acn, 1, P.polish_rtol, patol, pc, false);
             ++nni;
             if (!(del <= 1e300)) break;
             // converged, or stagnating at the rounding floor of the linear solve with an update that is
@@ -865,7 +809,6 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
         double* co = P.c_out + ((size_t)io * P.n_cells + cell) * nxm * S;
         double* go = P.g_out ? P.g_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
         double* po = P.phi_out ? P.phi_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
-        pair_sync<PAIR>(ws.bar_id);
         if (P.mode == CATINT_PNP_MODE_STEADY || status != CATINT_PNP_CELL_CONVERGED) {
             for (int idx = vlane; idx < N; idx += vstride) {
                 const int i = idx / NB, r = idx - i * NB;
@@ -876,10 +819,9 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
             }
         }
         __syncwarp();
-        pair_sync<PAIR>(ws.bar_id);
         // potential by the forward cumulative sum of the reference (calculator_old.py:798-800);
         // in Stern mode phi is an unknown of the state and has been written above
-        if (!ST && po && lane == 0 && half == 0) {
+        if (!ST && po && lane == 0) {
             double v = ws.cs.phi_wall;
             po[0] = v;
             double vm1 = v, vm2 = v;
@@ -895,13 +837,13 @@ __global__ void __launch_bounds__(PAIR ? 64 * PAIR_CELLS : 128, PAIR ? 1 : 2) pn
                 po[n - 1] = vm1 + (vm1 - vm2) * ratio;
             }
         }
-        if (P.flux_out && lane < S && half == 0) {
+        if (P.flux_out && lane < S) {
             const WallCoef w = wall_coef(ws.cs);
             const double bq = tb->use_migration ? sp->bq[lane] : 0.0;
             P.flux_out[(size_t)cell * S + lane] =
                 -sp->D[lane] * ((ws.y[2 * NB + lane] - ws.y[lane]) * w.w0 + bq * ws.y[NB + lane] * ws.y[NB + S]);
         }
-        if (lane == 0 && half == 0) {
+        if (lane == 0) {
             P.status[cell] = status;
             P.n_steps[cell] = B.nst;
             P.n_newton[cell] = nni;
@@ -950,6 +892,7 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     ws.scratch = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
     load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, ws.cs, sp);
     const int n = ws.cs.n, nxm = P.tb.nx_max;
+    if (n < 4 || n > nxm) return;                        // bad nx[cell]: skip, outputs untouched
     const double* y = P.y + (size_t)cell * nxm * NB;
     double* sl = ws.scratch + 2 * (NB + 2);
     double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
@@ -1020,37 +963,26 @@ template <int NB, bool ST>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
     const size_t species = ((sizeof(CellSpecies) + 15) & ~size_t(15));
-    const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST, false>();
-    const size_t warpd_pair = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST, true>();
+    const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST>();
     const size_t state = (size_t)2 * P.tb.nx_max * NB;
-    int dev = 0; cudaGetDevice(&dev);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return CATINT_PNP_ECUDA;
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    // (1) warp pair per cell (twisted sweeps), EXPERIMENTAL, only with CATINT_PNP_PAIR=1: correct (same parity
-    //     tests) but measured slower than (2) on the 1024-cell C2 batch (0.91-1.5 s vs 0.65 s per launch): at
-    //     12-14 warps/SM the kernel is limited to 128 registers/thread and spills ~4.8 KB/thread into an L1
-    //     that the 186 KB of shared state leaves almost empty.  Needs a leaner factor sweep first (round 2).
-    const size_t smem_pair = base + PAIR_CELLS * (species + (2 * warpd_pair + state + (size_t)NB * padded<NB, ST>() + 4) * sizeof(double));
-    const char* env = getenv("CATINT_PNP_PAIR");
-    const bool want_pair = (env && env[0] == '1') && P.tb.nx_max >= 12;
-    // (2) one warp per cell, four cells per block, state in shared memory; (3) state in the workspace
+    // one warp per cell, four cells per block; the Newton iterate and the update vector live in shared
+    // memory when they fit (SMEM = true), else in the workspace.  The shared-memory opt-in is a
+    // per-device function attribute: it is set on every launch (cheap, no cached state to race on).
     const size_t smem_single = base + 4 * (species + (warpd + state) * sizeof(double));
-    if (want_pair && smem_pair <= (size_t)max_optin) {
+    const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
+    if (smem_single <= (size_t)max_optin) {
         P.state_in_smem = 1;
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair);
-        const unsigned grid = (unsigned)((P.n_cells + PAIR_CELLS - 1) / PAIR_CELLS);
-        pnp_bdf_kernel<NB, ST, true, true><<<grid, 64 * PAIR_CELLS, smem_pair, st>>>(P);
-    } else if (smem_single <= (size_t)max_optin) {
-        P.state_in_smem = 1;
-        const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single);
-        pnp_bdf_kernel<NB, ST, true, false><<<grid, 128, smem_single, st>>>(P);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single);
+        pnp_bdf_kernel<NB, ST, true><<<grid, 128, smem_single, st>>>(P);
     } else {
         P.state_in_smem = 0;
-        const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
         const size_t smem = base + 4 * (species + warpd * sizeof(double));
-        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pnp_bdf_kernel<NB, ST, false, false><<<grid, 128, smem, st>>>(P);
+        cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        pnp_bdf_kernel<NB, ST, false><<<grid, 128, smem, st>>>(P);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }

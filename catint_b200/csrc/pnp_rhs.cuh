@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(RHS_WARPS * 32) pnp_rhs_kernel(RhsParams P) {
         CellScalars cs;
         load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, cs, sp);
         const int n = cs.n;
+        if (n < 4 || n > nxm) continue;                 // bad nx[cell]: skip (warp-uniform), outputs untouched
         const double* c = P.c + (size_t)cell * nxm * S;
         double* dst = P.dcdt + (size_t)cell * nxm * S;
         const bool mig = tb->use_migration;
@@ -188,21 +189,17 @@ int launch_rhs(RhsParams& P, cudaStream_t st) {
     const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
     const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + rhs_smem_doubles(S, P.tb.nx_max) * sizeof(double);
     const size_t smem = base + RHS_WARPS * per_warp;
-    // launch geometry is cached per (S, shared-memory size): the attribute/occupancy queries are host-side work
-    static size_t cached_smem = 0;
-    static int cached_blocks = 0;
-    if (cached_smem != smem) {
-        int dev = 0, sms = 148, max_optin = 0, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (smem > (size_t)max_optin) return CATINT_PNP_EINVAL;
-        cudaFuncSetAttribute(pnp_rhs_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnp_rhs_kernel<S>, RHS_WARPS * 32, smem);
-        if (per_sm < 1) per_sm = 1;
-        cached_blocks = sms * per_sm;
-        cached_smem = smem;
-    }
+    // per-device launch geometry, queried on every call (a few microseconds; no static state to race on,
+    // correct when one process drives several GPUs)
+    int dev = 0, sms = 148, max_optin = 0, per_sm = 1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return CATINT_PNP_ECUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_optin) return CATINT_PNP_EINVAL;
+    cudaFuncSetAttribute(pnp_rhs_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnp_rhs_kernel<S>, RHS_WARPS * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long long cached_blocks = (long long)sms * per_sm;
     const long long cap = cached_blocks;                      // one resident wave, persistent loop inside
     const long long want = (P.n_cells + RHS_WARPS - 1) / RHS_WARPS;
     const unsigned grid = (unsigned)(want < cap ? want : cap);

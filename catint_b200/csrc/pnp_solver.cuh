@@ -43,15 +43,7 @@ struct WarpState {
     CellScalars cs;
     int N;          // n*NB
     int lane;
-    int vlane, vstride;   // element-wise passes: first index and stride (a warp pair splits them)
-    int bar_id;           // named barrier of the warp pair (PAIR mode)
 };
-
-// barrier of the two warps that share a cell (64 threads, hardware barrier bar_id)
-__device__ __forceinline__ void pair_barrier(int bar_id) {
-    if (bar_id > 0) asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
-    else __syncwarp();          // one warp owns the whole cell: nothing to wait for
-}
 
 template <int NB, bool ST>
 __host__ __device__ constexpr int scratch_doubles() { return 2 * (NB + 2) + 4 * NB + 2; }   // >= 4*padded (sweep buffers)
@@ -64,7 +56,7 @@ __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 template <int NB, bool ST>
 __host__ __device__ constexpr int fac_rec() { return NB * padded<NB, ST>() + NB * 4; }
 // Node records in flight in the solve sweeps: four per chain (three iterations of look-ahead).  One warp
-// per cell walks two chains (8 slots), a warp of a pair one chain (4 slots).
+// per cell walks two chains (8 slots).
 constexpr int RING_CHAIN = 4;
 constexpr int RING = 2 * RING_CHAIN;   // slots of the one-warp-per-cell ring
 
@@ -87,15 +79,31 @@ __device__ __forceinline__ double pivot_rcp(double a) {
     return x;
 }
 
+// IN-PLACE Gauss-Jordan inversion with threshold row pivoting, TWO independent systems per warp: one per
+// half warp (lanes 0..15 / 16..31; hbase = lane & 16, l = lane & 15).  Lane l < NB owns column l of the
+// NB x NB matrix and ends up with column l of its inverse; lanes l >= NB carry right-hand-side columns
+// (-> inverse times that column).  Compared with eliminating [A | I | rhs] this needs NB+1 instead of
+// 2*NB+1 lanes per matrix, which is what lets the two halves of the twisted factorisation run
+// concurrently in one warp (see factor_nodes).
+//
+// ROLLED form: the pivot row always sits in register slot 0 and the rows rotate up by one slot per
+// step (after NB steps the pivot row of step k sits in slot k), so one loop body with static register
+// indices serves all NB steps; the fully unrolled form is ~8x larger and made the factorisation loop
+// overflow the SM's instruction cache.  Slots 0..NB-1-k hold the rows not yet used as
+// pivots.  The pivot column is broadcast from lane k of the half warp by shuffles.  In place: when
+// the row that originally was row p becomes the pivot row of step k, column k of the left part turns
+// into a unit vector and column p of the (implicit) identity on the right stops being one; the latter
+// is stored in the former's place, i.e. lane k finishes with column p_k of the inverse.  `orig` tracks
+// the original row of every slot (4 bits each, uniform per half warp); a final shuffle hands every
+// lane its own column (skipped when no half warp swapped rows, the common case: the algebraic rows are
+// pre-scaled so that the diagonal is an acceptable pivot).  Returns false on a zero/non-finite pivot.
 template <int NB, bool ST>
-__device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* pivbuf) {
-    // ROLLED elimination: the pivot row always sits in register slot 0 and the rows rotate up by one
-    // slot per step (after NB steps every row is back in its place), so one loop body with static
-    // register indices serves all NB steps.  The fully unrolled form is ~8x larger and made the
-    // factorisation loop overflow the SM's instruction cache.  Slots 0..NB-1-k hold the
-    // rows not yet used as pivots.  The pivot column is broadcast from lane k by shuffles.
-    (void)pivbuf;
+__device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int l, int hbase) {
+    static_assert(NB <= 15, "NB+1 columns per half warp");
     bool ok = true;
+    bool swapped = false;
+    unsigned long long orig = 0xFEDCBA9876543210ull;
+    int mysrc = l;
 #pragma unroll 1
     for (int k = 0; k < NB; ++k) {
         // magnitude keys: high word of |a| with the slot index in the low 4 bits
@@ -109,25 +117,37 @@ __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int lane, double* 
         // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
         int p = best & 0xf;
         if (diag + (3 << 20) >= best) p = 0;
-        p = __shfl_sync(FULL, p, k);          // the decision of the lane that owns column k
-        if (p != 0) {                          // warp-uniform: slots 0 and p change places
+        p = __shfl_sync(FULL, p, hbase + k);          // the decision of the lane that owns column k
+        if (p != 0) {                                  // uniform per half warp: slots 0 and p change places
             double a0 = A[0];
 #pragma unroll
             for (int r = 1; r < NB; ++r) {
                 if (r == p) { const double t = A[r]; A[r] = a0; a0 = t; }
             }
             A[0] = a0;
+            const unsigned long long x = ((orig >> (4 * p)) ^ orig) & 0xfull;
+            orig ^= x | (x << (4 * p));
+            swapped = true;
         }
+        const int pk = (int)(orig & 0xfull);           // original row of this step's pivot row
+        if (pk == l) mysrc = k;
+        orig = ((orig >> 4) & ~(0xfull << (4 * (NB - 1)))) | ((unsigned long long)pk << (4 * (NB - 1)));
         double col[NB];
 #pragma unroll
-        for (int r = 0; r < NB; ++r) col[r] = __shfl_sync(FULL, A[r], k);
+        for (int r = 0; r < NB; ++r) col[r] = __shfl_sync(FULL, A[r], hbase + k);
         const double ck = col[0];
         const double inv = pivot_rcp(ck);
         ok = ok && (ck != 0.0) && (fabs(inv) < 1e300);
-        const double a0 = A[0] * inv;
+        const bool own = l == k;                       // the pivot column itself: continue with e_k in its place
+        const double a0 = (own ? 1.0 : A[0]) * inv;
 #pragma unroll
-        for (int r = 1; r < NB; ++r) A[r - 1] = fma(-col[r], a0, A[r]);     // eliminate and rotate
+        for (int r = 1; r < NB; ++r) A[r - 1] = fma(-col[r], a0, own ? 0.0 : A[r]);     // eliminate and rotate
         A[NB - 1] = a0;
+    }
+    if (__any_sync(FULL, swapped)) {
+        const int src = hbase + (l < NB ? mysrc : l);
+#pragma unroll
+        for (int r = 0; r < NB; ++r) A[r] = __shfl_sync(FULL, A[r], src);
     }
     return ok;
 }
@@ -325,200 +345,186 @@ struct RecordFeed {
 };
 
 // ---------------------------------------------------------------------------
-// Twisted block factorisation of the Newton matrix.  Lanes: D = 0..NB-1 (columns of A_D'),
-// I = NB..2NB-1 (identity -> inverse), G = 2NB (g-column of the coupling block -> W[:,g]).
+// Twisted block factorisation of the Newton matrix, BOTH halves at once: the lower half warp
+// (lanes 0..15) eliminates the nodes 0..mid downwards, the upper half warp (lanes 16..31) the nodes
+// n-1..mid+1 upwards, in the same instruction stream.  Inside a half warp (l = lane & 15):
+// lanes l < NB own column l of A_D' (-> column l of inv_i, in-place Gauss-Jordan), lane NB carries the
+// g column u_g of the coupling block (-> W[:,g] = inv_i*u_g).
 //
-//   bottom half (FACTOR_BOTTOM): nodes n-1 down to mid+1 are eliminated upwards,
-//       A_D'_i = A_D,i - A_U,i * W^b_{i+1},   W^b_i = inv_i * A_L,i,   A_L = -(diag l + a e_g^T);
-//       W^b_{mid+1} is published in xch for the coupling node.
-//   top half (FACTOR_TOP): nodes 0..mid downwards,  A_D'_i = A_D,i - A_L,i * W_{i-1},  W_i = inv_i*A_U,i;
-//       node 0 carries the extra wall block A_E (V_0 = inv_0*A_E), which makes A_U of node 1 dense
-//       (second elimination, W_1 stored); the coupling node `mid` also subtracts A_U * W^b_{mid+1}.
+//   top    (nodes 0..mid):    A_D'_i = A_D,i - A_L,i * W_{i-1},   W_i = inv_i*A_U,i,  A_U = -(diag ud + ua e_g^T)
+//       node 0 carries the extra wall block A_E (V_0 = inv_0*A_E), which makes A_U of node 1 dense:
+//       W_1 = inv_1*(A_U,1 - A_L,1*V_0) is formed as an explicit product (inv_1 read back from the
+//       node record) and stored; the coupling node `mid` also subtracts A_U * W^b_{mid+1}, which it
+//       receives from the other half warp by shuffles.
+//   bottom (nodes n-1..mid+1): A_D'_i = A_D,i - A_U,i * W^b_{i+1},  W^b_i = inv_i*A_L,i, A_L = -(diag l + a e_g^T)
 //
-// Stores inv_i and the sparse coefficients of A_L/A_U per node, V_0 and W_1.  One warp runs both halves
-// one after the other (parts = FACTOR_BOTH); a warp pair runs one half each and meets at the named
-// barrier.  Every node of either half passes through the SAME elimination code: the routine is
-// deliberately not inlined and has a single gauss_jordan instance, because the unrolled elimination
-// is the bulk of the kernel's instruction footprint (instruction cache).
-constexpr int FACTOR_TOP = 1, FACTOR_BOTTOM = 2, FACTOR_BOTH = 3;
-
-// Elimination of one node of the factorisation sweep (see factor_nodes).  SPECIAL = false is the
-// compact body of the interior nodes; the wall node, node 1 (two passes), the bulk node and the
-// coupling node take the SPECIAL = true instance, which keeps their rarely executed code out of the
-// hot loop's instruction footprint.
-struct FactorLane { bool isD, isI, isG; int j, wsrc_top, wsrc_bot; };
-
+// Because A_L and A_U are diagonal plus the g column, column j of W is the scaled column j of inv_i
+// (already in lane j) or the result of the g lane: the Schur update of the next node needs no data
+// from other lanes except that one column.  Stores inv_i and the sparse coefficients of A_L/A_U per
+// node, V_0 and W_1.  Every interior node of either half passes through the SAME compact elimination
+// code; the wall/bulk pair, node 1 and the coupling node take the SPECIAL instance, which keeps their
+// rarely executed code out of the hot loop's instruction footprint (instruction cache).
 template <int NB, bool ST, bool SPECIAL>
-__device__ __forceinline__ bool eliminate_node(const WarpState<NB, ST>& ws, const FactorLane fl, double (&Wp)[NB],
-                                               int i, int pass, bool bottom, int mid, int slot, double inv_gamma,
-                                               double* xch) {
+__device__ __forceinline__ bool eliminate_pair(const WarpState<NB, ST>& ws, double (&Wp)[NB],
+                                               int k, int iters, int i, bool live, int slot, double inv_gamma) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
     constexpr int REC = fac_rec<NB, ST>();
     const int lane = ws.lane;
     const int n = ws.cs.n;
-    const bool isD = fl.isD, isI = fl.isI, isG = fl.isG;
-    const int j = fl.j, wsrc_top = fl.wsrc_top, wsrc_bot = fl.wsrc_bot;
+    const int l = lane & 15, hbase = lane & 16;
+    const bool bottom = hbase != 0;
+    const bool isD = l < NB, isG = l == NB;
+    const int j = isD ? l : 0;
+    const bool wall = SPECIAL && !bottom && k == 0;
+    const bool bulk = SPECIAL && bottom && k == 0;
+    const bool node1 = SPECIAL && !bottom && k == 1;
+    const bool couple = SPECIAL && k == iters - 1;                  // warp-uniform; concerns the top half
     double A[NB];
-    {
-        const bool bulk = SPECIAL && (i == n - 1);
-        const bool wall = SPECIAL && (i == 0);
-        const bool couple = SPECIAL && !bottom && (i == mid);
-        const bool node1 = SPECIAL && (i == 1);
-        if (!SPECIAL) pass = 0;
-        double* rec = ws.fac + (size_t)i * REC;
-        double* invcol = rec + j;                                   // column j of inv_i (I lanes)
-        NodeCoef k = NodeCoef{0, 0, 0, 1, 1};
-        if (bulk) k = interior_coef(ws.cs, i - 1);
-        // the node's record in the ring: raw A_D and the coefficient rows (ud of the g row is scaled)
-        const double* rr_ = ws.ring + (size_t)slot * REC;
-        const double* cof = rr_ + NB * NBP;
+    // the node's record in the ring: raw A_D and the coefficient rows (ud of the g row is scaled)
+    const double* rr_ = ws.ring + (size_t)slot * REC;
+    const double* cof = rr_ + NB * NBP;
 #define C_L(r_) cof[4 * (r_)]
 #define C_A(r_) cof[4 * (r_) + 1]
 #define C_UD(r_) cof[4 * (r_) + 2]
 #define C_UA(r_) cof[4 * (r_) + 3]
-        if (couple) pair_barrier(ws.bar_id);   // the bottom half has published W^b_{mid+1}
+    double Wb[NB];
+    if (SPECIAL && couple) {
+        // W^b_{mid+1} column j from the lane that owns it in the other half warp
 #pragma unroll
-        for (int r = 0; r < NB; ++r) A[r] = 0.0;
+        for (int r = 0; r < NB; ++r) Wb[r] = __shfl_sync(FULL, Wp[r], (lane + 16) & 31);
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) A[r] = 0.0;
 
-        // ---- column j of [A_D' | I | u_g] ----
-        if (wall) {
-            // A_D0 is diag(mass*inv_gamma - a); A_U0 = diag(-ud) + g-column(-ua); A_E = diag(-l)
-            if (isD || isI) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r)
-                    if (r == j) A[r] = isD ? ((j < S ? inv_gamma : 0.0) - C_A(r)) : 1.0;
-                if (ST && isD && j == S) A[NB - 1] = ws.cs.eps / ws.cs.cstern;      // -dF_phi/dg_0 (Robin row)
-            } else if (isG) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
-            }
-        } else if (pass == 1) {
-            // node 1, second elimination: A_U1' = A_U1 - A_L1*V_0 (dense in general)
-            if (isD) {
-                const double* d1 = ws.W1 + j;        // A_D1' parked there by pass 0
-#pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = d1[r * NBP];
-            } else if (isI) {
-                const double vg = Wp[S];
-#pragma unroll
-                for (int r = 0; r < NB; ++r) {
-                    double v = 0.0;
-                    if (r == j) v = -C_UD(r);
-                    if (j == S && r < S) v = -C_UA(r);
-                    if (r < S) v += C_L(r) * Wp[r] + C_A(r) * vg;
-                    if (ST && r == NB - 1) v += C_L(r) * Wp[r];
-                    A[r] = v;
-                }
-            }
-        } else if (isD) {
-            if (!bulk) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = rr_[r * NBP + j];
-                const double wg = Wp[S];
-                if (bottom) {
-                    // - A_U * W^b_{i+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
-#pragma unroll
-                    for (int r = 0; r < S; ++r) A[r] += C_UD(r) * Wp[r] + C_UA(r) * wg;
-                    A[S] += C_UD(S) * wg;
-                } else {
-                    // - A_L * W_{i-1}:  A_L = -(diag l + a e_g^T)
-#pragma unroll
-                    for (int r = 0; r < S; ++r) A[r] += C_L(r) * Wp[r] + C_A(r) * wg;
-                    if (ST) A[NB - 1] += C_L(NB - 1) * Wp[NB - 1];                  // phi row: A_L = -1 on the diagonal
-                    if (couple) {
-                        const double* xc = xch + j;
-                        const double xg = xc[S * NBP];
-#pragma unroll
-                        for (int r = 0; r < S; ++r) A[r] += C_UD(r) * xc[r * NBP] + C_UA(r) * xg;
-                        A[S] += C_UD(S) * xg;
-                    }
-                }
-            } else {
-                // bulk node: c rows identity; default Poisson BCs: g row identity;
-                // Stern: row S: phi_{n-1} = 0; row P: phi recursion with h_{n-2}
-#pragma unroll
-                for (int r = 0; r < S; ++r)
-                    if (r == j) A[r] = 1.0;
-                if (!ST) {
-                    if (j == S) A[S] = 1.0;
-                } else {
-                    if (j == S) A[NB - 1] = -k.hi;
-                    if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
-                }
-            }
-            if (node1) {
-                // park A_D1' for the second elimination (W1 is rewritten at the end of pass 1)
-                double* d1 = ws.W1 + j;
-#pragma unroll
-                for (int r = 0; r < NB; ++r) d1[r * NBP] = A[r];
-            }
-        } else if (isI) {
+    // ---- column of [A_D' | u_g] ----
+    if (wall) {
+        // A_D0 is diag(mass*inv_gamma - a); A_U0 = diag(-ud) + g-column(-ua); A_E = diag(-l)
+        if (isD) {
 #pragma unroll
             for (int r = 0; r < NB; ++r)
-                if (r == j) A[r] = 1.0;
+                if (r == j) A[r] = (j < S ? inv_gamma : 0.0) - C_A(r);
+            if (ST && j == S) A[NB - 1] = ws.cs.eps / ws.cs.cstern;             // -dF_phi/dg_0 (Robin row)
         } else if (isG) {
-            if (bottom) {
-                // g-column of A_L: -a_r on the transport rows
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_A(r) : 0.0;
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
+        }
+    } else if (bulk) {
+        // bulk node: c rows identity; default Poisson BCs: g row identity;
+        // Stern: row S: phi_{n-1} = 0; row P: phi recursion with h_{n-2}
+        if (isD) {
+#pragma unroll
+            for (int r = 0; r < S; ++r)
+                if (r == j) A[r] = 1.0;
+            if (!ST) {
+                if (j == S) A[S] = 1.0;
             } else {
+                const NodeCoef kc = interior_coef(ws.cs, n - 2);
+                if (j == S) A[NB - 1] = -kc.hi;
+                if (j == NB - 1) { A[S] = 1.0; A[NB - 1] = 1.0; }
+            }
+        } else if (isG) {
 #pragma unroll
-                for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_A(r) : 0.0;
+        }
+    } else if (isD) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) A[r] = rr_[r * NBP + j];
+        const double wg = Wp[S];
+        if (bottom) {
+            // - A_U * W^b_{i+1}:  A_U = -(diag ud + ua e_g^T), g row: -ud*sg
+#pragma unroll
+            for (int r = 0; r < S; ++r) A[r] += C_UD(r) * Wp[r] + C_UA(r) * wg;
+            A[S] += C_UD(S) * wg;
+        } else {
+            // - A_L * W_{i-1}:  A_L = -(diag l + a e_g^T)
+#pragma unroll
+            for (int r = 0; r < S; ++r) A[r] += C_L(r) * Wp[r] + C_A(r) * wg;
+            if (ST) A[NB - 1] += C_L(NB - 1) * Wp[NB - 1];                      // phi row: A_L = -1 on the diagonal
+            if (SPECIAL && couple) {
+                const double xg = Wb[S];
+#pragma unroll
+                for (int r = 0; r < S; ++r) A[r] += C_UD(r) * Wb[r] + C_UA(r) * xg;
+                A[S] += C_UD(S) * xg;
             }
         }
-        // scales of this lane's inverse column, read before the ring slot may be refilled
-        const int jc = (isD || isI) ? j : 0;
-        const double c_l = C_L(jc), c_ud = C_UD(jc);
+    } else if (isG) {
+        if (bottom) {
+            // g-column of A_L: -a_r on the transport rows
+#pragma unroll
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_A(r) : 0.0;
+        } else {
+#pragma unroll
+            for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
+        }
+    }
+    // scale of this lane's column of the coupling block, read before the ring slot may be refilled:
+    // top A_U = diag(-ud) on the c columns (no phi column), bottom A_L = diag(-l) on the c and phi columns;
+    // the g column comes from the G lane
+    const double c_l = C_L(j), c_ud = C_UD(j);
+    double cj = bottom ? -c_l : (j < S ? -c_ud : 0.0);
+    if (j == S) cj = 1.0;
+    // node 1: column j of A_U1' = A_U1 - A_L1*V_0 (dense in general)
+    double U1[NB];
+    if (SPECIAL && node1) {
+        // column j of V_0, written by the wall iteration (a warp barrier ago)
+        double V0p[NB];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) V0p[r] = __ldcg(ws.V0 + r * NBP + j);
+        const double vg = V0p[S];
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            double v = 0.0;
+            if (r == j) v = -C_UD(r);
+            if (j == S && r < S) v = -C_UA(r);
+            if (r < S) v += C_L(r) * V0p[r] + C_A(r) * vg;
+            if (ST && r == NB - 1) v += C_L(r) * V0p[r];
+            U1[r] = v;
+        }
+    }
 #undef C_L
 #undef C_A
 #undef C_UD
 #undef C_UA
 
-        bool ok = gauss_jordan<NB, ST>(A, lane, ws.scratch);
+    const bool ok = gauss_jordan<NB, ST>(A, l, hbase);
 
-        // ---- store the inverse, form the W columns for the next node ----
-        int src = bottom ? wsrc_bot : wsrc_top;
-        if (pass == 1) {
-            if (isI) {
-                double* w1col = ws.W1 + j;
+    // ---- store the inverse, form the W column for the next node ----
+    double* rec = ws.fac + (size_t)i * REC;
+    if (isD && live) {
+        double* invcol = rec + j;
 #pragma unroll
-                for (int r = 0; r < NB; ++r) w1col[r * NBP] = A[r];
-            }
-            src = isD ? lane + NB : lane;
-        } else if (isI) {
-            // scale of column j of the coupling block: top A_U = diag(-ud) (c columns), bottom
-            // A_L = diag(-l) (c and phi columns); the g column comes from the G lane
-            const bool scaled = bottom ? (j != S) : (j < S);
-            const double cj = bottom ? -c_l : -c_ud;
-            const double ae = -c_l;
-            double* v0col = ws.V0 + j;
+        for (int r = 0; r < NB; ++r) invcol[r * NBP] = A[r];
+    }
+    if (SPECIAL && wall && isD) {
+        // V_0 = inv_0*A_E, A_E = diag(-l): needed for the modified A_U of node 1 and by the back substitution
+        double* v0col = ws.V0 + j;
+#pragma unroll
+        for (int r = 0; r < NB; ++r) v0col[r * NBP] = A[r] * (-c_l);
+    }
+    const int src = (isD && j == S) ? hbase + NB : lane;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+        const double t = __shfl_sync(FULL, A[r], src);
+        if (live) Wp[r] = t * cj;
+    }
+    if (SPECIAL && k == 1) {
+        // W_1 = inv_1 * A_U1' as an explicit product; inv_1 comes back from the node record (L2)
+        __syncwarp();
+        if (node1 && isD) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) {
-                invcol[r * NBP] = A[r];
-                if (wall) v0col[r * NBP] = A[r] * ae;
-                if (scaled) A[r] *= cj;
+                double s_ = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) s_ = fma(__ldcg(rec + r * NBP + c), U1[c], s_);
+                Wp[r] = s_;
             }
-        }
-        // (between the two eliminations of node 1 the I lanes still need their V_0 columns)
-        if (!(node1 && pass == 0 && !bottom)) {
+            double* w1col = ws.W1 + j;
 #pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = __shfl_sync(FULL, A[r], src);
+            for (int r = 0; r < NB; ++r) w1col[r * NBP] = Wp[r];
         }
-        if (ST && !bottom && pass == 0 && isD && j == NB - 1) {
-            // A_U has no phi column: W[:,phi] = 0
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
-        }
-        if (wall && isI) {
-            // the I lanes keep V_0 columns for the modified A_U of node 1
-            const double* v0col = ws.V0 + j;
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = v0col[r * NBP];
-        }
-
-        return ok;
     }
+    return ok || !live;
 }
 
 // The warp state is passed BY VALUE: handing out a reference would force the caller's copy into
@@ -530,14 +536,14 @@ __device__ __forceinline__ bool eliminate_node(const WarpState<NB, ST>& ws, cons
 // lane assembles one column of A_D and one row of coefficients of a different (node, unknown) pair
 // at a time, with the whole warp busy, straight into the node records in global memory.
 // ELIMINATION: the sequential sweep then only streams the records back through the cp.async ring
-// (three nodes ahead), applies the Schur update and eliminates.  Doing the assembly inside the
-// sequential sweep (one node at a time, 9 of 32 lanes busy, every load latency exposed) cost more
-// than the elimination itself.
+// (three nodes ahead, both chains), applies the Schur update and eliminates.  Doing the assembly
+// inside the sequential sweep (one node at a time, every load latency exposed) cost more than the
+// elimination itself.
 struct SmemOffsets { unsigned scratch, sp, y, ring; };
 
 template <int NB, bool ST, bool SMEM>
 __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
-                                          int mid, double* xch, int parts) {
+                                          int mid) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
     constexpr int REC = fac_rec<NB, ST>();
@@ -551,12 +557,10 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
     const int lane = ws.lane;
     const int n = ws.cs.n;
     const bool mig = ws.tb->use_migration;
-    const bool isD = lane < NB, isI = lane >= NB && lane < 2 * NB, isG = lane == 2 * NB;
-    const int j = isD ? lane : lane - NB;
     const double* y = ws.y;
 
     // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
-    for (int item = ws.vlane; item < n * NB; item += ws.vstride) {
+    for (int item = lane; item < n * NB; item += 32) {
         const int i = item / NB, r = item - i * NB;
         double* rec = ws.fac + (size_t)i * REC;
         double4 co = node_coeff_row<NB, ST>(ws, y, i, r);
@@ -572,63 +576,32 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
         reinterpret_cast<double4*>(rec + NB * NBP)[r] = co;
     }
     __syncwarp();
-    if (parts != FACTOR_BOTH) pair_barrier(ws.bar_id);               // the pair shares the assembly
 
-    // source lane of the W column that D-lane j needs for the next Schur update: the scaled inverse
-    // column where the coupling block has a diagonal entry in column j, the G lane for the g column
-    FactorLane fl;
-    fl.isD = isD; fl.isI = isI; fl.isG = isG; fl.j = j;
-    fl.wsrc_top = isD ? (j < S ? lane + NB : 2 * NB) : lane;
-    fl.wsrc_bot = isD ? (j != S ? lane + NB : 2 * NB) : lane;
+    // ---- elimination: top chain 0..mid in the lower half warp, bottom chain n-1..mid+1 in the upper ----
+    const int grp = lane >> 4;
+    const int iters = mid + 1;                   // nodes of the top chain (>= those of the bottom chain)
+    const int nbot = n - 1 - mid;
     double Wp[NB];
 #pragma unroll
     for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
     bool ok = true;
-
-    bool bottom = (parts & FACTOR_BOTTOM) != 0;
-    int i = bottom ? n - 1 : 0;
-    int pass = 0;            // node 1 is eliminated twice (pass 1: [A_D1' | A_U1'] -> dense W_1)
-    const Chain none = {0, 0, 1};
     RecordFeed<NB, ST> feed;
-    int kk = 0;              // position in the current chain
-    feed.init(ws.fac, ws.ring, lane, bottom ? Chain{n - 1, n - 1 - mid, -1} : Chain{0, mid + 1, +1}, none);
+    feed.init(ws.fac, ws.ring, lane, Chain{0, iters, +1}, Chain{n - 1, nbot, -1});
 #pragma unroll 1
     for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
 #pragma unroll 1
-    for (;;) {
-        if (bottom && i <= mid) {
-            // bottom half done: publish W^b_{mid+1}
-            if (isD) {
-#pragma unroll
-                for (int r = 0; r < NB; ++r) xch[r * NBP + j] = Wp[r];
-            }
-            if (!(parts & FACTOR_TOP)) { pair_barrier(ws.bar_id); break; }
-            bottom = false; i = 0;
-#pragma unroll
-            for (int r = 0; r < NB; ++r) Wp[r] = 0.0;
-            cp_wait<0>();
-            __syncwarp();
-            kk = 0;
-            feed.init(ws.fac, ws.ring, lane, Chain{0, mid + 1, +1}, none);
-#pragma unroll 1
-            for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
-        }
-        if (!bottom && i > mid) break;
-
-        const bool special = (i <= 1) || (i == n - 1) || (!bottom && i == mid);
-        if (pass == 0) { cp_wait<RING_CHAIN - 2>(); __syncwarp(); }
-        const int slot = kk & (RING_CHAIN - 1);
-        if (special) ok = eliminate_node<NB, ST, true>(ws, fl, Wp, i, pass, bottom, mid, slot, inv_gamma, xch) && ok;
-        else ok = eliminate_node<NB, ST, false>(ws, fl, Wp, i, pass, bottom, mid, slot, inv_gamma, xch) && ok;
-
-        // ---- next task ----
-        if (!bottom && i == 1 && pass == 0) { pass = 1; continue; }
-        pass = 0;
-        i += bottom ? -1 : 1;
-        __syncwarp();                           // every lane is done with this node's ring slot
-        feed.issue(kk + RING_CHAIN - 1);
+    for (int k = 0; k < iters; ++k) {
+        cp_wait<RING_CHAIN - 2>();
+        __syncwarp();
+        const int slot = (2 * k + grp) & (RING - 1);
+        const int i = grp ? n - 1 - k : k;
+        const bool live = grp ? k < nbot : true;
+        const bool special = (k <= 1) || (k == iters - 1);
+        if (special) ok = eliminate_pair<NB, ST, true>(ws, Wp, k, iters, i, live, slot, inv_gamma) && ok;
+        else ok = eliminate_pair<NB, ST, false>(ws, Wp, k, iters, i, live, slot, inv_gamma) && ok;
+        __syncwarp();                           // every lane is done with this iteration's ring slots
+        feed.issue(k + RING_CHAIN - 1);
         cp_commit();
-        ++kk;
     }
     cp_wait<0>();
     __syncwarp();
@@ -644,7 +617,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     const int n = ws.cs.n;
     const DevTables& tb = *ws.tb;
     const double* y = ws.y;
-    for (int i = ws.vlane; i < n; i += ws.vstride) {
+    for (int i = ws.lane; i < n; i += 32) {
         const double* y0 = y + (size_t)i * NB;
         double* out = ws.zb + (size_t)i * NB;
         // mass term of the BDF corrector: psi streams from global memory, loaded first so that its
@@ -705,10 +678,8 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
 // into a shared-memory ring by cp.async, RING-1 nodes ahead of use, so that the sequential
 // chain over the nodes never waits for DRAM.  Lane r (< NB) owns row r.
 //
-// All sweeps take a node range and a direction so that the same code serves the one-warp
-// elimination (top-down over all nodes) and the twisted elimination of a warp pair: the "top"
-// warp eliminates nodes 0..m-1 downwards, the "bottom" warp nodes n-1..m+1 upwards, node m
-// couples the two halves (see pnp_kernels.cuh, PAIR).
+// All sweeps take node ranges and directions (Chain): with the twisted factors the lower half warp
+// walks nodes 0..m-1 downwards and the upper half warp nodes n-1..m+1 upwards, node m couples them.
 template <int NB, bool ST>
 struct FactorRow {
     double v[NB];

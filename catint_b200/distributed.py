@@ -5,78 +5,159 @@ grid with a static round-robin map ``itask % mpi_size == mpi_rank``
 (/root/reference/catint/calculator.py:209-212) and a gather of the result
 dictionaries (/root/reference/catint/catint_io.py:154-178; disabled upstream).
 Here: one process per GPU, cell j -> rank j % world_size, no traffic while the
-cells integrate, ONE final all_gather of the result arrays (NCCL over
-NVLink/NVSwitch on a B200 box; gloo in the CPU tests of the host logic).
+cells integrate, and ONE collective at the end: every rank packs its results
+(concentrations, potential, gradient, wall fluxes, status and counters) into one
+device buffer [cells_per_rank, width], a single ``all_gather_into_tensor`` over
+NCCL (NVLink/NVSwitch) assembles them on every GPU, and one device->host copy
+brings them to the host, where the round-robin order is undone.  (gloo with CPU
+tensors in the tests of the host logic: same code path.)
 """
+import os
+
 import numpy as np
 
-# result arrays and the axis that indexes cells
+# result arrays and the axis that indexes cells; packed in this order
 _CELL_AXIS = {'c': 1, 'phi': 1, 'g': 1, 'flux': 0, 'status': 0, 'n_steps': 0, 'n_newton': 0, 'n_setups': 0}
+_INT_FIELDS = ('status', 'n_steps', 'n_newton', 'n_setups')
 
 
 def world():
+    """(rank, world_size) of the initialised process group, else of the launcher's environment
+    (torchrun sets RANK / WORLD_SIZE before init_process_group), else (0, 1)."""
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(), dist.get_world_size()
     except ImportError:
         pass
-    return 0, 1
+    try:
+        return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    except ValueError:
+        return 0, 1
+
+
+def group_ready():
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized()
+    except ImportError:
+        return False
 
 
 def shard_indices(n_cells, rank, world_size):
     return np.arange(rank, n_cells, world_size)
 
 
-def gather_results(local, n_cells, rank, world_size, device=None):
-    """all_gather the per-rank result dicts (numpy) and restore the original
-    cell order.  Shards are padded to the same length for the collective."""
+def result_shapes(n_out, nx_max, S):
+    """per-cell shapes of the result arrays (cell axis removed), in packing order"""
+    return {'c': (n_out, nx_max, S), 'phi': (n_out, nx_max), 'g': (n_out, nx_max), 'flux': (S,),
+            'status': (), 'n_steps': (), 'n_newton': (), 'n_setups': ()}
+
+
+def empty_results(n_out, nx_max, S):
+    """result dict of a rank whose shard is empty (fewer cells than ranks)"""
+    out = {}
+    for name, shp in result_shapes(n_out, nx_max, S).items():
+        axis = _CELL_AXIS[name]
+        full = list(shp)
+        full.insert(axis, 0)
+        out[name] = np.zeros(full, dtype=np.int32 if name in _INT_FIELDS else np.float64)
+    return out
+
+
+def pack_results(local, per, n_out, nx_max, S, device=None):
+    """result dict (torch tensors on any device, or numpy arrays) -> one float64 tensor [per, width],
+    cell-major, rows beyond the shard's length zero.  int32 fields are exact in float64."""
+    import torch
+    cols = []
+    n_loc = None
+    for name, shp in result_shapes(n_out, nx_max, S).items():
+        a = local[name]
+        t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        if device is not None:
+            t = t.to(device)
+        t = t.movedim(_CELL_AXIS[name], 0).to(torch.float64)
+        n_loc = t.shape[0]
+        cols.append(t.reshape(n_loc, int(np.prod(shp)) if shp else 1))
+    packed = torch.cat(cols, dim=1)
+    if n_loc < per:
+        pad = torch.zeros((per - n_loc, packed.shape[1]), dtype=torch.float64, device=packed.device)
+        packed = torch.cat([packed, pad], dim=0)
+    return packed.contiguous()
+
+
+def unpack_results(gathered, n_cells, world_size, n_out, nx_max, S):
+    """host array [world_size*per, width] -> ordered result dict (numpy), undoing cell j -> rank j % N"""
+    per = gathered.shape[0] // world_size
+    g = gathered.reshape(world_size, per, -1)
+    order = np.zeros((n_cells, g.shape[2]))
+    for r in range(world_size):
+        idx = shard_indices(n_cells, r, world_size)
+        order[idx] = g[r, :len(idx)]
+    full = {}
+    off = 0
+    for name, shp in result_shapes(n_out, nx_max, S).items():
+        w = int(np.prod(shp)) if shp else 1
+        a = order[:, off:off + w].reshape((n_cells,) + shp)
+        off += w
+        if name in _INT_FIELDS:
+            a = np.rint(a).astype(np.int32)
+        full[name] = np.ascontiguousarray(np.moveaxis(a, 0, _CELL_AXIS[name]))
+    return full
+
+
+def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
+    """ONE all_gather of the packed per-rank results, then one copy to the host."""
     import torch
     import torch.distributed as dist
     per = (n_cells + world_size - 1) // world_size
     backend = dist.get_backend()
-    dev = torch.device(device if (backend == 'nccl' and device is not None) else
-                       ('cuda' if backend == 'nccl' else 'cpu'))
-    full = {}
-    for name, axis in _CELL_AXIS.items():
-        a = np.asarray(local[name])
-        a = np.moveaxis(a, axis, 0)
-        pad = np.zeros((per,) + a.shape[1:], dtype=a.dtype)
-        pad[:a.shape[0]] = a
-        t = torch.from_numpy(np.ascontiguousarray(pad)).to(dev)
-        out = torch.empty((world_size * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(out, t)
-        out = out.cpu().numpy().reshape((world_size, per) + tuple(t.shape[1:]))
-        merged = np.zeros((n_cells,) + a.shape[1:], dtype=a.dtype)
-        for r in range(world_size):
-            idx = shard_indices(n_cells, r, world_size)
-            merged[idx] = out[r, :len(idx)]
-        full[name] = np.moveaxis(merged, 0, axis)
-    return full
-
-
-def solve_sharded(calc, batch, solve_fn=None):
-    """Solve ``batch`` with the cells split over all ranks; every rank returns
-    the complete, ordered result dict.  ``solve_fn(sub_batch) -> dict`` defaults
-    to the CUDA path ``calc.solve_batch`` (tests of the host logic inject their
-    own function; there is no CPU solver in the product)."""
-    rank, ws = world()
-    if solve_fn is None:
-        solve_fn = calc.solve_batch
-    if ws == 1:
-        return solve_fn(batch)
-    idx = shard_indices(batch.B, rank, ws)
-    sub = batch.select(idx)
-    local = solve_fn(sub)
     dev = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            dev = 'cuda:%d' % torch.cuda.current_device()
-    except ImportError:
-        pass
-    full = gather_results(local, batch.B, rank, ws, device=dev)
-    for k in local:
-        if k not in full:
-            full[k] = local[k]
+    if backend == 'nccl':
+        dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    packed = pack_results(local, per, n_out, nx_max, S, device=dev)
+    out = torch.empty((world_size * per, packed.shape[1]), dtype=torch.float64, device=packed.device)
+    dist.all_gather_into_tensor(out, packed)
+    host = out.cpu().numpy()
+    full = unpack_results(host, n_cells, world_size, n_out, nx_max, S)
+    full['gather_bytes'] = int(out.numel() * 8)
     return full
+
+
+def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None):
+    """Solve ``batch`` with the cells split over all ranks; every rank returns
+    the complete, ordered result dict (numpy).  ``solve_fn(sub_batch) -> dict`` of
+    torch tensors (device) or numpy arrays defaults to the CUDA path
+    ``calc.solve_batch_device`` (tests of the host logic inject their own
+    function; there is no CPU solver in the product).  A rank whose shard is
+    empty (fewer cells than ranks) skips the solve and still joins the gather,
+    like the reference's ``itask % size != rank: continue``."""
+    rank, ws = world()
+    if ws > 1 and not group_ready():
+        raise RuntimeError('catint_b200: WORLD_SIZE=%d but torch.distributed is not initialised; call '
+                           'torch.distributed.init_process_group first (one process per GPU)' % ws)
+    if ws == 1:
+        if solve_fn is None:
+            return calc.solve_batch(batch)
+        return _to_host(solve_fn(batch))
+    if solve_fn is None:
+        solve_fn = calc.solve_batch_device
+    if n_out is None:
+        n_out = len(calc.output_times())
+    idx = shard_indices(batch.B, rank, ws)
+    extra = {}
+    if len(idx) == 0:
+        local = empty_results(n_out, batch.nx_max, batch.S)
+    else:
+        local = solve_fn(batch.select(idx))
+        extra = {k: v for k, v in local.items() if k not in _CELL_AXIS}
+    full = gather_results(local, batch.B, ws, n_out, batch.nx_max, batch.S, device=device)
+    full.update(extra)
+    return full
+
+
+def _to_host(res):
+    out = {}
+    for k, v in res.items():
+        out[k] = v.cpu().numpy() if hasattr(v, 'cpu') else v
+    return out

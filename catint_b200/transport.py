@@ -652,8 +652,9 @@ class Transport(object):
         if catint_path is None:
             catint_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         self.catint_path = catint_path
-        self.mpi_rank = 0
-        self.mpi_size = 1
+        # one process per GPU under torch.distributed (the reference's mpi_rank/mpi_size, transport.py:27-36,54-66)
+        from . import distributed as _dist
+        self.mpi_rank, self.mpi_size = _dist.world()
 
         self.model_name = 'catint' if model_name is None else model_name
         self._make_results_folder(resultsdir)
@@ -684,6 +685,8 @@ class Transport(object):
         self.system['potential'] = np.zeros([self.nx])
         self.system['charge_density'] = np.zeros([self.nx])
 
+        if 'RF' not in self.system:
+            self.system['RF'] = 1.0                   # roughness factor default (transport.py:844-851)
         self.initialize_descriptors(descriptors)
         self.catmap_args = catmap_args
         self.comsol_args = self._comsol_defaults(comsol_args)
@@ -691,22 +694,36 @@ class Transport(object):
 
     # ------------------------------------------------------------------
     def _make_results_folder(self, resultsdir):
-        """<resultsdir>/<model_name>_results[_NNNN] (transport.py:70-106)."""
+        """<resultsdir>/<model_name>_results[_NNNN] (transport.py:70-106).  With several ranks the folder is
+        created by rank 0 only and its name is broadcast (reference: transport.py:54-110 creates it on rank 0,
+        broadcasts and barriers); before the process group exists the other ranks get a private
+        <model_name>_results.rankNNN folder for their log file, so nothing races."""
         root = os.getcwd()
         if resultsdir is None:
             resultsdir = root
-        if not os.path.exists(resultsdir):
-            os.makedirs(resultsdir)
-        self.outputfoldername = resultsdir + '/' + self.model_name + '_results'
+        os.makedirs(resultsdir, exist_ok=True)
         self.inputfilename = sys.argv[0] if len(sys.argv) else ''
-        if not os.path.exists(self.outputfoldername):
-            os.makedirs(self.outputfoldername)
-        else:
-            pat = re.compile(self.model_name + '_results_[0-9]+')
-            numbered = sorted(f for f in os.listdir(resultsdir) if pat.search(f))
-            number = int(numbered[-1].split('_')[-1]) + 1 if numbered else 2
-            self.outputfoldername = self.outputfoldername + '_' + str(number).zfill(4)
-            os.makedirs(self.outputfoldername)
+        from . import distributed as _dist
+        shared = self.mpi_size > 1 and _dist.group_ready()
+        if self.mpi_rank == 0:
+            self.outputfoldername = resultsdir + '/' + self.model_name + '_results'
+            if not os.path.exists(self.outputfoldername):
+                os.makedirs(self.outputfoldername)
+            else:
+                pat = re.compile(self.model_name + '_results_[0-9]+')
+                numbered = sorted(f for f in os.listdir(resultsdir) if pat.search(f))
+                number = int(numbered[-1].split('_')[-1]) + 1 if numbered else 2
+                self.outputfoldername = self.outputfoldername + '_' + str(number).zfill(4)
+                os.makedirs(self.outputfoldername)
+        elif not shared:
+            self.outputfoldername = resultsdir + '/' + self.model_name + '_results.rank' + str(self.mpi_rank).zfill(3)
+            os.makedirs(self.outputfoldername, exist_ok=True)
+        if shared:
+            import torch.distributed as dist
+            name = [self.outputfoldername if self.mpi_rank == 0 else None]
+            dist.broadcast_object_list(name, src=0)
+            self.outputfoldername = name[0]
+            dist.barrier()
         self.logfilename = self.outputfoldername + '/transport.log'
         if self.inputfilename and os.path.isfile(self.inputfilename):
             try:

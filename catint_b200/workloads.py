@@ -73,7 +73,7 @@ def geometric_mesh(n_nodes=1001, first_spacing=5e-11, L=50e-6):
     from scipy.optimize import brentq
     m = n_nodes - 1
     f = lambda r: L * (r - 1.0) / (r ** m - 1.0) - first_spacing
-    r = brentq(f, 1.0 + 1e-9, 2.0)
+    r = brentq(f, 1.0 + 1e-9, min(2.0, float(np.exp(600.0 / m))))     # r**m must not overflow
     i = np.arange(n_nodes, dtype=float)
     return (r ** i - 1.0) / (r ** m - 1.0)
 
@@ -84,3 +84,25 @@ def c3(n_phi=128, n_pH=128):
     kw = co2r_inputs(i_CO=tafel_current(-10.), i_H2=tafel_current(-5.))
     kw['descriptors'] = {'phiM': list(np.linspace(-0.5, -1.5, n_phi)), 'bulk_pH': list(np.linspace(6.0, 7.8, n_pH))}
     return kw
+
+
+def scaled_tafel_current(i_ref, phi_ref=-0.9, slope=0.12, clip=150.0):
+    """Tafel current multiplied by the roughness factor system['RF'] (the reference's flux multiplier,
+    /root/reference/catint/transport.py:844-851), clipped like tafel_current."""
+    def current(system):
+        i = i_ref * float(system.get('RF', 1.0)) * 10.0 ** (-(system['phiM'] - phi_ref) / slope)
+        return float(np.sign(i_ref) * min(abs(i), clip))
+    return current
+
+
+def c5(n_phi=64, n_scale=64, nx=5000):
+    """C5: CO2R/KHCO3 transient from the bulk state to steady state on a 5001-node mesh, 64 phiM x
+    64 flux scalings (descriptor 'RF').  Use Calculator(..., mesh=geometric_mesh(5001, C5_FIRST_SPACING),
+    mode='time-dependent') with an output time mesh; the default Poisson boundary (block size 9)."""
+    kw = co2r_inputs(i_CO=scaled_tafel_current(-10.), i_H2=scaled_tafel_current(-5.), nx=nx)
+    kw['descriptors'] = {'phiM': list(np.linspace(-0.5, -1.5, n_phi)), 'RF': list(np.geomspace(0.25, 4.0, n_scale))}
+    return kw
+
+
+C5_FIRST_SPACING = 5e-11
+C5_T_OUT = [1e-6, 1e-3, 1.0, 200.0]

@@ -25,7 +25,8 @@
  * are HOST memory.  No hidden allocation: scratch comes from a caller-provided
  * workspace sized by catint_pnp_workspace_bytes().  All functions return 0 on
  * success or a negative CATINT_PNP_E* code (never exit); catint_pnp_last_error()
- * gives the text.  Thread-safe per stream.
+ * gives the text.  Thread-safe per stream: no static launch state, the error text and the debug hook
+ * are per host thread, every call checks that the current device is sm_100.
  *
  * Layouts (doubles):
  *   concentrations  c   [B][nx_max][S]      node-major, species interleaved
@@ -48,6 +49,11 @@ extern "C" {
 #define CATINT_PNP_MAX_SPECIES   14
 #define CATINT_PNP_MAX_REACTIONS 12
 #define CATINT_PNP_MAX_REACTANTS 4      /* per side of one reaction */
+#define CATINT_PNP_MAX_BLOCK     13     /* catint_pnp_solve_batch / _jacobian_batch: unknowns per node, S+1
+                                           (default Poisson boundary) or S+2 (Stern) must be 2..13        */
+#define CATINT_PNP_MIN_NODES     6      /* every nx[cell] must satisfy MIN_NODES <= nx[cell] <= nx_max     */
+#define CATINT_PNP_MAX_OUTPUT_TIMES 4096 /* n_out per catint_pnp_solve_batch call (the output times travel
+                                           in the tail of the workspace)                                   */
 
 enum {
     CATINT_PNP_OK = 0,
@@ -68,7 +74,8 @@ enum {
     CATINT_PNP_CELL_ERROR_TEST_FAILED = 3,
     CATINT_PNP_CELL_NOT_FINITE = 4,
     CATINT_PNP_CELL_POLISH_FAILED = 5,   /* integrated to t_end but Newton on the steady residual did not converge */
-    CATINT_PNP_CELL_STEP_UNDERFLOW = 6   /* t+h == t: the discrete ODE blows up in finite time (LSODA: 'step size too small') */
+    CATINT_PNP_CELL_STEP_UNDERFLOW = 6,  /* t+h == t: the discrete ODE blows up in finite time (LSODA: 'step size too small') */
+    CATINT_PNP_CELL_BAD_INPUT = 7        /* nx[cell] outside CATINT_PNP_MIN_NODES..nx_max: the cell was skipped, its outputs untouched */
 };
 
 /* Model tables shared by all cells of a batch (HOST memory). */

@@ -30,3 +30,23 @@ def system_from_setup(su, rate_mode='summed', literal_sign=False, **over):
               g_bulk=float(su['g_bulk']), uniform=True)
     kw.update(over)
     return PnpSystem(**kw)
+
+
+def system_from_batch(batch, c, rate_mode='summed'):
+    """oracle PnpSystem of cell c of a catint_b200 CellBatch (uniform or table mesh, default or Stern
+    Poisson boundary) -- the inverse of catint_b200.calculator.build_cell_batch's parameter records
+    (include/catint_pnp.h: CATINT_PNP_P_*)."""
+    S = batch.S
+    p = batch.par[c]
+    n = int(batch.nx[c])
+    uniform = batch.mesh_id is None or int(batch.mesh_id[c]) < 0
+    if uniform:
+        x = np.arange(n) * p[3 * S + 5]
+    else:
+        x = p[3 * S + 5] * np.asarray(batch.mesh_xi[int(batch.mesh_id[c])][:n], dtype=float)
+    stern = int(batch.poisson_bc) == 1
+    return PnpSystem(z=batch.z, D=p[2 * S:3 * S], c_bulk=p[0:S], J=p[S:2 * S], x=x, beta=p[3 * S], eps=p[3 * S + 1],
+                     reactions=batch.reactions, rate_mode=rate_mode, use_migration=batch.use_migration,
+                     poisson_bc='stern_robin' if stern else 'dirichlet_wall_neumann_bulk',
+                     phi_wall=p[3 * S + 2], g_bulk=p[3 * S + 3], phiM=p[3 * S + 2], phiPZC=0.0,
+                     C_stern=p[3 * S + 4], uniform=uniform)

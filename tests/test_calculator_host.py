@@ -95,14 +95,14 @@ def test_scatter_results_conventions(resultsdir):
     ad = tp.alldata[1]
     k = names.index('CO')
     assert ad['species']['CO']['surface_concentration'] == res['c'][-1, 1, 0, k]
-    assert ad['species']['CO']['concentration'] == list(res['c'][-1, 1, :, k])
+    assert np.array_equal(ad['species']['CO']['concentration'], res['c'][-1, 1, :, k])
     j = res['flux'][1, k]
     assert ad['species']['CO']['electrode_flux'] == j
     assert ad['species']['CO']['electrode_current_density'] == pytest.approx(j * 2 * 96485.33289 / 1 / 10.)
     assert 'electrode_current_density' not in ad['species']['K+']
     h = names.index('H+')
     assert ad['system']['surface_pH'] == pytest.approx(-np.log10(res['c'][-1, 1, 0, h] / 1000.))
-    assert ad['system']['efield'] == list(-res['g'][-1, 1])
+    assert np.array_equal(ad['system']['efield'], -res['g'][-1, 1])
     assert ad['system']['surface_potential'] == res['phi'][-1, 1, 0]
     q = np.array([tp.species[s]['charge'] for s in names]) * 96485.33289
     assert ad['system']['charge_density'][5] == pytest.approx(float(res['c'][-1, 1, 5] @ q))

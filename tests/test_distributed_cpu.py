@@ -22,7 +22,7 @@ def fake_solve(sub):
     c += key[None, :, None, None] * 1e6
     c += np.arange(n)[None, None, :, None] + 0.01 * np.arange(S)[None, None, None, :] + np.arange(2)[:, None, None, None] * 100
     return {'c': c, 'phi': c[..., 0] * 2, 'g': c[..., 1] * 3, 'flux': sub.par[:, S:2 * S].copy(),
-            'status': (key > np.median(key)).astype(np.int32), 'n_steps': (np.arange(B) + 7).astype(np.int32) * 0 + sub.nx,
+            'status': (np.floor(key * 1e7) % 3).astype(np.int32), 'n_steps': (np.arange(B) + 7).astype(np.int32) * 0 + sub.nx,
             'n_newton': sub.nx * 2, 'n_setups': sub.nx * 3}
 
 
@@ -35,16 +35,36 @@ def make_batch(B=7):
     return batch
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n_cells=7):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        batch = make_batch()
-        full = D.solve_sharded(None, batch, solve_fn=fake_solve)
+        batch = make_batch(n_cells)
+        calls = []
+
+        def solve(sub):
+            calls.append(sub.B)
+            return fake_solve(sub)
+        full = D.solve_sharded(None, batch, solve_fn=solve, n_out=2)
+        full['solve_calls'] = np.array(calls)
         q.put((rank, {k: v for k, v in full.items()}))
     finally:
         dist.destroy_process_group()
+
+
+def _run_ranks(world, n_cells):
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_cells)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got
 
 
 def test_shard_map_is_round_robin():
@@ -55,23 +75,67 @@ def test_shard_map_is_round_robin():
 
 
 def test_two_rank_gather_restores_cell_order():
-    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = dict(q.get(timeout=60) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = _run_ranks(2, 7)
     want = fake_solve(make_batch())
     for r in range(2):
         for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'):
             assert np.array_equal(got[r][k], want[k]), (r, k)
+            assert got[r][k].dtype == want[k].dtype, (r, k)
+        # ONE packed collective: [2 ranks x 4 cells, width] doubles
+        n_out, n, S = 2, 101, 8
+        assert got[r]['gather_bytes'] == 2 * 4 * (n_out * n * S + 2 * n_out * n + S + 4) * 8
+
+
+def test_fewer_cells_than_ranks():
+    """a rank whose round-robin shard is empty skips the solve and still joins the gather (the reference's
+    `itask % size != rank: continue`, calculator.py:209-212)"""
+    got = _run_ranks(3, 2)
+    want = fake_solve(make_batch(2))
+    for r in range(3):
+        for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'):
+            assert np.array_equal(got[r][k], want[k]), (r, k)
+    assert list(got[0]['solve_calls']) == [1] and list(got[1]['solve_calls']) == [1]
+    assert list(got[2]['solve_calls']) == []
 
 
 def test_single_process_passthrough():
     batch = make_batch(5)
-    full = D.solve_sharded(None, batch, solve_fn=fake_solve)
+    full = D.solve_sharded(None, batch, solve_fn=fake_solve, n_out=2)
     assert np.array_equal(full['c'], fake_solve(batch)['c'])
+
+
+def _transport_worker(rank, world, port, q, resultsdir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['CATINT_QUIET'] = '1'
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from catint_b200 import workloads
+        from catint_b200.transport import Transport
+        tp = Transport(resultsdir=resultsdir, model_name='shared', **workloads.c2(n_potentials=3))
+        tp.save()
+        dist.barrier()
+        q.put((rank, (tp.mpi_rank, tp.mpi_size, tp.outputfoldername, sorted(os.listdir(tp.outputfoldername)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_results_folder_is_created_once_and_saved_by_rank_zero(tmp_path):
+    """every rank used to create its own numbered folder and pickle into the same files.  Now rank 0
+    creates the folder and broadcasts its name, log files are per rank, only rank 0 saves."""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_transport_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][:2] == (0, 2) and got[1][:2] == (1, 2)
+    assert got[0][2] == got[1][2]
+    assert sorted(os.listdir(str(tmp_path))) == ['shared_results']
+    files = got[1][3]
+    assert 'transport_id000.log' in files and 'transport_id001.log' in files
+    assert sum(1 for f in files if f.startswith('alldata')) == 1

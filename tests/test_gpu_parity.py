@@ -18,7 +18,8 @@ RTOL_PROFILE = 1e-6
 def bk():
     import torch
     from catint_b200 import backend as be
-    assert torch.cuda.is_available(), 'GPU tests need a B200'
+    if not torch.cuda.is_available():
+        pytest.skip('GPU tests need a B200')
     return be.PnpBackend('cuda:0')
 
 
@@ -287,7 +288,11 @@ def _batch_from_par(par, nx, template_batch):
 
 def test_ten_species_ragged_sweep_cells(bk, resultsdir):
     """C4-type cells: 10 species (CH4 from a third electrode reaction, inert Cl-), bulk_pH x boundary
-    thickness sweep (101/102 nodes), block size 11; checked against the CPU BDF oracle + Newton root."""
+    thickness sweep (101/102 nodes), block size 11, against goldens from the REFERENCE'S integrator (scipy
+    odeint, tests/golden/make_c4_golden.py): end state at t=200 s and the Newton root started from it.
+    The three thin-layer cells (dx = 0.1 um) are cells where odeint itself leaves every physical range
+    at t ~ 1.2e-4 s (the discrete ODE blows up in finite time; growth record in the golden file): the GPU
+    must report a failure there, not invent a result."""
     from catint_b200 import backend as be, workloads
     from catint_b200.transport import Transport
     from catint_b200.calculator import build_cell_batch
@@ -296,27 +301,33 @@ def test_ten_species_ragged_sweep_cells(bk, resultsdir):
     batch, _ = build_cell_batch(tp)
     assert batch.S == 10 and batch.b == 11 and batch.B == 16
     cells = [int(c) for c in go['cells']]
+    assert cells == list(range(16))
     assert np.array_equal(batch.par[cells], go['par']) and np.array_equal(batch.nx[cells], go['nx'])
     out = bk.solve(bk.upload(batch), [200.0], mode=be.MODE_STEADY, max_steps=20000)
     status = out['status'].cpu().numpy()
-    n_ok = 0
+    odeint_failed = [c for c in cells if not bool(go['ok_%d' % c])]
+    assert odeint_failed == [0, 4, 8]
     for c in cells:
-        if not bool(go['ok_%d' % c]):
-            # the reference ODE itself blows up in finite time for this cell (thin layer, dx = 0.1 um):
-            # the oracle's BDF underflows its step at t ~ 1e-4 s; the GPU must report it, not invent a result
-            assert status[c] != 0, c
+        if c in odeint_failed:
+            assert 'blow-up guard' in str(go['msg_%d' % c]) and float(go['fail_cmax_%d' % c]) > 1e3
+            assert status[c] == be_status('step_underflow'), (c, status[c])
             continue
-        n_ok += 1
         assert status[c] == 0, c
         n = int(batch.nx[c])
         cs = np.max(np.abs(batch.par[c, :10]))
         got = out['c'][-1, c, :n].cpu().numpy()
         assert relerr(got, go['newton_c_%d' % c], cs) < RTOL_PROFILE, c
+        # odeint's own end state: not yet steady to 1e-6 at t=200 s for the 200 um layers (diffusion time 40 s)
+        assert relerr(got, go['c_end_%d' % c], cs, floor=1e-9) < (RTOL_PROFILE if n * batch.par[c, 35] < 1e-4 else 5e-6), c
         gsc = np.max(np.abs(go['g_%d' % c]))
         assert np.max(np.abs(out['g'][-1, c, :n].cpu().numpy() - go['g_%d' % c])) < RTOL_PROFILE * gsc
         psc = np.max(np.abs(go['phi_%d' % c]))
         assert np.max(np.abs(out['phi'][-1, c, :n].cpu().numpy() - go['phi_%d' % c])) < RTOL_PROFILE * psc
-    assert n_ok == 13
+
+
+def be_status(name):
+    from catint_b200 import backend as be
+    return {v: k for k, v in be.CELL_STATUS.items()}[name]
 
 
 def test_c4_sweep_4096_cells_properties(bk, resultsdir):
@@ -370,11 +381,15 @@ def test_thousand_node_grid_uses_global_state(bk, resultsdir):
     cs = np.max(np.abs(batch.par[0, :8]))
     tr = bk.solve(db, go['t_out'], mode=be.MODE_TRANSIENT)
     assert tr['status'].tolist() == [0, 0, 0]
-    # t=1e-3 s: before the grid-scale instability of the reference scheme sets in -> tight;
-    # t=1 s: inside the phase where that unstable mode (growth rate ~1e3/s) saturates, two integrators
-    # with the same tolerances but different step sequences or summation orders differ by ~1e-2 -> loose
-    # (sanity bound only); t=200 s: steady again
-    for k, tol in zip(range(len(go['t_out'])), (1e-5, 5e-2, 1e-5)):
+    # Conditioning of the transient (tests/golden/make_n1001_golden.py): the golden holds a second CPU run whose
+    # initial state was perturbed by 1e-13 relative.  Where the two runs agree to 1e-5 the GPU must match to
+    # 1e-5 (t = 1e-3, 1e-2 and 200 s); inside the window where the grid-scale mode of the reference scheme grows
+    # and saturates (t = 1 s: the 1e-13 perturbation is amplified to >1e-4, i.e. by >1e9, so integration errors
+    # of order rtol = 1.5e-8 are amplified to O(0.1) in ANY integrator, odeint included) only a sanity bound holds.
+    sens = go['sensitivity']
+    assert sens[0] < 1e-5 and sens[1] < 1e-5 and sens[3] < 1e-9 and sens[2] > 1e-5
+    for k in range(len(go['t_out'])):
+        tol = 1e-5 if sens[k] < 1e-5 else 0.3
         assert relerr(tr['c'][k, 1].cpu().numpy(), go['bdf_c'][k], cs, floor=1e-9) < tol, k
     st = bk.solve(db, [200.0], mode=be.MODE_STEADY)
     assert st['status'].tolist() == [0, 0, 0]
@@ -382,13 +397,17 @@ def test_thousand_node_grid_uses_global_state(bk, resultsdir):
     assert np.max(np.abs(st['phi'][-1, 0].cpu().numpy() - go['phi'])) < RTOL_PROFILE * np.max(np.abs(go['phi']))
 
 
-@pytest.mark.parametrize('nn', [201, 1001])
+@pytest.mark.parametrize('nn', [101, 201, 1001])
 def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
     """C3-type cells: Stern-layer (Robin) Poisson boundary, phi carried as an unknown (block size S+2),
-    geometric mesh with a 0.05 nm first interval; phiM x bulk_pH corner cells against the CPU BDF oracle +
-    Newton root of the same discrete system (extension beyond the reference FD code).  A cell
-    whose discrete ODE blows up in finite time in the oracle must be reported as failed by the GPU too.
-    nn=1001 runs through the global-state kernel variant (the iterate does not fit in shared memory)."""
+    geometric mesh with a 0.05 nm first interval; the four phiM x bulk_pH corner cells (extension beyond the
+    reference FD code; goldens: tests/golden/make_c3_golden.py).
+      nn=101  against the REFERENCE'S integrator (scipy odeint on the restated RHS with the same extension):
+              end state and its Newton root; the same file pins the CPU BDF against odeint (1e-8 / 1e-9);
+      nn=201, 1001  dense odeint is out of reach; CPU BDF + Newton root (nn=1001 runs through the global-state
+              kernel variant: the iterate does not fit in shared memory).
+    Cell 2 (phiM=-1.5 V, pH 6) has no bounded solution: odeint (nn=101) and the CPU BDF (all nn) both leave
+    every bounded range at t = 0.685..0.689 s; the GPU must report exactly that cell as failed."""
     from catint_b200 import backend as be, workloads
     from catint_b200.transport import Transport
     from catint_b200.calculator import build_cell_batch
@@ -399,19 +418,27 @@ def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
     assert np.array_equal(batch.par, go['par']) and np.allclose(batch.mesh_xi[0], go['mesh'], rtol=0, atol=0)
     out = bk.solve(bk.upload(batch), [200.0], mode=be.MODE_STEADY, max_steps=50000)
     status = out['status'].cpu().numpy()
-    n_ok = 0
+    assert [c for c in range(4) if not bool(go['ok_%d' % c])] == [2]
+    assert 0.68 < float(go['fail_t_2']) < 0.69
+    if nn == 101:
+        # the rung that pins the CPU BDF (and the failure) against odeint
+        assert [c for c in range(4) if not bool(go['odeint_ok_%d' % c])] == [2]
+        assert abs(float(go['odeint_fail_t_2']) - float(go['fail_t_2'])) < 1e-3
+        for c in (0, 1, 3):
+            assert float(go['bdf_vs_odeint_end_%d' % c]) < 1e-7 and float(go['bdf_vs_odeint_root_%d' % c]) < 1e-8
     for c in range(batch.B):
-        if not bool(go['ok_%d' % c]):
-            assert status[c] != 0, c
+        if c == 2:
+            assert status[c] == be_status('step_underflow'), (c, status)
             continue
-        n_ok += 1
         assert status[c] == 0, (c, status)
         cs = np.max(np.abs(batch.par[c, :8]))
         got = out['c'][-1, c].cpu().numpy()
         assert relerr(got, go['newton_c_%d' % c], cs) < RTOL_PROFILE, c
         assert np.max(np.abs(out['phi'][-1, c].cpu().numpy() - go['phi_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['phi_%d' % c]))
         assert np.max(np.abs(out['g'][-1, c].cpu().numpy() - go['g_%d' % c])) < RTOL_PROFILE * np.max(np.abs(go['g_%d' % c]))
-    assert n_ok >= 2
+        if nn == 101:
+            assert relerr(got, go['odeint_newton_c_%d' % c], cs) < RTOL_PROFILE, c
+            assert relerr(got, go['odeint_c_end_%d' % c], cs, floor=1e-9) < RTOL_PROFILE, c
 
 
 def test_warm_start_from_results_folder(bk, resultsdir):
