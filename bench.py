@@ -52,6 +52,24 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def fp64_peak():
+    """fp64 FMA peak measured on this GPU pool with scripts/native/fp64_peak.cu (profiles/fp64_peak.json)."""
+    p = os.path.join(ROOT, 'profiles', 'fp64_peak.json')
+    if os.path.isfile(p):
+        return float(json.load(open(p))['fp64_tflops']), 'measured (profiles/fp64_peak.json, scripts/native/fp64_peak.cu)'
+    return 37.0, 'fallback (B200 datasheet class, 64 DFMA/clk/SM x 148 SMs x 1.965 GHz)'
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json:
     dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same workload), or None."""
@@ -63,15 +81,13 @@ def ncu_traffic(kernel):
     return None
 
 
-def c2_batch(rank=0, world=1, n_cells=CELLS_PER_GPU):
-    """the rank's sweep as a host CellBatch (model tables from the fixture-verified Transport)."""
+def c2_batch(n_cells=CELLS_PER_GPU):
+    """the potential sweep as a host CellBatch (model tables from the fixture-verified Transport)."""
     import tempfile
     from catint_b200.transport import Transport
     from catint_b200.calculator import build_cell_batch
     from catint_b200 import workloads
     kw = workloads.c2(n_potentials=n_cells)
-    shift = (rank / float(max(world, 1))) * (1.0 / n_cells) if world > 1 else 0.0
-    kw['descriptors'] = {'phiM': [p - shift for p in kw['descriptors']['phiM']]}
     tp = Transport(resultsdir=tempfile.mkdtemp(prefix='catint_bench_'), model_name='bench', **kw)
     tp.set_calculator('odeint')
     batch, _ = build_cell_batch(tp)
@@ -164,7 +180,51 @@ def cpu_sweep(batch, n_cells, cores, seed=0):
         res = pool.map(_cpu_cell, jobs, chunksize=1)
     wall = time.time() - t0
     n_ok = sum(1 for r in res if r[0])
-    return n_ok / wall, wall, n_ok, pick
+    nfe = float(np.mean([r[2] for r in res])) if res else 0.0
+    return n_ok / wall, wall, n_ok, pick, nfe
+
+
+def literal_rhs_seconds(batch, cell=0, reps=3):
+    """one call of the loop-literal RHS (what the reference's ode_func would execute,
+    oracle/pnp_oracle.py:rhs_literal) on the bulk state of one cell"""
+    from oracle.pnp_oracle import PnpSystem
+    S = batch.S
+    par = batch.par[cell]
+    x = np.arange(int(batch.nx[cell])) * par[3 * S + 5]
+    s = PnpSystem(z=batch.z, D=par[2 * S:3 * S], c_bulk=par[0:S], J=par[S:2 * S], x=x, beta=par[3 * S],
+                  eps=par[3 * S + 1], reactions=batch.reactions, rate_mode='summed', use_migration=True,
+                  phi_wall=par[3 * S + 2], g_bulk=par[3 * S + 3], uniform=True)
+    c0 = s.c0_flat() * (1.0 + 1e-3 * np.sin(np.arange(S * s.n)))
+    s.rhs_literal(c0)
+    t0 = time.time()
+    for _ in range(reps):
+        s.rhs_literal(c0)
+    t_lit = (time.time() - t0) / reps
+    t0 = time.time()
+    for _ in range(20 * reps):
+        s.rhs(c0)
+    t_vec = (time.time() - t0) / (20 * reps)
+    return t_lit, t_vec
+
+
+def cpu_baseline_block(batch, cores, cells_per_core=2):
+    """the oracle (scipy odeint on the restated RHS) as a multiprocessing sweep over a seed-0 random subsample
+    of the same cells, >= 2 cells per core, plus the loop-literal RHS figure."""
+    n_cells = min(cells_per_core * cores, batch.B)
+    v, wall, n_ok, pick, nfe = cpu_sweep(batch, n_cells, cores)
+    t_lit, t_vec = literal_rhs_seconds(batch, int(pick[0]))
+    return {
+        'value': v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port', 'cpu_model': cpu_model(),
+        'sample': '%d seed-0 random cells of the same 1024-cell sweep (%d per core, multiprocessing.Pool(%d)), scipy '
+                  'odeint on the numpy-vectorised restated RHS (dense FD Jacobian, t_end=200 s, default rtol/atol), '
+                  '%.1f s wall, %d converged, mean %.0f RHS calls per cell' % (n_cells, cells_per_core, cores, wall, n_ok, nfe),
+        'loop_literal': {
+            'rhs_ms': 1e3 * t_lit, 'vectorised_rhs_ms': 1e3 * t_vec,
+            'estimated_cells_per_s_per_core': 1.0 / max(nfe * t_lit, 1e-30),
+            'note': 'loop-literal transcription of the reference ode_func (what the reference would execute), timed '
+                    'per call on one cell of the sample; a full literal cell is mean RHS calls x rhs_ms = %.0f s, '
+                    'so the cells/s figure is that product, not a completed run' % (nfe * t_lit)},
+    }
 
 
 def run_reference(args):
@@ -173,32 +233,34 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     tp, batch = c2_batch()
-    n_cells = min(cores, batch.B)
+    n_cells = min(2 * cores, batch.B)
     budget = float(os.environ.get('CATINT_REF_BUDGET_S', '240'))
     t_start = time.time()
     times, values = [], []
     warm = 0
     # one warm-up step tells the step time; the rest of W/K is clamped to the wall-clock budget
     if args.warmup > 0:
-        v, wall, n_ok, _ = cpu_sweep(batch, n_cells, cores)
+        v, wall, n_ok, _, _ = cpu_sweep(batch, n_cells, cores)
         warm = 1
         step_t = wall
     else:
         step_t = 70.0
     k_eff = max(1, min(args.steps, int((budget - (time.time() - t_start)) // max(step_t, 1.0))))
     for k in range(k_eff):
-        v, wall, n_ok, _ = cpu_sweep(batch, n_cells, cores, seed=k)
+        v, wall, n_ok, _, _ = cpu_sweep(batch, n_cells, cores, seed=k)
         times.append(wall); values.append(v)
     value = float(np.sum([v * t for v, t in zip(values, times)]) / np.sum(times))
-    sample = ('%d seed-k random cells of the 1024-cell sweep per step (one per core), scipy odeint on the '
-              'numpy-vectorised restated RHS, dense FD Jacobian, t_end=200 s, default rtol/atol; '
-              'requested steps/warmup %d/%d clamped to a %d s budget' % (n_cells, args.steps, args.warmup, int(budget)))
+    sample = ('%d seed-k random cells of the 1024-cell sweep per step (two per core, multiprocessing.Pool(%d)), scipy '
+              'odeint on the numpy-vectorised restated RHS, dense FD Jacobian, t_end=200 s, default rtol/atol; '
+              'requested steps/warmup %d/%d clamped to a %d s budget; CPU: %s'
+              % (n_cells, cores, args.steps, args.warmup, int(budget), cpu_model()))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'cells/s', 'n_gpus': args.gpus,
         'steps': k_eff, 'warmup': warm, 'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'cells_per_step': n_cells},
-        'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'cpu_model': cpu_model()},
         'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -247,7 +309,7 @@ def rhs_roofline(bk, batch, dev, n_cells=131072, reps=10):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from catint_b200 import backend as be
+    from catint_b200 import backend as be, distributed as D
     from catint_b200.calculator import Calculator
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -260,7 +322,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
-    tp, batch = c2_batch(rank, world)
+    # Weak scaling: the job is ONE potential sweep of 1024*N cells over the same phiM range, sharded round-robin
+    # (cell j -> rank j % N, catint_b200/distributed.py), i.e. every rank integrates a 1024-point sweep.
+    tp, gbatch = c2_batch(n_cells=CELLS_PER_GPU * world)
+    batch = gbatch.select(D.shard_indices(gbatch.B, rank, world)) if world > 1 else gbatch
     bk = be.PnpBackend(dev)
     db = bk.upload(batch)
     out = bk.alloc_outputs(db, 1)
@@ -293,79 +358,103 @@ def run_gpu(args):
     launches = bk.launches - launches0
     dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
     n_conv = int((out['status'] == 0).sum().item())
-    n_newton = out['n_newton'].to(torch.float64)
-    newton_total = float(n_newton.sum().item())
-    steps_mean = float(out['n_steps'].to(torch.float64).mean().item())
+    newton_total = float(out['n_newton'].to(torch.float64).sum().item())
+    setups_total = float(out['n_setups'].to(torch.float64).sum().item())
+    steps_total = float(out['n_steps'].to(torch.float64).sum().item())
 
-    # ---- e2e: host buffers in, host buffers out, every step -----------------------
+    # ---- e2e: the reference-facing path with HOST buffers, every step: H2D of the cell parameters (pinned),
+    # solve, ONE packed NCCL all_gather of the results on the devices (N > 1), D2H of the gathered results.
+    # This is Calculator.run()'s device section (catint_b200/distributed.py:solve_sharded). -----------------
     calc = Calculator(transport=tp, dt=0.5, tmax=T_END, ntout=1, mode='stationary', rtol=RTOL, atol=ATOL, device=dev)
     pinned = {'par': torch.from_numpy(batch.par).pin_memory(), 'nx': torch.from_numpy(batch.nx).pin_memory()}
+    h2d_local = [0]
+
+    def solve_fn(sub):
+        r = calc.solve_batch_device(sub, backend=bk, pinned=pinned)
+        h2d_local[0] = int(r.pop('h2d_bytes'))
+        return r
+
+    def e2e_step():
+        return D.solve_sharded(calc, gbatch, solve_fn=solve_fn, device=dev)
+
     e2e_steps = max(1, min(args.steps, 3))
-    res = calc.solve_batch(batch, backend=bk, pinned=pinned)          # warm
+    res = e2e_step()                                                   # warm
     sync_all()
     t0 = time.perf_counter()
     e2e_conv = 0
     for _ in range(e2e_steps):
-        res = calc.solve_batch(batch, backend=bk, pinned=pinned)
-        e2e_conv += int(np.sum(res['status'] == 0))
-    torch.cuda.synchronize()
+        res = e2e_step()
+        e2e_conv += int(np.sum(res['status'] == 0))                    # whole job (gathered on every rank)
+    sync_all()
     e2e_s = time.perf_counter() - t0
-    h2d, d2h = int(res['h2d_bytes']), int(res['d2h_bytes'])
+    d2h_local = int(res.get('gather_bytes', 0)) or sum(int(v.nbytes) for k, v in res.items() if hasattr(v, 'nbytes'))
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(t[0]), float(t[1])
-        c = torch.tensor([n_conv, e2e_conv, newton_total], dtype=torch.float64, device=dev)
+        c = torch.tensor([n_conv, h2d_local[0], d2h_local], dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        n_conv_all, e2e_conv_all, newton_all = float(c[0]), float(c[1]), float(c[2])
+        n_conv_all, h2d_all, d2h_all = float(c[0]), float(c[1]), float(c[2])
     else:
-        n_conv_all, e2e_conv_all, newton_all = float(n_conv), float(e2e_conv), newton_total
+        n_conv_all, h2d_all, d2h_all = float(n_conv), float(h2d_local[0]), float(d2h_local)
 
     if rank == 0:
         value = n_conv_all * args.steps / (dev_ms * 1e-3)
-        e2e_value = e2e_conv_all / e2e_s
-        # roofline of pnp_bdf_kernel (one launch per step and rank).  Algorithmic bytes:
-        #   per Newton iteration  16*S*n (state in, update out) + 2*8*n*REC (the stored block factors are
-        #                         streamed once by the forward and once by the backward solve sweep)
-        #   per factorisation     8*n*REC written (REC = b*bp + 4*b doubles per node, bp = b rounded up to even)
-        #   per BDF step          26*8*n*b (Nordsieck history: predict pass reads/writes 6 vectors, correction
-        #                         pass reads 7 and writes 7)
+        e2e_value = e2e_conv / e2e_s
+        # ---- roofline of pnp_bdf_kernel (one launch per step and rank), SURVEY 8(d) --------------------------
+        # per Newton iteration and cell: bytes 16*S*n (state in, update out; + 16*b^2*n when the b x b blocks
+        # W cannot stay on chip, 8*b^2*n > 227 KB) ; flops 4*b^2*n for the two block sweeps;
+        # per factorisation and cell: 14/3*b^3*n (block LU 2/3, W = D'^-1 U 2, Schur update 2; dense-block count).
+        # A modified-Newton step re-uses the factors, so factorisations are counted where they happen.
         S, n, b = batch.S, int(batch.nx_max), batch.b
-        rec = b * (b + (b & 1)) + 4 * b
-        bytes_newton = 16.0 * S * n + 16.0 * n * rec
-        bytes_factor = 8.0 * n * rec
-        bytes_step = 26.0 * 8.0 * n * b
-        setups_total = float(out['n_setups'].to(torch.float64).sum().item())
-        steps_total = float(out['n_steps'].to(torch.float64).sum().item())
-        algo_bytes = newton_total * bytes_newton + setups_total * bytes_factor + steps_total * bytes_step
-        flops = (setups_total * n * (8.0 / 3.0 * b ** 3 + 4.0 * b ** 2)        # block inverse + W column + Schur
-                 + newton_total * n * (4.0 * b ** 2 + 40.0 * S))             # two mat-vecs + residual
+        w_on_chip = 8.0 * b * b * n <= 227e3
+        bytes_newton = 16.0 * S * n + (0.0 if w_on_chip else 16.0 * b * b * n)
+        flops_newton = 4.0 * b * b * n
+        flops_factor = 14.0 / 3.0 * b ** 3 * n
+        algo_bytes = newton_total * bytes_newton
+        algo_flops = newton_total * flops_newton + setups_total * flops_factor
         launch_s = dev_ms * 1e-3 / args.steps
-        peak, which = measured_peaks()
-        achieved = algo_bytes / launch_s / 1e9                                  # this rank's launch
-        roofline = {'bound': 'hbm', 'kernel': 'pnp_bdf_kernel<9,false,true,false>', 'achieved': achieved, 'peak': peak,
-                    'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic('pnp_bdf_kernel'), 'peak_source': which,
-                    'algorithmic_bytes_per_launch': algo_bytes,
-                    'newton_iterations_per_launch': newton_total, 'factorisations_per_launch': setups_total,
-                    'bdf_steps_per_launch': steps_total,
-                    'bytes_per_newton_iteration': bytes_newton, 'bytes_per_factorisation': bytes_factor,
-                    'bytes_per_bdf_step': bytes_step,
-                    'fp64_tflops_algorithmic': flops / launch_s / 1e12,
-                    'note': 'one warp per cell, 1024 cells = 7 warps/SM: the kernel is bound by the dependency '
-                            'latency of the sequential block sweeps, not by HBM; traffic = DRAM bytes of one launch '
-                            '(ncu, L2 absorbs the rest of the algorithmic bytes), see DESIGN.md 6'}
+        hbm_peak, hbm_src = measured_peaks()
+        f64_peak, f64_src = fp64_peak()
+        hbm_ach = algo_bytes / launch_s / 1e9
+        f64_ach = algo_flops / launch_s / 1e12
+        hbm_frac, f64_frac = hbm_ach / hbm_peak, f64_ach / f64_peak
+        traffic = ncu_traffic('pnp_bdf_kernel')
+        by_f64 = f64_frac >= hbm_frac
+        roofline = {
+            'kernel': 'pnp_bdf_kernel<9,false,true>',
+            'bound': 'latency',
+            'bound_detail': 'ncu: neither roof is near -- one warp per cell walks sequential block sweeps; issue '
+                            'slots / dependency latency limit it (profiles/r2/). achieved = max(hbm_frac, fp64_frac) '
+                            'as SURVEY 8(d) prescribes; the fp64 term is the relevant one at n=101 (blocks stay on chip)',
+            'achieved': f64_ach if by_f64 else hbm_ach, 'peak': f64_peak if by_f64 else hbm_peak,
+            'unit': 'TFLOP/s' if by_f64 else 'GB/s', 'frac': max(hbm_frac, f64_frac),
+            'hbm': {'achieved': hbm_ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm_frac, 'peak_source': hbm_src,
+                    'algorithmic_bytes_per_launch': algo_bytes, 'bytes_per_newton_iteration': bytes_newton},
+            'fp64': {'achieved': f64_ach, 'peak': f64_peak, 'unit': 'TFLOP/s', 'frac': f64_frac, 'peak_source': f64_src,
+                     'algorithmic_flops_per_launch': algo_flops, 'flops_per_newton_iteration': flops_newton,
+                     'flops_per_factorisation': flops_factor},
+            'traffic': traffic,
+            'traffic_over_algorithmic': (traffic / algo_bytes) if traffic else None,
+            'newton_iterations_per_launch': newton_total, 'factorisations_per_launch': setups_total,
+            'bdf_steps_per_launch': steps_total, 'seconds_per_launch': launch_s,
+        }
         line = {
             'metric': METRIC, 'value': value, 'unit': 'cells/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'cells_per_gpu': CELLS_PER_GPU,
+            'config': {'workload': WORKLOAD, 'cells_per_gpu': CELLS_PER_GPU, 'cells_total': int(gbatch.B),
+                       'sharding': 'one %d-cell sweep, cell j -> rank j %% N' % gbatch.B,
                        'l2': 'flushed between timed steps (256 MiB device write)',
-                       'mean_bdf_steps_per_cell': steps_mean, 'mean_newton_per_cell': newton_total / batch.B,
+                       'mean_bdf_steps_per_cell': steps_total / batch.B, 'mean_newton_per_cell': newton_total / batch.B,
                        'mean_factorisations_per_cell': setups_total / batch.B},
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': h2d * args.gpus,
-                    'd2h_bytes_per_step': d2h * args.gpus, 'steps': e2e_steps},
+            'e2e': {'value': e2e_value, 'unit': 'cells/s', 'h2d_bytes_per_step': int(h2d_all),
+                    'd2h_bytes_per_step': int(d2h_all), 'steps': e2e_steps,
+                    'path': 'Calculator.solve_batch_device + distributed.solve_sharded: H2D (pinned) -> solve -> '
+                            + ('one packed NCCL all_gather_into_tensor on the devices -> ' if world > 1 else '')
+                            + 'D2H of all results; wall clock, barrier on both sides, max over ranks'},
             'gpu_launches': launches * args.gpus,
             'converged_cells_per_step': n_conv_all,
             'roofline': roofline,
@@ -373,14 +462,7 @@ def run_gpu(args):
         if args.gpus == 1:
             line['roofline_rhs'] = rhs_roofline(bk, batch, dev)
         if args.gpus == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            n_cells = min(cores, batch.B)
-            v, wall, n_ok, pick = cpu_sweep(batch, n_cells, cores)
-            line['cpu_baseline'] = {
-                'value': v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
-                'sample': '%d seed-0 random cells of the same 1024-cell sweep, one per core, scipy odeint on the '
-                          'numpy-vectorised restated RHS (dense FD Jacobian, t_end=200 s, default rtol/atol), '
-                          '%.1f s wall, %d converged' % (n_cells, wall, n_ok)}
+            line['cpu_baseline'] = cpu_baseline_block(batch, os.cpu_count() or 1)
         else:
             line['cpu_baseline'] = None
         print(json.dumps(line), flush=True)

@@ -2,13 +2,25 @@
 // (/root/reference/catint/calculator_old.py:827-935, Poisson :680-819, rates :159-208).
 //
 // Pure streaming stencil: 16*S*n algorithmic bytes per cell (read c, write dc/dt), ~1.4 flop/B,
-// HBM bound.  One warp per cell:
-//   1. the cell's interleaved state [node][species] is read with coalesced 16-byte loads and
-//      transposed into shared memory [species][node] (conflict-free lane-per-node access);
-//   2. charge density per node, warp-scan suffix sum from the bulk -> g (field gradient);
-//   3. stencil + mass-action rates, lane per node; each lane writes its node record (S doubles,
-//      16-byte stores; the partial sectors merge in the write-back L2).  No output staging in
-//      shared memory: occupancy matters more than store coalescing for this latency-bound body.
+// HBM bound.  Design for B200:
+//   * a block of 256 threads works on up to RHS_NODES = 512 nodes at a time, one node per thread and
+//     round: either a GROUP of whole small cells (n <= 512: five 101-node cells = 505 of 512 lanes busy,
+//     where a warp-per-cell mapping left 21 % of the lanes idle), or one TILE of a large cell (n > 512,
+//     e.g. the 1001/5001-node grids of C3/C5), tiles walked from the bulk towards the wall so that the
+//     backward cumulative sum of the reference's Poisson solve (:753-759,793-796) is carried from tile to
+//     tile and the state is read exactly once;
+//   * every thread reads its node record (S contiguous doubles, 16-byte loads: a warp covers 32*8*S
+//     contiguous bytes, every sector is used) straight into registers, keeps it there for the stencil and
+//     drops a transposed copy [species][node] (odd pitch, conflict-free lane-per-node access) into shared
+//     memory for its neighbours and for the mass-action products; the node's charge density comes from the
+//     registers for free;
+//   * g (the field gradient) by a warp-per-cell shuffle scan (groups) or a block-wide scan with carry (tiles);
+//   * stencil + mass-action rates from registers/shared memory, results stored straight from registers with
+//     16-byte stores (each thread writes its own contiguous record; the half-filled sectors of one store
+//     instruction are completed by the next one and merge in L2: DRAM traffic = algorithmic bytes);
+//   * the reaction table is pre-compiled per block into byte offsets into the transposed state, so a
+//     product of concentrations costs one add, one LDS and one multiply per factor, no predication.
+// Grid = resident blocks x SMs, persistent loop over groups / cells.
 #pragma once
 #include "pnp_kernels.cuh"
 
@@ -21,174 +33,345 @@ struct RhsParams {
     double* dcdt; double* g_out; double* phi_out;
 };
 
-constexpr int RHS_WARPS = 4;
+constexpr int RHS_THREADS = 256;
+constexpr int RHS_WARPS = RHS_THREADS / 32;
+constexpr int RHS_NODES = 512;                 // node slots per block iteration (two rounds of 256)
+constexpr int RHS_ROUNDS = RHS_NODES / RHS_THREADS;
+constexpr int RHS_NP = RHS_NODES + 3;          // odd pitch of the transposed state (slot = node + 1)
+constexpr int RHS_MAXG = 16;                   // cells per group (tiny grids use fewer slots)
+#ifndef CATINT_RHS_MINB
+#define CATINT_RHS_MINB 3                      // resident blocks per SM the register allocation aims at
+#endif
 
-// shared-memory doubles per warp: state [S][NP] + g [NP]
-__host__ __device__ inline size_t rhs_smem_doubles(int S, int nxm) {
-    const size_t NP = (size_t)(nxm | 1) + 2;      // odd pitch
-    return ((size_t)S + 1) * NP;
-}
+// per-cell constants of the cells of a group (shared memory)
+struct RhsCell {
+    double D[MAXS], J[MAXS];
+    double bF, Feps;            // beta*F (0 without migration), F/eps
+    double dx, g_bulk, phi_wall;
+    const double* xi;           // normalised mesh row or nullptr (uniform)
+    int n, first;               // nodes (0: cell skipped, bad nx), first node slot of this cell in the group
+};
+
+// reaction program: byte offsets of the factors into the transposed state
+struct RhsProg {
+    int ne[MAXR], np[MAXR];
+    int off[MAXR][2 * MAXRT];   // educts then products
+};
 
 template <int S>
-__global__ void __launch_bounds__(RHS_WARPS * 32) pnp_rhs_kernel(RhsParams P) {
+__host__ __device__ inline size_t rhs_smem_bytes() {
+    size_t b = (sizeof(DevTables) + 15) & ~size_t(15);
+    b += (sizeof(RhsProg) + 15) & ~size_t(15);
+    b += sizeof(RhsCell) * RHS_MAXG;
+    b += sizeof(double) * ((size_t)S * RHS_NP + 2 * (RHS_NODES + 4) + 2 * RHS_WARPS + 8);
+    return b;
+}
+
+__device__ __forceinline__ double mesh_h(const RhsCell& ce, int i) {       // h_i = x_{i+1} - x_i
+    return ce.xi ? ce.dx * (ce.xi[i + 1] - ce.xi[i]) : ce.dx;
+}
+
+// inclusive warp scan (sum) by shuffles
+__device__ __forceinline__ double warp_scan(double t, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(FULL, t, o);
+        if (lane >= o) t += v;
+    }
+    return t;
+}
+
+// potential by the reference's forward cumulative sum (:798-800): v_0 = phi_wall, v_i = v_{i-1} + g_i*h_{i-1}
+// for i = 1..n-2, linear extrapolation to the bulk node.  One warp; g indexed by node.
+__device__ __forceinline__ void potential_scan(const RhsCell& ce, const double* g, double* po, int lane) {
+    const int n = ce.n;
+    double run = ce.phi_wall, vm1 = run, vm2 = run;
+    for (int bot = 1; bot <= n - 2; bot += 32) {
+        const int i = bot + lane;
+        const double t = warp_scan(i <= n - 2 ? g[i] * mesh_h(ce, i - 1) : 0.0, lane);
+        const double v = run + t;
+        if (i <= n - 2) po[i] = v;
+        const int last = (n - 2 - bot) < 31 ? (n - 2 - bot) : 31;
+        const double vl = __shfl_sync(FULL, v, last);
+        const double vprev = __shfl_sync(FULL, v, last > 0 ? last - 1 : 0);
+        vm2 = last > 0 ? vprev : run;
+        vm1 = vl;
+        run = vl;
+    }
+    if (lane == 0) {
+        po[0] = ce.phi_wall;
+        const double ratio = ce.xi ? mesh_h(ce, n - 2) / mesh_h(ce, n - 3) : 1.0;
+        po[n - 1] = vm1 + (vm1 - vm2) * ratio;
+    }
+}
+
+template <int S, bool LARGE>
+__global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(RhsParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
     {
         const int words = (int)(sizeof(DevTables) / 4);
         const int* src = reinterpret_cast<const int*>(&P.tb);
         int* dst = reinterpret_cast<int*>(tb);
-        for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+        for (int w = tid; w < words; w += RHS_THREADS) dst[w] = src[w];
+    }
+    size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
+    RhsProg* prog = reinterpret_cast<RhsProg*>(smem_raw + off);   off += (sizeof(RhsProg) + 15) & ~size_t(15);
+    RhsCell* cells = reinterpret_cast<RhsCell*>(smem_raw + off);  off += sizeof(RhsCell) * RHS_MAXG;
+    double* cs_ = reinterpret_cast<double*>(smem_raw + off);      // [S][RHS_NP] transposed state, slot = node + 1
+    double* term = cs_ + (size_t)S * RHS_NP;                      // [RHS_NODES + 4] (F/eps)*sum z c * h_i per slot
+    double* gs = term + RHS_NODES + 4;                            // [RHS_NODES + 4] g per slot
+    double* wsum = gs + RHS_NODES + 4;                            // [2*RHS_WARPS] block scan partials
+    double* carry_s = wsum + 2 * RHS_WARPS;                       // [8] carry between tiles
+    __syncthreads();
+    if (tid < tb->R) {
+        const int r = tid;
+        prog->ne[r] = tb->ned[r]; prog->np[r] = tb->npr[r];
+        for (int e = 0; e < MAXRT; ++e) {
+            prog->off[r][e] = (e < tb->ned[r] ? (int)tb->ed[r][e] : 0) * RHS_NP * 8;
+            prog->off[r][MAXRT + e] = (e < tb->npr[r] ? (int)tb->pr[r][e] : 0) * RHS_NP * 8;
+        }
     }
     __syncthreads();
     const int nxm = P.tb.nx_max;
-    const int NP = (nxm | 1) + 2;
-    const size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + rhs_smem_doubles(S, nxm) * sizeof(double);
-    unsigned char* mine = smem_raw + off + (size_t)warp * per_warp;
-    CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
-    double* cs_ = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));   // [S][NP]
-    double* gs = cs_ + (size_t)S * NP;                                                           // [NP]
+    const bool mig = tb->use_migration;
+#ifdef CATINT_RHS_NOREACT
+    const int R = 0;
+#else
+    const int R = tb->R;
+#endif
 
-    // persistent over cells: grid = multiple of the SM count
-    for (long long cell = (long long)blockIdx.x * RHS_WARPS + warp; cell < P.n_cells;
-         cell += (long long)gridDim.x * RHS_WARPS) {
-        CellScalars cs;
-        load_cell(*tb, P.par, P.nx, P.mesh_id, P.mesh_xi, cell, lane, cs, sp);
-        const int n = cs.n;
-        if (n < 4 || n > nxm) continue;                 // bad nx[cell]: skip (warp-uniform), outputs untouched
-        const double* c = P.c + (size_t)cell * nxm * S;
-        double* dst = P.dcdt + (size_t)cell * nxm * S;
-        const bool mig = tb->use_migration;
-
-        // ---- 1. coalesced load + transpose
-        const int total = n * S;                       // doubles of this cell
-        if (((size_t)c & 15) == 0) {
-            const double2* c2 = reinterpret_cast<const double2*>(c);
-            for (int e2 = lane; e2 < total / 2; e2 += 32) {
-                const double2 v = c2[e2];
-                const int e = 2 * e2;
-                const int i = e / S, s = e - i * S;
-                cs_[s * NP + i] = v.x;
-                if (s + 1 < S) cs_[(s + 1) * NP + i] = v.y; else cs_[i + 1] = v.y;
-            }
-            if ((total & 1) && lane == 0) { const int e = total - 1; cs_[(e % S) * NP + e / S] = c[e]; }
+    // one node: stencil + rates -> global.  c0: this node's record (registers); slot: its slot in the
+    // transposed state (neighbours at slot-1 / slot+1); i: node index in its cell.
+    auto node_rhs = [&](const RhsCell& ce, const double (&c0)[S], int slot, int i, double* __restrict__ o) {
+        double res[S];
+        const int n = ce.n;
+        if (i == n - 1) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) res[s] = 0.0;                                    // frozen bulk node (:886)
+        } else if (i == 0) {
+            double w0, ih0;
+            if (ce.xi) { const double h0 = mesh_h(ce, 0), h1 = mesh_h(ce, 1); w0 = 1.0 / (h0 + h1); ih0 = 1.0 / h0; }
+            else { w0 = 1.0 / (2.0 * ce.dx); ih0 = 2.0 * w0; }
+            const double g1 = gs[slot + 1];
+#pragma unroll
+            for (int s = 0; s < S; ++s)                                                  // :902-909, inward flux
+                res[s] = (ce.D[s] * ((cs_[s * RHS_NP + slot + 2] - c0[s]) * w0
+                                     + ce.bF * tb->z[s] * cs_[s * RHS_NP + slot + 1] * g1) + ce.J[s]) * ih0;
         } else {
-            for (int e = lane; e < total; e += 32) cs_[(e % S) * NP + e / S] = c[e];
-        }
-        __syncwarp();
-
-        // ---- 2. g_i = g_bulk - sum_{j=i}^{n-2} lapl_j*h_j (i=1..n-2), lapl = -sum q c/eps
-        if (mig) {
-            double carry = 0.0;
-            for (int base = n - 2; base >= 1; base -= 32) {
-                const int i = base - lane;
-                double term = 0.0;
-                if (i >= 1) {
-                    double lapl = 0.0;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) lapl = fma(-sp->qe[s], cs_[s * NP + i], lapl);   // :767-771
-                    const double hi = cs.uniform ? cs.dx : cs.dx * (cs.xi[i + 1] - cs.xi[i]);
-                    term = lapl * hi;
-                }
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double v = __shfl_up_sync(FULL, term, o);
-                    if (lane >= o) term += v;
-                }
-                if (i >= 1) gs[i] = cs.g_bulk - (carry + term);
-                carry += __shfl_sync(FULL, term, 31);
+            double am, ap, ac;
+            if (ce.xi) {
+                const double hm = mesh_h(ce, i - 1), hp = mesh_h(ce, i);
+                am = 2.0 / (hm * (hm + hp)); ap = 2.0 / (hp * (hm + hp)); ac = 1.0 / (hm + hp);
+            } else {
+                am = ap = 1.0 / (ce.dx * ce.dx); ac = 1.0 / (2.0 * ce.dx);
             }
-            if (lane == 0) gs[n - 1] = cs.g_bulk;
-            __syncwarp();
-            if (lane == 0) {
-                const WallCoef w = wall_coef(cs);
-                gs[0] = gs[1] + (gs[1] - gs[2]) * w.ext;
+            const double gm = gs[slot - 1], gp = gs[slot + 1];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const double cm = cs_[s * RHS_NP + slot - 1], cp = cs_[s * RHS_NP + slot + 1];
+                double d2;
+                if (!ce.xi) d2 = (cp - 2.0 * c0[s] + cm) * am;                           // :890 (reciprocal hoisted)
+                else d2 = am * cm - (am + ap) * c0[s] + ap * cp;
+                const double dcg = (cp * gp - cm * gm) * ac;                             // :892
+                res[s] = ce.D[s] * (d2 + ce.bF * tb->z[s] * dcg);
+            }
+            // mass-action rates (:159-208): factors by pre-compiled byte offsets into the transposed state
+            const unsigned char* mine = reinterpret_cast<const unsigned char*>(cs_ + slot);
+#pragma unroll 1
+            for (int rr = 0; rr < R; ++rr) {
+                double f = tb->kf[rr], b = tb->kr[rr];
+                const int ne = prog->ne[rr], np = prog->np[rr];
+                const int* po = prog->off[rr];
+#pragma unroll 1
+                for (int e = 0; e < ne; ++e) f *= *reinterpret_cast<const double*>(mine + po[e]);
+#pragma unroll 1
+                for (int e = 0; e < np; ++e) b *= *reinterpret_cast<const double*>(mine + po[MAXRT + e]);
+                const double net = f - b;
+                const double* nur = tb->nu[rr];
+#pragma unroll
+                for (int s = 0; s < S; ++s) res[s] = fma(nur[s], net, res[s]);           // :920-927
+            }
+        }
+        if ((S % 2 == 0) && ((((size_t)o) & 15) == 0)) {
+#pragma unroll
+            for (int s = 0; s + 1 < S; s += 2) *reinterpret_cast<double2*>(o + s) = make_double2(res[s], res[s + 1]);
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) o[s] = res[s];
+        }
+    };
+
+    // node record -> registers, transposed copy, charge term
+    auto load_node = [&](const RhsCell& ce, const double* __restrict__ src, int slot, int i, double (&c0)[S]) {
+        if ((S % 2 == 0) && ((((size_t)src) & 15) == 0)) {
+#pragma unroll
+            for (int s = 0; s + 1 < S; s += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(src + s);
+                c0[s] = v.x; c0[s + 1] = v.y;
             }
         } else {
-            for (int i = lane; i < n; i += 32) gs[i] = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) c0[s] = src[s];
         }
-        __syncwarp();
+        double rho = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            cs_[s * RHS_NP + slot] = c0[s];
+            rho = fma(tb->z[s], c0[s], rho);                                             // :767-771
+        }
+        // g_i = g_{i+1} + (F/eps)*sum z c * h_i for i = n-2..1; nodes 0 and n-1 add nothing
+        term[slot] = (mig && i >= 1 && i <= ce.n - 2) ? rho * ce.Feps * mesh_h(ce, i) : 0.0;
+    };
 
-        // ---- 3. stencil, lane per node
-        for (int i = lane; i < n; i += 32) {
-            double res[S];
-            if (i == n - 1) {
+    auto fill_cell = [&](RhsCell& ce, long long cell, int first) {
+        const int NPAR = 3 * S + 8;
+        const double* p = P.par + (size_t)cell * NPAR;
+        const int n = P.nx[cell];
+        ce.n = (n < 4 || n > nxm) ? 0 : n;                   // bad nx[cell]: the cell is skipped, outputs untouched
+        ce.first = first;
+        const int mid = P.mesh_id ? P.mesh_id[cell] : -1;
+        ce.xi = mid < 0 ? nullptr : P.mesh_xi + (size_t)mid * nxm;
+        const double beta = p[3 * S + 0], eps = p[3 * S + 1];
+        ce.bF = mig ? beta * UNIT_F : 0.0;
+        ce.Feps = UNIT_F / eps;
+        ce.phi_wall = p[3 * S + 2];
+        ce.g_bulk = p[3 * S + 3];
+        ce.dx = p[3 * S + 5];
+        for (int s = 0; s < S; ++s) { ce.J[s] = p[S + s]; ce.D[s] = p[2 * S + s]; }
+    };
+
+    if constexpr (!LARGE) {
+        // ------------------------------------------------------------------ groups of whole cells
+        int G = RHS_NODES / nxm;
+        if (G > RHS_MAXG) G = RHS_MAXG;
+        const long long n_groups = (P.n_cells + G - 1) / G;
+        for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+            const long long cell0 = grp * G;
+            const int gc = (int)((P.n_cells - cell0) < G ? (P.n_cells - cell0) : G);
+            if (tid < gc) fill_cell(cells[tid], cell0 + tid, tid * nxm);
+            __syncthreads();
+            double c0[RHS_ROUNDS][S];
+            int ci[RHS_ROUNDS], ii[RHS_ROUNDS];
 #pragma unroll
-                for (int s = 0; s < S; ++s) res[s] = 0.0;                                // frozen bulk node (:886)
-            } else if (i == 0) {
-                const WallCoef w = wall_coef(cs);
-                const double g1 = gs[1];
-#pragma unroll
-                for (int s = 0; s < S; ++s)
-                    res[s] = (sp->D[s] * ((cs_[s * NP + 2] - cs_[s * NP]) * w.w0 + sp->bq[s] * cs_[s * NP + 1] * g1)
-                              + sp->J[s]) * w.ih0;
-            } else {
-                const NodeCoef k = interior_coef(cs, i);
-                const double gm = gs[i - 1], gp = gs[i + 1];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const double cm = cs_[s * NP + i - 1], cp = cs_[s * NP + i + 1], c0 = cs_[s * NP + i];
-                    double d2, dcg;
-                    if (cs.uniform) {
-                        d2 = (cp - 2.0 * c0 + cm) * cs.u_am;                            // :890 (reciprocal hoisted)
-                        dcg = (cp * gp - cm * gm) * cs.u_ac;                            // :892
-                    } else {
-                        d2 = k.am * cm - (k.am + k.ap) * c0 + k.ap * cp;
-                        dcg = (cp * gp - cm * gm) * k.ac;
-                    }
-                    res[s] = sp->D[s] * (d2 + sp->bq[s] * dcg);
+            for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
+                const int j = tid + rd * RHS_THREADS;
+                const int cg = j / nxm;
+                const int i = j - cg * nxm;
+                const bool valid = cg < gc && i < cells[cg < gc ? cg : 0].n;
+                ci[rd] = valid ? cg : -1; ii[rd] = i;
+                if (valid) load_node(cells[cg], P.c + ((size_t)(cell0 + cg) * nxm + i) * S, j + 1, i, c0[rd]);
+            }
+            __syncthreads();
+            // g per cell: warp-per-cell suffix scan from the bulk (:753-759,793-796)
+            for (int cg = warp; cg < gc; cg += RHS_WARPS) {
+                const RhsCell& ce = cells[cg];
+                const int n = ce.n;
+                if (n == 0) continue;
+                double* gc_ = gs + ce.first + 1;                    // g of this cell, indexed by node
+                const double* tc_ = term + ce.first + 1;
+                double carry = 0.0;
+                for (int top = n - 2; top >= 1; top -= 32) {
+                    const int i = top - lane;
+                    const double t = warp_scan(i >= 1 ? tc_[i] : 0.0, lane);
+                    if (i >= 1) gc_[i] = mig ? ce.g_bulk + (carry + t) : 0.0;
+                    carry += __shfl_sync(FULL, t, 31);
                 }
-                for (int rr = 0; rr < tb->R; ++rr) {
-                    const unsigned ew = *reinterpret_cast<const unsigned*>(tb->ed[rr]);
-                    const unsigned pw = *reinterpret_cast<const unsigned*>(tb->pr[rr]);
-                    const int ne = tb->ned[rr], np = tb->npr[rr];
-                    double f = tb->kf[rr], b = tb->kr[rr];
+                if (lane == 0) gc_[n - 1] = mig ? ce.g_bulk : 0.0;
+                __syncwarp();
+                if (lane == 0) {
+                    const double ext = ce.xi ? mesh_h(ce, 0) / mesh_h(ce, 1) : 1.0;
+                    gc_[0] = mig ? gc_[1] + (gc_[1] - gc_[2]) * ext : 0.0;                       // :796
+                }
+                __syncwarp();
+                if (P.g_out) for (int i = lane; i < n; i += 32) P.g_out[(size_t)(cell0 + cg) * nxm + i] = gc_[i];
+                if (P.phi_out) potential_scan(ce, gc_, P.phi_out + (size_t)(cell0 + cg) * nxm, lane);
+            }
+            __syncthreads();
 #pragma unroll
-                    for (int e = 0; e < MAXRT; ++e) {
-                        if (e < ne) f *= cs_[((ew >> (8 * e)) & 0xff) * NP + i];
-                        if (e < np) b *= cs_[((pw >> (8 * e)) & 0xff) * NP + i];
-                    }
-                    const double net = f - b;
-                    const double* nur = tb->nu[rr];
-#pragma unroll
-                    for (int s = 0; s < S; ++s) res[s] = fma(nur[s], net, res[s]);       // :920-927
+            for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
+                if (ci[rd] >= 0) {
+                    const int j = tid + rd * RHS_THREADS;
+                    node_rhs(cells[ci[rd]], c0[rd], j + 1, ii[rd], P.dcdt + ((size_t)(cell0 + ci[rd]) * nxm + ii[rd]) * S);
                 }
             }
-            double* o = dst + (size_t)i * S;
-            if ((((size_t)o) & 15) == 0) {
+            __syncthreads();
+        }
+    } else {
+        // ------------------------------------------------------------------ tiles of one large cell
+        constexpr int TILE = RHS_NODES - 2;                       // nodes computed per tile (+ one halo node each side)
+        for (long long cell = blockIdx.x; cell < P.n_cells; cell += gridDim.x) {
+            __syncthreads();
+            if (tid == 0) fill_cell(cells[0], cell, 0);
+            __syncthreads();
+            const RhsCell& ce = cells[0];
+            const int n = ce.n;
+            if (n == 0) continue;                                 // block-uniform
+            const double* csrc = P.c + (size_t)cell * nxm * S;
+            double* cdst = P.dcdt + (size_t)cell * nxm * S;
+            const int n_tiles = (n + TILE - 1) / TILE;
+            if (tid == 0) carry_s[0] = mig ? ce.g_bulk : 0.0;
+            // tiles from the bulk end to the wall; tile t covers nodes [a, b]; slot of node i: i - a + 1
+            for (int t = n_tiles - 1; t >= 0; --t) {
+                const int a = t * TILE;
+                const int b = (a + TILE - 1 < n - 1) ? a + TILE - 1 : n - 1;
+                const int lo = a > 0 ? a - 1 : 0, hi = b < n - 1 ? b + 1 : n - 1;     // with halo
+                __syncthreads();
+                double c0[RHS_ROUNDS][S];
+                int ii[RHS_ROUNDS];
 #pragma unroll
-                for (int s = 0; s + 1 < S; s += 2) *reinterpret_cast<double2*>(o + s) = make_double2(res[s], res[s + 1]);
-                if (S & 1) o[S - 1] = res[S - 1];
-            } else {
+                for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
+                    const int i = lo + tid + rd * RHS_THREADS;
+                    ii[rd] = i <= hi ? i : -1;
+                    if (i <= hi) load_node(ce, csrc + (size_t)i * S, i - a + 1, i, c0[rd]);
+                }
+                __syncthreads();
+                // block-wide suffix scan over the nodes hi..lo (reversed index r = hi - i): the carry is g at
+                // node hi (computed by the previous tile, or g_bulk at the bulk end), so node hi adds nothing
+                {
+                    const int M = hi - lo + 1;
+                    const int r0 = 2 * tid, r1 = 2 * tid + 1;
+                    const double t0 = (r0 < M && r0 > 0) ? term[hi - r0 - a + 1] : 0.0;
+                    const double t1 = r1 < M ? term[hi - r1 - a + 1] : 0.0;
+                    const double s2 = warp_scan(t0 + t1, lane);
+                    if (lane == 31) wsum[warp] = s2;
+                    __syncthreads();
+                    double pre = 0.0;
+                    for (int w = 0; w < warp; ++w) pre += wsum[w];
+                    const double base = carry_s[0];
+                    const double incl1 = pre + s2, incl0 = incl1 - t1;
+                    if (r0 < M) gs[hi - r0 - a + 1] = mig ? base + incl0 : 0.0;
+                    if (r1 < M) gs[hi - r1 - a + 1] = mig ? base + incl1 : 0.0;
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (a == 0) {
+                            const double ext = ce.xi ? mesh_h(ce, 0) / mesh_h(ce, 1) : 1.0;
+                            gs[1] = mig ? gs[2] + (gs[2] - gs[3]) * ext : 0.0;                  // g_0 (:796)
+                        }
+                        carry_s[0] = gs[1];                        // g at node a = the next tile's node hi
+                    }
+                    __syncthreads();
+                }
+                if (P.g_out) for (int i = a + tid; i <= b; i += RHS_THREADS) P.g_out[(size_t)cell * nxm + i] = gs[i - a + 1];
 #pragma unroll
-                for (int s = 0; s < S; ++s) o[s] = res[s];
+                for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
+                    const int i = ii[rd];
+                    if (i >= a && i <= b) node_rhs(ce, c0[rd], i - a + 1, i, cdst + (size_t)i * S);
+                }
+            }
+            __syncthreads();
+            if (P.phi_out && P.g_out && warp == 0) {
+                // potential from the g this block has just written (needs g_out): one warp, scan from the wall
+                potential_scan(ce, P.g_out + (size_t)cell * nxm, P.phi_out + (size_t)cell * nxm, lane);
             }
         }
-        if (P.g_out) for (int i = lane; i < n; i += 32) P.g_out[(size_t)cell * nxm + i] = gs[i];
-        if (P.phi_out && lane == 0) {
-            double* po = P.phi_out + (size_t)cell * nxm;
-            double v = cs.phi_wall, vm1 = v, vm2 = v;
-            po[0] = v;
-            for (int i = 1; i <= n - 2; ++i) {
-                const double him = cs.uniform ? cs.dx : cs.dx * (cs.xi[i] - cs.xi[i - 1]);
-                v = v + gs[i] * him;
-                po[i] = v; vm2 = vm1; vm1 = v;
-            }
-            if (n >= 3) {
-                const double ratio = cs.uniform ? 1.0 : (cs.xi[n - 1] - cs.xi[n - 2]) / (cs.xi[n - 2] - cs.xi[n - 3]);
-                po[n - 1] = vm1 + (vm1 - vm2) * ratio;
-            }
-        }
-        __syncwarp();
     }
 }
 
 template <int S>
 int launch_rhs(RhsParams& P, cudaStream_t st) {
-    const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
-    const size_t per_warp = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + rhs_smem_doubles(S, P.tb.nx_max) * sizeof(double);
-    const size_t smem = base + RHS_WARPS * per_warp;
+    const size_t smem = rhs_smem_bytes<S>();
     // per-device launch geometry, queried on every call (a few microseconds; no static state to race on,
     // correct when one process drives several GPUs)
     int dev = 0, sms = 148, max_optin = 0, per_sm = 1;
@@ -196,14 +379,24 @@ int launch_rhs(RhsParams& P, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)max_optin) return CATINT_PNP_EINVAL;
-    cudaFuncSetAttribute(pnp_rhs_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnp_rhs_kernel<S>, RHS_WARPS * 32, smem);
+    const bool large = P.tb.nx_max > RHS_NODES;
+    long long want;
+    if (large) {
+        cudaFuncSetAttribute(pnp_rhs_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnp_rhs_kernel<S, true>, RHS_THREADS, smem);
+        want = P.n_cells;
+    } else {
+        cudaFuncSetAttribute(pnp_rhs_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pnp_rhs_kernel<S, false>, RHS_THREADS, smem);
+        int G = RHS_NODES / P.tb.nx_max;
+        if (G > RHS_MAXG) G = RHS_MAXG;
+        want = (P.n_cells + G - 1) / G;
+    }
     if (per_sm < 1) per_sm = 1;
-    const long long cached_blocks = (long long)sms * per_sm;
-    const long long cap = cached_blocks;                      // one resident wave, persistent loop inside
-    const long long want = (P.n_cells + RHS_WARPS - 1) / RHS_WARPS;
+    const long long cap = (long long)sms * per_sm;            // one resident wave, persistent loop inside
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    pnp_rhs_kernel<S><<<grid, RHS_WARPS * 32, smem, st>>>(P);
+    if (large) pnp_rhs_kernel<S, true><<<grid, RHS_THREADS, smem, st>>>(P);
+    else pnp_rhs_kernel<S, false><<<grid, RHS_THREADS, smem, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 

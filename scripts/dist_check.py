@@ -16,13 +16,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
     kw = workloads.c2(n_potentials=21, phi_min=-0.7, phi_max=-1.2)
-    tp = Transport(resultsdir=tempfile.mkdtemp(prefix='dist_r%d_' % rank), **kw)
+    tp = Transport(resultsdir=tempfile.mkdtemp(prefix='dist_r%d_' % rank), **kw)     # rank 0's folder is broadcast
     tp.set_calculator('odeint')
     calc = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', device='cuda:%d' % local)
     res = calc.run()
     batch, _ = build_cell_batch(tp)
     ref = calc.solve_batch(batch)                      # all cells on this rank alone
-    ok = all(np.array_equal(res[k], ref[k]) for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton'))
+    ok = all(np.array_equal(res[k], ref[k]) for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'))
+    ok = ok and res['c'].dtype == ref['c'].dtype and res['status'].dtype == ref['status'].dtype
     print('rank %d/%d: sharded == single-rank: %s, converged %d/%d, CO2(0) first/last %.6f %.6f' % (
         rank, world, ok, int((res['status'] == 0).sum()), batch.B,
         tp.alldata[0]['species']['CO2']['surface_concentration'], tp.alldata[-1]['species']['CO2']['surface_concentration']), flush=True)
