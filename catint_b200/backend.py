@@ -29,6 +29,19 @@ _LIB_NAME = 'libcatint_pnp.so'
 _lib = None
 
 
+MAX_FLUX_EQ, MAX_FLUX_CODE, MAX_FLUX_CONST, MAX_FLUX_PAR = 4, 96, 32, 24
+
+
+class CatintPnpFluxEq(ctypes.Structure):
+    _fields_ = [
+        ('n_eq', ctypes.c_int32), ('n_par', ctypes.c_int32),
+        ('n_code', ctypes.c_int32 * MAX_FLUX_EQ),
+        ('code', (ctypes.c_int32 * MAX_FLUX_CODE) * MAX_FLUX_EQ),
+        ('consts', (ctypes.c_double * MAX_FLUX_CONST) * MAX_FLUX_EQ),
+        ('coef', (ctypes.c_double * MAX_FLUX_EQ) * MAX_SPECIES),
+    ]
+
+
 class CatintPnpShared(ctypes.Structure):
     _fields_ = [
         ('S', ctypes.c_int32), ('nx_max', ctypes.c_int32), ('R', ctypes.c_int32),
@@ -39,12 +52,13 @@ class CatintPnpShared(ctypes.Structure):
         ('kf', ctypes.c_double * MAX_REACTIONS),
         ('kr', ctypes.c_double * MAX_REACTIONS),
         ('nu', (ctypes.c_double * MAX_REACTIONS) * MAX_SPECIES),
+        ('flux_eq', ctypes.POINTER(CatintPnpFluxEq)),
     ]
 
 
 class CatintPnpCells(ctypes.Structure):
     _fields_ = [('par', ctypes.c_void_p), ('nx', ctypes.c_void_p), ('mesh_id', ctypes.c_void_p),
-                ('mesh_xi', ctypes.c_void_p)]
+                ('mesh_xi', ctypes.c_void_p), ('fpar', ctypes.c_void_p)]
 
 
 class CatintPnpControl(ctypes.Structure):
@@ -107,7 +121,8 @@ class CellBatch(object):
     """
 
     def __init__(self, z, reactions, nu, par, nx, nx_max=None, use_migration=True,
-                 poisson_bc=BC_DIRICHLET_WALL_NEUMANN_BULK, mesh_id=None, mesh_xi=None, species=None):
+                 poisson_bc=BC_DIRICHLET_WALL_NEUMANN_BULK, mesh_id=None, mesh_xi=None, species=None,
+                 flux_eq=None, fpar=None):
         self.z = np.asarray(z, dtype=np.int32)
         self.S = len(self.z)
         self.reactions = [(list(e), list(p), float(kf), float(kr)) for (e, p, kf, kr) in reactions]
@@ -123,6 +138,11 @@ class CellBatch(object):
         self.mesh_id = None if mesh_id is None else np.ascontiguousarray(mesh_id, dtype=np.int32)
         self.mesh_xi = None if mesh_xi is None else np.ascontiguousarray(mesh_xi, dtype=np.float64)
         self.species = list(species) if species is not None else None
+        # wall kinetics as expressions (catint_b200/fluxeq.py: FluxEquations) and their per-cell parameters [B, n_par]
+        self.flux_eq = flux_eq
+        self.fpar = None
+        if flux_eq is not None and flux_eq.n_eq > 0:
+            self.fpar = np.ascontiguousarray(fpar, dtype=np.float64).reshape(self.B, len(flux_eq.par_names))
         self.origin = np.arange(self.B)          # cell indices in the batch this one was selected from
         if self.S > MAX_SPECIES or self.R > MAX_REACTIONS:
             raise ValueError('at most %d species and %d reactions' % (MAX_SPECIES, MAX_REACTIONS))
@@ -166,6 +186,22 @@ class CellBatch(object):
             sh.kf[r], sh.kr[r] = kf, kr
             for k in range(self.S):
                 sh.nu[k][r] = float(self.nu[k, r])
+        self._fq_struct = None
+        if self.flux_eq is not None and self.flux_eq.n_eq > 0:
+            fq = CatintPnpFluxEq()
+            fq.n_eq, fq.n_par = self.flux_eq.n_eq, len(self.flux_eq.par_names)
+            for e, prog in enumerate(self.flux_eq.programs):
+                fq.n_code[e] = len(prog.code)
+                for k, w in enumerate(prog.code):
+                    fq.code[e][k] = int(w)
+                for k, v in enumerate(prog.consts):
+                    fq.consts[e][k] = float(v)
+            for k in range(self.S):
+                for e in range(fq.n_eq):
+                    fq.coef[k][e] = float(self.flux_eq.coef[k][e])
+            self._fq_struct = fq                   # keep the host struct alive as long as the shared struct
+            sh.flux_eq = ctypes.pointer(fq)
+            sh._fq_keepalive = fq
         return sh
 
     def select(self, idx):
@@ -179,7 +215,8 @@ class CellBatch(object):
         return CellBatch(self.z, self.reactions, self.nu, self.par[idx], self.nx[idx], nx_max=self.nx_max,
                          use_migration=self.use_migration, poisson_bc=self.poisson_bc,
                          mesh_id=None if self.mesh_id is None else self.mesh_id[idx], mesh_xi=self.mesh_xi,
-                         species=self.species)
+                         species=self.species, flux_eq=self.flux_eq,
+                         fpar=None if self.fpar is None else self.fpar[idx])
 
 
 def stoichiometry(S, reactions, rate_mode='summed'):
@@ -225,14 +262,16 @@ class DeviceBatch(object):
         self.nx = up('nx', batch.nx, torch.int32)
         self.mesh_id = up('mesh_id', batch.mesh_id, torch.int32)
         self.mesh_xi = up('mesh_xi', batch.mesh_xi, torch.float64)
+        self.fpar = up('fpar', batch.fpar if (batch.fpar is not None and batch.fpar.size) else None, torch.float64)
         self.shared = batch.shared_struct()
         self.cells = CatintPnpCells()
         self.cells.par = self.par.data_ptr()
         self.cells.nx = self.nx.data_ptr()
         self.cells.mesh_id = self.mesh_id.data_ptr() if self.mesh_id is not None else None
         self.cells.mesh_xi = self.mesh_xi.data_ptr() if self.mesh_xi is not None else None
+        self.cells.fpar = self.fpar.data_ptr() if self.fpar is not None else None
         self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in
-                             (self.par, self.nx, self.mesh_id, self.mesh_xi) if t is not None)
+                             (self.par, self.nx, self.mesh_id, self.mesh_xi, self.fpar) if t is not None)
 
 
 class PnpBackend(object):

@@ -61,7 +61,13 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
             tp.logger.error('| CI | -- | species set changes along the descriptor grid; cannot batch')
             sys.exit()
         if m.flux_bound is None:
-            tp.logger.error('| CI | -- | flux-equation / catmap fluxes are not available in the FD-PNP backend')
+            tp.logger.error('| CI | -- | catmap fluxes are not available in the FD-PNP backend')
+            sys.exit()
+        if (m.flux_eq is None) != (m0.flux_eq is None) or (m.flux_eq is not None and (
+                [p.code for p in m.flux_eq.programs] != [p.code for p in m0.flux_eq.programs]
+                or [p.consts for p in m.flux_eq.programs] != [p.consts for p in m0.flux_eq.programs]
+                or not np.array_equal(m.flux_eq.coef, m0.flux_eq.coef))):
+            tp.logger.error('| CI | -- | flux equations change along the descriptor grid; cannot batch')
             sys.exit()
     # reaction table (species not transported -- H2O, e- -- drop out, calculator_old.py:169-171)
     reactions = []
@@ -109,6 +115,10 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
     kw = {}
     if mesh is not None:
         kw = dict(mesh_id=np.zeros(B, dtype=np.int32), mesh_xi=np.asarray(mesh, dtype=np.float64)[None, :])
+    if m0.flux_eq is not None:
+        # wall kinetics as expressions of the surface state: programs shared, parameter values per cell
+        kw['flux_eq'] = m0.flux_eq
+        kw['fpar'] = np.array([m.fpar for m in models], dtype=float).reshape(B, len(m0.flux_eq.par_names))
     batch = _be.CellBatch(z, reactions, nu, par, nx, use_migration=m0.use_migration, species=names,
                           poisson_bc=_be.BC_STERN_ROBIN if poisson_bc == 'stern' else _be.BC_DIRICHLET_WALL_NEUMANN_BULK,
                           **kw)

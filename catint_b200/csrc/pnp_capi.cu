@@ -101,6 +101,44 @@ static int build_tables(const CatintPnpShared* sh, DevTables& tb) {
     tb.tbeg[sh->S] = (int8_t)T;
     for (int j = sh->S + 1; j <= MAXS; ++j) tb.tbeg[j] = (int8_t)T;
     tb.T = T;
+    // flux equations: copy and validate the programs (operands in range, stack never under- or overflows)
+    tb.fpar = nullptr;
+    if (sh->flux_eq && sh->flux_eq->n_eq > 0) {
+        const CatintPnpFluxEq& fq = *sh->flux_eq;
+        if (fq.n_eq > CATINT_PNP_MAX_FLUX_EQ || fq.n_par < 0 || fq.n_par > CATINT_PNP_MAX_FLUX_PAR)
+            return fail(CATINT_PNP_EINVAL, "flux equations: n_eq / n_par out of range");
+        for (int e = 0; e < fq.n_eq; ++e) {
+            if (fq.n_code[e] < 1 || fq.n_code[e] > CATINT_PNP_MAX_FLUX_CODE)
+                return fail(CATINT_PNP_EINVAL, "flux equations: program length out of range");
+            int depth = 0;
+            for (int k = 0; k < fq.n_code[e]; ++k) {
+                const int op = fq.code[e][k] & 0xff, arg = fq.code[e][k] >> 8;
+                if (op > 14) return fail(CATINT_PNP_EINVAL, "flux equations: unknown opcode");
+                if (op <= 3) {
+                    if ((op == 0 && (arg < 0 || arg >= CATINT_PNP_MAX_FLUX_CONST)) || (op == 1 && (arg < 0 || arg >= fq.n_par)) ||
+                        (op == 2 && (arg < 0 || arg >= sh->S)))
+                        return fail(CATINT_PNP_EINVAL, "flux equations: operand out of range");
+                    ++depth;
+                } else if (op <= 8) {
+                    if (depth < 2) return fail(CATINT_PNP_EINVAL, "flux equations: malformed program (stack underflow)");
+                    --depth;
+                } else if (depth < 1) {
+                    return fail(CATINT_PNP_EINVAL, "flux equations: malformed program (stack underflow)");
+                }
+                if (depth > CATINT_PNP_MAX_FLUX_STACK) return fail(CATINT_PNP_EINVAL, "flux equations: stack too deep");
+            }
+            if (depth != 1) return fail(CATINT_PNP_EINVAL, "flux equations: malformed program");
+        }
+        tb.fq = fq;
+    }
+    return CATINT_PNP_OK;
+}
+
+// per-cell parameters of the flux equations
+static int attach_fpar(DevTables& tb, const CatintPnpCells* cells) {
+    if (tb.fq.n_eq > 0 && tb.fq.n_par > 0 && !cells->fpar)
+        return fail(CATINT_PNP_EINVAL, "flux equations need cells->fpar");
+    tb.fpar = cells->fpar;
     return CATINT_PNP_OK;
 }
 
@@ -110,11 +148,11 @@ static int block_size_of(const CatintPnpShared* sh) {
 
 static size_t ws_doubles_per_cell(const CatintPnpShared* sh) {
     const size_t NB = (size_t)block_size_of(sh), nxm = (size_t)sh->nx_max;
-    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1[NB][NBP] + (y,psi,zb)[N] (used only when the state
+    // zn[LMAX][N] + ewt[N] + inv[nx][NB][NBP] + la[nx][NB][4] + V0,W1,dJ[NB][NBP] + (y,psi,zb)[N] (used only when the state
     // does not fit in shared memory, always reserved so that the size query is stateless)
     const size_t NBP = NB + (NB & 1);
     const size_t REC = NB * NBP + NB * 4;
-    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 2 * align4(NB * NBP) +
+    size_t d = align4((size_t)LMAX * nxm * NB) + align4(nxm * NB) + align4(nxm * REC) + 3 * align4(NB * NBP) +
                3 * align4(nxm * NB);
     return (d + 15) & ~size_t(15);
 }
@@ -178,6 +216,8 @@ extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCe
     RhsParams P;
     rc = build_tables(sh, P.tb);
     if (rc) return rc;
+    rc = attach_fpar(P.tb, cells);
+    if (rc) return rc;
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
     P.c = c; P.n_cells = n_cells; P.dcdt = dcdt; P.g_out = g_out; P.phi_out = phi_out;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -202,6 +242,8 @@ extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const Catint
     if (!y) return fail(CATINT_PNP_EINVAL, "y is NULL");
     JacParams P;
     rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    rc = attach_fpar(P.tb, cells);
     if (rc) return rc;
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
     P.y = y; P.n_cells = n_cells; P.F = F; P.Lb = Lb; P.Db = Db; P.Ub = Ub;
@@ -232,6 +274,8 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
 
     SolveParams P;
     rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    rc = attach_fpar(P.tb, cells);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "pnp_fluxeq.cuh"
 
 namespace catint {
 
@@ -37,6 +38,9 @@ struct DevTables {
     int8_t tr[MAXT], ti1[MAXT], ti2[MAXT], ti3[MAXT];
     double tcoef[MAXT];
     int8_t tbeg[MAXS + 1];
+    // wall kinetics (flux equations): programs + coefficient table (by value), per-cell parameters (device)
+    const double* fpar;
+    CatintPnpFluxEq fq;
 };
 
 // Per-cell parameters held in registers by every lane (uniform across the warp).
@@ -47,6 +51,7 @@ struct CellScalars {
     double beta, eps;
     double phi_wall, g_bulk, cstern;
     const double* xi;   // normalised mesh row (non-uniform) or nullptr
+    const double* fpar; // this cell's flux-equation parameters or nullptr
     double u_am, u_ac;  // cached uniform-mesh stencil weights 1/dx^2, 1/(2dx)
     double u_sg;        // cached uniform-mesh g-row scale eps/(dx*F)
 };
@@ -54,6 +59,7 @@ struct CellScalars {
 // Per-cell, per-species parameters in shared memory (one copy per warp).
 struct CellSpecies {
     double D[MAXS], q[MAXS], bq[MAXS], cb[MAXS], J[MAXS], qe[MAXS];   // qe = q/eps
+    double Jfix[MAXS];     // the fixed part of the inward wall flux (J = Jfix + flux equations, refreshed per residual)
 };
 
 struct NodeCoef {
@@ -133,6 +139,7 @@ __device__ __forceinline__ void load_cell_scalars(const DevTables& tb, const dou
     const int mid = mesh_id ? mesh_id[cell] : -1;
     cs.uniform = mid < 0;
     cs.xi = mid < 0 ? nullptr : mesh_xi + (size_t)mid * tb.nx_max;
+    cs.fpar = (tb.fq.n_eq > 0 && tb.fpar) ? tb.fpar + (size_t)cell * tb.fq.n_par : nullptr;
     cs.beta = p[3 * S + 0];
     cs.eps = p[3 * S + 1];
     cs.phi_wall = p[3 * S + 2];
@@ -155,6 +162,7 @@ __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par
     const int mid = mesh_id ? mesh_id[cell] : -1;
     cs.uniform = mid < 0;
     cs.xi = mid < 0 ? nullptr : mesh_xi + (size_t)mid * tb.nx_max;
+    cs.fpar = (tb.fq.n_eq > 0 && tb.fpar) ? tb.fpar + (size_t)cell * tb.fq.n_par : nullptr;
     cs.beta = p[3 * S + 0];
     cs.eps = p[3 * S + 1];
     cs.phi_wall = p[3 * S + 2];
@@ -167,6 +175,7 @@ __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par
     if (lane < S) {
         sp->cb[lane] = p[lane];
         sp->J[lane] = p[S + lane];
+        sp->Jfix[lane] = p[S + lane];
         sp->D[lane] = p[2 * S + lane];
         const double q = tb.z[lane] * UNIT_F;
         sp->q[lane] = q;

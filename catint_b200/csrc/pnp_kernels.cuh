@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     ws.fac = g;                g += align4((size_t)nxm * fac_rec<NB, ST>());
     ws.V0 = g;                 g += align4((size_t)NB * NBP);
     ws.W1 = g;                 g += align4((size_t)NB * NBP);
+    ws.dJ = g;                 g += align4((size_t)NB * NBP);
     ws.psi = g;                g += align4((size_t)nxm * NB);
     ws.ring = ws.scratch + scratch_doubles<NB, ST>();
     double* sdyn = cellbase + WARPD;
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     }
     __syncwarp();
     consistent_field<NB, ST>(ws, ws.y);
+    refresh_wall_flux<NB, ST>(ws, ws.y);
 
     const double rtol = P.rtol, atol = P.atol;
 
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                 B.qwait = LONG_WAIT;
                 for (int idx = vlane; idx < N; idx += vstride) ws.y[idx] = ws.zn[idx];
                 __syncwarp();
+                refresh_wall_flux<NB, ST>(ws, ws.y);
                 for (int idx = vlane; idx < N; idx += vstride) {
                     const int i = idx / NB, r = idx - i * NB;
                     const bool mass = r < S && i < n - 1;
@@ -894,6 +897,7 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     const int n = ws.cs.n, nxm = P.tb.nx_max;
     if (n < 4 || n > nxm) return;                        // bad nx[cell]: skip, outputs untouched
     const double* y = P.y + (size_t)cell * nxm * NB;
+    refresh_wall_flux<NB, ST>(ws, y);
     double* sl = ws.scratch + 2 * (NB + 2);
     double* sa = sl + NB; double* sud = sa + NB; double* sua = sud + NB;
     for (int i = 0; i < n; ++i) {
@@ -914,6 +918,16 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
                 for (int r = 0; r < NB; ++r) {
                     if (r == j) { Dcol[r] = sa[r]; Ucol[r] = sud[r]; Lcol[r] = sl[r]; }   // Lcol = extra block (0,2)
                     if (j == S && r < S) Ucol[r] = sua[r];
+                }
+                if (tb->fq.n_eq > 0 && j < S) {
+                    // flux equations: dF_r/dc_j(0) += ih0*dJ_r/dc_j(0)
+                    const double ih0 = wall_coef(ws.cs).ih0;
+                    for (int e = 0; e < tb->fq.n_eq; ++e) {
+                        double ge = 0.0;
+                        fluxeq_eval(&tb->fq, e, ws.cs.fpar, y, ws.cs.phi_wall, j, S, &ge);
+#pragma unroll
+                        for (int r = 0; r < S; ++r) Dcol[r] += ih0 * tb->fq.coef[r][e] * ge;
+                    }
                 }
             } else if (i == n - 1) {
 #pragma unroll

@@ -40,7 +40,7 @@ constexpr int RHS_ROUNDS = RHS_NODES / RHS_THREADS;
 constexpr int RHS_NP = RHS_NODES + 3;          // odd pitch of the transposed state (slot = node + 1)
 constexpr int RHS_MAXG = 16;                   // cells per group (tiny grids use fewer slots)
 #ifndef CATINT_RHS_MINB
-#define CATINT_RHS_MINB 3                      // resident blocks per SM the register allocation aims at
+#define CATINT_RHS_MINB 2                      // resident blocks per SM the register allocation aims at
 #endif
 
 // per-cell constants of the cells of a group (shared memory)
@@ -48,7 +48,9 @@ struct RhsCell {
     double D[MAXS], J[MAXS];
     double bF, Feps;            // beta*F (0 without migration), F/eps
     double dx, g_bulk, phi_wall;
+    double u_am, u_ac;          // uniform mesh: 1/dx^2, 1/(2dx) (the divisions are done once per cell)
     const double* xi;           // normalised mesh row or nullptr (uniform)
+    const double* fpar;         // flux-equation parameters of the cell or nullptr
     int n, first;               // nodes (0: cell skipped, bad nx), first node slot of this cell in the group
 };
 
@@ -62,7 +64,7 @@ template <int S>
 __host__ __device__ inline size_t rhs_smem_bytes() {
     size_t b = (sizeof(DevTables) + 15) & ~size_t(15);
     b += (sizeof(RhsProg) + 15) & ~size_t(15);
-    b += sizeof(RhsCell) * RHS_MAXG;
+    b += sizeof(RhsCell) * 2 * RHS_MAXG;            // double-buffered (the next group's cells are filled early)
     b += sizeof(double) * ((size_t)S * RHS_NP + 2 * (RHS_NODES + 4) + 2 * RHS_WARPS + 8);
     return b;
 }
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
     }
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     RhsProg* prog = reinterpret_cast<RhsProg*>(smem_raw + off);   off += (sizeof(RhsProg) + 15) & ~size_t(15);
-    RhsCell* cells = reinterpret_cast<RhsCell*>(smem_raw + off);  off += sizeof(RhsCell) * RHS_MAXG;
+    RhsCell* cells_all = reinterpret_cast<RhsCell*>(smem_raw + off);  off += sizeof(RhsCell) * 2 * RHS_MAXG;
     double* cs_ = reinterpret_cast<double*>(smem_raw + off);      // [S][RHS_NP] transposed state, slot = node + 1
     double* term = cs_ + (size_t)S * RHS_NP;                      // [RHS_NODES + 4] (F/eps)*sum z c * h_i per slot
     double* gs = term + RHS_NODES + 4;                            // [RHS_NODES + 4] g per slot
@@ -153,19 +155,30 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
         } else if (i == 0) {
             double w0, ih0;
             if (ce.xi) { const double h0 = mesh_h(ce, 0), h1 = mesh_h(ce, 1); w0 = 1.0 / (h0 + h1); ih0 = 1.0 / h0; }
-            else { w0 = 1.0 / (2.0 * ce.dx); ih0 = 2.0 * w0; }
+            else { w0 = ce.u_ac; ih0 = 2.0 * ce.u_ac; }
             const double g1 = gs[slot + 1];
+            double Jw[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) Jw[s] = ce.J[s];
+            if (tb->fq.n_eq > 0) {
+                // flux equations (pnp_fluxeq.cuh): J = J_fixed + sum_e coef[.][e]*E_e(c(0), phi_wall)
+                for (int e = 0; e < tb->fq.n_eq; ++e) {
+                    const double E = fluxeq_eval(&tb->fq, e, ce.fpar, c0, ce.phi_wall, -1, S, nullptr);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) Jw[s] = fma(tb->fq.coef[s][e], E, Jw[s]);
+                }
+            }
 #pragma unroll
             for (int s = 0; s < S; ++s)                                                  // :902-909, inward flux
                 res[s] = (ce.D[s] * ((cs_[s * RHS_NP + slot + 2] - c0[s]) * w0
-                                     + ce.bF * tb->z[s] * cs_[s * RHS_NP + slot + 1] * g1) + ce.J[s]) * ih0;
+                                     + ce.bF * tb->z[s] * cs_[s * RHS_NP + slot + 1] * g1) + Jw[s]) * ih0;
         } else {
             double am, ap, ac;
             if (ce.xi) {
                 const double hm = mesh_h(ce, i - 1), hp = mesh_h(ce, i);
                 am = 2.0 / (hm * (hm + hp)); ap = 2.0 / (hp * (hm + hp)); ac = 1.0 / (hm + hp);
             } else {
-                am = ap = 1.0 / (ce.dx * ce.dx); ac = 1.0 / (2.0 * ce.dx);
+                am = ap = ce.u_am; ac = ce.u_ac;
             }
             const double gm = gs[slot - 1], gp = gs[slot + 1];
 #pragma unroll
@@ -189,9 +202,13 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
 #pragma unroll 1
                 for (int e = 0; e < np; ++e) b *= *reinterpret_cast<const double*>(mine + po[MAXRT + e]);
                 const double net = f - b;
-                const double* nur = tb->nu[rr];
+                const double2* nur = reinterpret_cast<const double2*>(tb->nu[rr]);   // 16-byte aligned rows (MAXS even)
 #pragma unroll
-                for (int s = 0; s < S; ++s) res[s] = fma(nur[s], net, res[s]);           // :920-927
+                for (int s = 0; s < S; s += 2) {                                         // :920-927
+                    const double2 nn = nur[s / 2];
+                    res[s] = fma(nn.x, net, res[s]);
+                    if (s + 1 < S) res[s + 1] = fma(nn.y, net, res[s + 1]);
+                }
             }
         }
         if ((S % 2 == 0) && ((((size_t)o) & 15) == 0)) {
@@ -203,8 +220,8 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
         }
     };
 
-    // node record -> registers, transposed copy, charge term
-    auto load_node = [&](const RhsCell& ce, const double* __restrict__ src, int slot, int i, double (&c0)[S]) {
+    // node record -> registers
+    auto fetch_node = [&](const double* __restrict__ src, double (&c0)[S]) {
         if ((S % 2 == 0) && ((((size_t)src) & 15) == 0)) {
 #pragma unroll
             for (int s = 0; s + 1 < S; s += 2) {
@@ -215,6 +232,9 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
 #pragma unroll
             for (int s = 0; s < S; ++s) c0[s] = src[s];
         }
+    };
+    // registers -> transposed copy + charge term
+    auto publish_node = [&](const RhsCell& ce, int slot, int i, const double (&c0)[S]) {
         double rho = 0.0;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -225,6 +245,11 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
         term[slot] = (mig && i >= 1 && i <= ce.n - 2) ? rho * ce.Feps * mesh_h(ce, i) : 0.0;
     };
 
+    auto load_node = [&](const RhsCell& ce, const double* __restrict__ src, int slot, int i, double (&c0)[S]) {
+        fetch_node(src, c0);
+        publish_node(ce, slot, i, c0);
+    };
+
     auto fill_cell = [&](RhsCell& ce, long long cell, int first) {
         const int NPAR = 3 * S + 8;
         const double* p = P.par + (size_t)cell * NPAR;
@@ -233,26 +258,47 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
         ce.first = first;
         const int mid = P.mesh_id ? P.mesh_id[cell] : -1;
         ce.xi = mid < 0 ? nullptr : P.mesh_xi + (size_t)mid * nxm;
+        ce.fpar = (tb->fq.n_eq > 0 && tb->fpar) ? tb->fpar + (size_t)cell * tb->fq.n_par : nullptr;
         const double beta = p[3 * S + 0], eps = p[3 * S + 1];
         ce.bF = mig ? beta * UNIT_F : 0.0;
         ce.Feps = UNIT_F / eps;
         ce.phi_wall = p[3 * S + 2];
         ce.g_bulk = p[3 * S + 3];
         ce.dx = p[3 * S + 5];
+        ce.u_am = 1.0 / (ce.dx * ce.dx);
+        ce.u_ac = 1.0 / (2.0 * ce.dx);
         for (int s = 0; s < S; ++s) { ce.J[s] = p[S + s]; ce.D[s] = p[2 * S + s]; }
     };
 
     if constexpr (!LARGE) {
         // ------------------------------------------------------------------ groups of whole cells
+        // Software pipeline: while group g is scanned and computed, the node records of group g+1 are already
+        // in flight into registers and its cell constants are being filled into the other cell buffer, so
+        // the DRAM latency of one group hides behind the arithmetic of the previous one.
         int G = RHS_NODES / nxm;
         if (G > RHS_MAXG) G = RHS_MAXG;
         const long long n_groups = (P.n_cells + G - 1) / G;
-        for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        double c0[RHS_ROUNDS][S], cn[RHS_ROUNDS][S];
+        int buf = 0;
+        auto prefetch = [&](long long grp, int b) {
             const long long cell0 = grp * G;
             const int gc = (int)((P.n_cells - cell0) < G ? (P.n_cells - cell0) : G);
-            if (tid < gc) fill_cell(cells[tid], cell0 + tid, tid * nxm);
-            __syncthreads();
-            double c0[RHS_ROUNDS][S];
+            if (tid < gc) fill_cell(cells_all[b * RHS_MAXG + tid], cell0 + tid, tid * nxm);
+#pragma unroll
+            for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
+                const int j = tid + rd * RHS_THREADS;
+                const int cg = j / nxm;
+                // padding nodes (i >= nx[cell]) are fetched too (inside the cell's slice) and dropped later
+                if (cg < gc) fetch_node(P.c + ((size_t)cell0 * nxm + j) * S, cn[rd]);
+            }
+        };
+        long long grp = blockIdx.x;
+        if (grp < n_groups) prefetch(grp, buf);
+        for (; grp < n_groups; grp += gridDim.x) {
+            RhsCell* cells = cells_all + buf * RHS_MAXG;
+            const long long cell0 = grp * G;
+            const int gc = (int)((P.n_cells - cell0) < G ? (P.n_cells - cell0) : G);
+            __syncthreads();                       // cells[] of this group visible; everyone is done with the shared state
             int ci[RHS_ROUNDS], ii[RHS_ROUNDS];
 #pragma unroll
             for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
@@ -261,9 +307,12 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                 const int i = j - cg * nxm;
                 const bool valid = cg < gc && i < cells[cg < gc ? cg : 0].n;
                 ci[rd] = valid ? cg : -1; ii[rd] = i;
-                if (valid) load_node(cells[cg], P.c + ((size_t)(cell0 + cg) * nxm + i) * S, j + 1, i, c0[rd]);
+#pragma unroll
+                for (int s = 0; s < S; ++s) c0[rd][s] = cn[rd][s];
+                if (valid) publish_node(cells[cg], j + 1, i, c0[rd]);
             }
             __syncthreads();
+            if (grp + gridDim.x < n_groups) prefetch(grp + gridDim.x, buf ^ 1);
             // g per cell: warp-per-cell suffix scan from the bulk (:753-759,793-796)
             for (int cg = warp; cg < gc; cg += RHS_WARPS) {
                 const RhsCell& ce = cells[cg];
@@ -296,16 +345,16 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                     node_rhs(cells[ci[rd]], c0[rd], j + 1, ii[rd], P.dcdt + ((size_t)(cell0 + ci[rd]) * nxm + ii[rd]) * S);
                 }
             }
-            __syncthreads();
+            buf ^= 1;
         }
     } else {
         // ------------------------------------------------------------------ tiles of one large cell
         constexpr int TILE = RHS_NODES - 2;                       // nodes computed per tile (+ one halo node each side)
         for (long long cell = blockIdx.x; cell < P.n_cells; cell += gridDim.x) {
             __syncthreads();
-            if (tid == 0) fill_cell(cells[0], cell, 0);
+            if (tid == 0) fill_cell(cells_all[0], cell, 0);
             __syncthreads();
-            const RhsCell& ce = cells[0];
+            const RhsCell& ce = cells_all[0];
             const int n = ce.n;
             if (n == 0) continue;                                 // block-uniform
             const double* csrc = P.c + (size_t)cell * nxm * S;

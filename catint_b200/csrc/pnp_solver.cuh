@@ -36,6 +36,7 @@ struct WarpState {
     double* fac;    // per node record [ inv_i: NB x NBP | per row l, a (A_L), ud, ua (A_U): NB x 4 ]  (global)
     double* W1;     // inv_1*A_U1' (dense because of the wall block)   [NB][NBP]
     double* V0;     // inv_0*A_E                           [NB][NBP]
+    double* dJ;     // flux equations: dJ_r/dc_j(0), dJ_r/dphi(0)   [S][S+1]  (global)
     double* ring;   // shared: node records staged by cp.async ahead of the sweeps (+ weights, history chunks)
     double* scratch;            // shared, per warp
     const CellSpecies* sp;      // shared, per warp
@@ -345,6 +346,50 @@ struct RecordFeed {
 };
 
 // ---------------------------------------------------------------------------
+// Flux equations (pnp_fluxeq.cuh): the inward wall flux J = Jfix + sum_e coef[.][e]*E_e(c(0), phi(0)) of the
+// current iterate, refreshed in the per-warp species table before every residual evaluation; lane r owns J_r.
+// Out of line, plain arguments: models without flux equations (the common case) only pay a uniform test.
+static __device__ __noinline__ void fluxeq_refresh(const DevTables* tb, const double* fpar, const double* y0,
+                                                   double phi0, int S, int lane, CellSpecies* sp) {
+    double add = 0.0;
+    for (int e = 0; e < tb->fq.n_eq; ++e) {
+        const double E = fluxeq_eval(&tb->fq, e, fpar, y0, phi0, -1, S, nullptr);
+        if (lane < S) add += tb->fq.coef[lane][e] * E;
+    }
+    if (lane < S) sp->J[lane] = sp->Jfix[lane] + add;
+    __syncwarp();
+}
+
+// dJ_r/dy_0 for the wall block of the Newton matrix -> dJ[r*(S+1) + comp]; lane = component comp
+// (0..S-1: c_comp(0), S: phi(0))
+static __device__ __noinline__ void fluxeq_jacobian(const DevTables* tb, const double* fpar, const double* y0,
+                                                    double phi0, int S, int lane, double* dJ) {
+    for (int r = 0; r < S; ++r) {
+        double col = 0.0;
+        for (int e = 0; e < tb->fq.n_eq; ++e) {
+            double g = 0.0;
+            fluxeq_eval(&tb->fq, e, fpar, y0, phi0, lane, S, &g);
+            col = fma(tb->fq.coef[r][e], g, col);
+        }
+        if (lane <= S) dJ[r * (S + 1) + lane] = col;
+    }
+}
+
+template <int NB, bool ST>
+__device__ __forceinline__ void refresh_wall_flux(const WarpState<NB, ST>& ws, const double* y) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    if (ws.tb->fq.n_eq <= 0) return;
+    fluxeq_refresh(ws.tb, ws.cs.fpar, y, ST ? y[S + 1] : ws.cs.phi_wall, S, ws.lane, const_cast<CellSpecies*>(ws.sp));
+}
+
+template <int NB, bool ST>
+__device__ __forceinline__ void wall_flux_jacobian(const WarpState<NB, ST>& ws, const double* y) {
+    constexpr int S = NB - 1 - (ST ? 1 : 0);
+    if (ws.tb->fq.n_eq <= 0) return;
+    fluxeq_jacobian(ws.tb, ws.cs.fpar, y, ST ? y[S + 1] : ws.cs.phi_wall, S, ws.lane, ws.dJ);
+}
+
+// ---------------------------------------------------------------------------
 // Twisted block factorisation of the Newton matrix, BOTH halves at once: the lower half warp
 // (lanes 0..15) eliminates the nodes 0..mid downwards, the upper half warp (lanes 16..31) the nodes
 // n-1..mid+1 upwards, in the same instruction stream.  Inside a half warp (l = lane & 15):
@@ -405,6 +450,15 @@ __device__ __forceinline__ bool eliminate_pair(const WarpState<NB, ST>& ws, doub
             for (int r = 0; r < NB; ++r)
                 if (r == j) A[r] = (j < S ? inv_gamma : 0.0) - C_A(r);
             if (ST && j == S) A[NB - 1] = ws.cs.eps / ws.cs.cstern;             // -dF_phi/dg_0 (Robin row)
+            if (ws.tb->fq.n_eq > 0) {
+                // flux equations: -dF_r/dy_0 = -ih0*dJ_r/dy_0 makes the wall block dense
+                const int comp = j < S ? j : ((ST && j == NB - 1) ? S : -1);
+                if (comp >= 0) {
+                    const double ih0 = wall_coef(ws.cs).ih0;
+#pragma unroll
+                    for (int r = 0; r < S; ++r) A[r] -= ih0 * __ldcg(ws.dJ + r * (S + 1) + comp);
+                }
+            }
         } else if (isG) {
 #pragma unroll
             for (int r = 0; r < NB; ++r) A[r] = r < S ? -C_UA(r) : -C_UD(r);
@@ -559,6 +613,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
     const bool mig = ws.tb->use_migration;
     const double* y = ws.y;
 
+    wall_flux_jacobian<NB, ST>(ws, y);            // flux equations: dJ/dy_0 for the wall block (no-op without them)
     // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
     for (int item = lane; item < n * NB; item += 32) {
         const int i = item / NB, r = item - i * NB;
@@ -617,6 +672,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     const int n = ws.cs.n;
     const DevTables& tb = *ws.tb;
     const double* y = ws.y;
+    refresh_wall_flux<NB, ST>(ws, y);
     for (int i = ws.lane; i < n; i += 32) {
         const double* y0 = y + (size_t)i * NB;
         double* out = ws.zb + (size_t)i * NB;

@@ -257,7 +257,7 @@ def _solve_bulk_equilibria(species, unknowns, eq_names, library, constraints, el
 
 
 def derive_model(species_in, electrode_reactions_in, electrolyte_reactions_in, system_in, pb_bound_in,
-                 nx_in, logger, tables, quiet=False):
+                 nx_in, logger, tables, quiet=False, flux_env=None):
     """dicts -> DerivedModel.  Pure: inputs are deep-copied.  Follows the
     order of operations of the reference constructor (transport.py:183-509),
     which matters (e.g. the bulk_pH override happens after charge neutrality)."""
@@ -504,7 +504,13 @@ def derive_model(species_in, electrode_reactions_in, electrolyte_reactions_in, s
 
     # ---- boundary fluxes (transport.py:929-1095) ------------------------
     m.use_catmap = False
-    _derive_fluxes(m, species, system, exclude, fatal, info)
+    m.flux_eq = None
+    m.fpar = None
+    eq_owners = [sp for sp in species if 'flux-equation' in species[sp]]
+    if not eq_owners or not m.use_electrode_reactions:
+        _derive_fluxes(m, species, system, exclude, fatal, info)
+    else:
+        _derive_flux_equations(m, species, system, exclude, fatal, info, eq_owners, flux_env)
 
     m.species = species
     m.system = system
@@ -522,7 +528,12 @@ def derive_model(species_in, electrode_reactions_in, electrolyte_reactions_in, s
             m.pb_bound[kind][side] = val
     m.boundary_type = 'flux'
     fluxes_numeric = not any(isinstance(species[sp]['flux'], str) for sp in species)
-    if fluxes_numeric:
+    if m.flux_eq is not None:
+        # flux equations: flux_bound carries the FIXED part, the expressions are evaluated by the solver backend
+        fb = np.zeros([m.nspecies, 2])
+        fb[:, 0] = m.flux_fixed
+        m.flux_bound = fb
+    elif fluxes_numeric:
         fb = np.zeros([m.nspecies, 2])
         fb[:, 0] = [species[sp]['flux'] for sp in species]
         m.flux_bound = fb
@@ -636,6 +647,42 @@ def _derive_fluxes(m, species, system, exclude, fatal, info):
             species[sp]['flux'] = '0.0' if symbolic else 0.0
 
 
+def _derive_flux_equations(m, species, system, exclude, fatal, info, eq_owners, flux_env):
+    """species[sp]['flux-equation'] (docs/source/topics/flux_definition.rst:100-156): the flux of the owner is
+    the expression RF*flux_factor*(...) (comsol_model.py:1000), the fluxes of the other reactants follow from
+    the stoichiometry (transport.py:1057-1087).  That propagation is linear in the given fluxes, so it is run
+    numerically (same code as for fixed fluxes) once with all expressions at zero -- the fixed part -- and once
+    per expression at one: J = fixed + sum_e coef[:, e]*E_e.  The expressions are compiled for the device."""
+    from .fluxeq import FluxEquations, FluxEqError, parameter_values
+    params, variables = flux_env if flux_env is not None else ({}, {})
+    names = list(species)
+
+    def propagate(values):
+        sp2 = copy.deepcopy(species)
+        for o in eq_owners:
+            sp2[o].pop('flux-equation')
+            sp2[o]['flux'] = values[o]
+        _derive_fluxes(m, sp2, system, exclude, fatal, lambda *a: None)
+        return np.array([float(sp2[s]['flux']) for s in names])
+
+    fixed = propagate({o: 0.0 for o in eq_owners})
+    fe = FluxEquations(names)
+    coef = np.zeros((len(names), len(eq_owners)))
+    try:
+        for e, o in enumerate(eq_owners):
+            coef[:, e] = propagate({oo: (1.0 if oo == o else 0.0) for oo in eq_owners}) - fixed
+            fe.add(o, 'RF*flux_factor*(' + species[o]['flux-equation'] + ')', variables)
+        fe.coef = coef
+        m.fpar = np.array(parameter_values(fe.par_names, system, params, m), dtype=float)
+    except FluxEqError as err:
+        fatal(str(err))
+    m.flux_eq = fe
+    m.flux_fixed = fixed
+    for k, sp in enumerate(names):
+        species[sp]['flux'] = species[sp]['flux-equation'] if sp in eq_owners else float(fixed[k])
+    info('Fluxes of {} are given as flux equations, evaluated on the surface state by the solver'.format(eq_owners))
+
+
 # ----------------------------------------------------------------------
 class Transport(object):
 
@@ -666,6 +713,13 @@ class Transport(object):
             electrolyte_reactions=copy.deepcopy(electrolyte_reactions), system=copy.deepcopy(system),
             pb_bound=copy.deepcopy(pb_bound), nx=nx)
         self._tables = self._load_tables()
+        # parameters / variables flux equations may refer to (the reference's comsol_args, comsol_model.py:962-978)
+        ca = comsol_args if comsol_args is not None else {}
+        variables = {}
+        for key in ('global_variables', 'boundary_variables'):
+            for name, val in (ca.get(key, None) or {}).items():
+                variables[name] = val[0] if isinstance(val, (list, tuple)) else val
+        self._flux_env = (dict(ca.get('parameter', None) or {}), variables)
 
         model = self.derive_for(_quiet=False)
         self._adopt(model)
@@ -777,7 +831,7 @@ class Transport(object):
                      'electrolyte_reactions', 'electrode_reactions', 'product_list', 'educt_list',
                      'electrolyte_list', 'ionic_strength', 'debye_length', 'xmax', 'dx', 'xmesh', 'nx',
                      'use_catmap', 'c0', 'pb_bound', 'boundary_type', 'flux_bound', 'dc_dt_bound',
-                     'efield_bound'):
+                     'efield_bound', 'flux_eq', 'fpar'):
             setattr(self, name, getattr(m, name))
         if hasattr(m, 'boundary_thickness'):
             self.boundary_thickness = m.boundary_thickness
@@ -821,7 +875,7 @@ class Transport(object):
                         species[sp][key] = float(species[sp][key](view))
         return derive_model(species, self._inputs['electrode_reactions'], self._inputs['electrolyte_reactions'],
                             system, self._inputs['pb_bound'], self._inputs['nx'], self.logger, self._tables,
-                            quiet=_quiet)
+                            quiet=_quiet, flux_env=self._flux_env)
 
     # ------------------------------------------------------------------
     def initialize_descriptors(self, descriptors):

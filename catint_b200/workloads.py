@@ -106,3 +106,28 @@ def c5(n_phi=64, n_scale=64, nx=5000):
 
 C5_FIRST_SPACING = 5e-11
 C5_T_OUT = [1e-6, 1e-3, 1.0, 200.0]
+
+
+def c2_kinetic(n_potentials=1024, phi_min=-0.6, phi_max=-1.15, stern=False):
+    """C2 with the wall kinetics evaluated on the surface state (flux equations) instead of host-side
+    Tafel currents: CO2 reduction first order in the SURFACE CO2 concentration, both reactions with a transfer
+    coefficient of 0.5 (118 mV/decade), -10 / -5 A/m^2 at phiM = -0.9 V and bulk composition.  With the Stern
+    boundary (`stern=True`, use Calculator(..., poisson_bc='stern')) the driving force is the potential drop
+    across the Stern layer, phiM - phi(0), as in the reference's docs (flux_definition.rst:108-118).
+    Returns (Transport keywords, comsol_args)."""
+    kw = co2r_inputs()
+    drive = '(phiM-phi-phiEq_%s)' if stern else '(phiM-phiEq_%s)'
+    kw['species']['CO'] = {'bulk_concentration': 0.0,
+                           'flux-equation': 'k0_CO*[[CO2]]/conc_std*exp(-alpha*F_const*' + drive % 'CO' + '/RT)'}
+    kw['species']['H2'] = {'bulk_concentration': 0.0,
+                           'flux-equation': 'k0_H2*exp(-alpha*F_const*' + drive % 'H2' + '/RT)'}
+    kw['descriptors'] = {'phiM': list(np.linspace(phi_min, phi_max, n_potentials))}
+    # rate constants: with the Stern boundary the driving force is the (nearly potential-independent, ~ -0.1 V) drop
+    # across the Stern layer, so the constants are chosen to give currents of the same order (-20 / -5 A/m^2)
+    k0 = ('4.0e-6', '4.0e-6') if stern else ('3.2e-13', '6.4e-13')
+    comsol_args = {'parameter': {'k0_CO': [k0[0] + '[mol/m^2/s]', 'CO2R rate constant'],
+                                 'k0_H2': [k0[1] + '[mol/m^2/s]', 'HER rate constant'],
+                                 'alpha': ['0.5', 'transfer coefficient'],
+                                 'phiEq_CO': ['-0.11[V]', 'equilibrium potential CO2R'],
+                                 'phiEq_H2': ['0.0[V]', 'equilibrium potential HER']}}
+    return kw, comsol_args

@@ -98,7 +98,33 @@ typedef struct CatintPnpShared {
        the reference's legacy overwrite semantics is the same formula with another table
        (SURVEY 0-6), so the switch is data, not code.                                             */
     double  nu[CATINT_PNP_MAX_SPECIES][CATINT_PNP_MAX_REACTIONS];
+    const struct CatintPnpFluxEq* flux_eq;             /* HOST pointer or NULL: wall kinetics (below)          */
 } CatintPnpShared;
+
+/* Flux equations (HOST): wall kinetics as expressions of the surface concentrations and the surface potential,
+ * the reference's species[sp]['flux-equation'] (docs/source/topics/flux_definition.rst:100-156,
+ * catint/comsol_model.py:986-1000), which only its COMSOL backend could evaluate.  The inward wall flux becomes
+ *     J_k = par[FLUX + k] + sum_e coef[k][e] * E_e(c(0), phi(0); fpar[cell])
+ * (the stoichiometric propagation of catint/transport.py:1057-1087 is linear, hence the coefficient table).
+ * E_e is a postfix program of int32 words  opcode | operand << 8  evaluated on the device together with its
+ * derivatives (they enter the wall block of the Newton matrix):
+ *     0 CONST i  push consts[e][i]        4 ADD  5 SUB  6 MUL  7 DIV  8 POW  (binary, pop 2 push 1)
+ *     1 PAR i    push fpar[cell][i]       9 NEG 10 EXP 11 LOG 12 SQRT 13 LOG10 14 TANH (unary)
+ *     2 CONC k   push c_k(0)
+ *     3 PHI      push phi(0) (the wall potential with the default Poisson boundary, an unknown with Stern)  */
+#define CATINT_PNP_MAX_FLUX_EQ     4
+#define CATINT_PNP_MAX_FLUX_CODE   96
+#define CATINT_PNP_MAX_FLUX_CONST  32
+#define CATINT_PNP_MAX_FLUX_PAR    24
+#define CATINT_PNP_MAX_FLUX_STACK  16
+typedef struct CatintPnpFluxEq {
+    int32_t n_eq;                                      /* 0: no flux equations                                 */
+    int32_t n_par;                                     /* doubles per cell in CatintPnpCells.fpar              */
+    int32_t n_code[CATINT_PNP_MAX_FLUX_EQ];
+    int32_t code[CATINT_PNP_MAX_FLUX_EQ][CATINT_PNP_MAX_FLUX_CODE];
+    double  consts[CATINT_PNP_MAX_FLUX_EQ][CATINT_PNP_MAX_FLUX_CONST];
+    double  coef[CATINT_PNP_MAX_SPECIES][CATINT_PNP_MAX_FLUX_EQ];
+} CatintPnpFluxEq;
 
 /* offsets inside one cell-parameter record of NPAR = 3*S+8 doubles */
 #define CATINT_PNP_NPAR(S)      (3 * (S) + 8)
@@ -120,6 +146,7 @@ typedef struct CatintPnpCells {
     const int32_t* nx;         /* [B] nodes of each cell (ragged: 101 or 102 for nx=100, SURVEY C-6) */
     const int32_t* mesh_id;    /* [B] row of mesh_xi, or -1 = uniform mesh x_i = i*scale             */
     const double*  mesh_xi;    /* [n_mesh][nx_max] normalised node positions (may be NULL)           */
+    const double*  fpar;       /* [B][flux_eq->n_par] per-cell parameters of the flux equations, or NULL */
 } CatintPnpCells;
 
 /* Integrator control (HOST). */

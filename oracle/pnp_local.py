@@ -149,7 +149,11 @@ class LocalForm(object):
         cg = c * g[:, None]
         F[1:-1, :S] = D * (am * c[:-2] - (am + ap) * c[1:-1] + ap * c[2:]
                            + bq * (cg[2:] - cg[:-2]) * ac) + Rk[1:-1]
-        F[0, :S] = (s.D * ((c[2] - c[0]) * self.w0 + s.beta * s.q * c[1] * g[1]) + s.J) * self.ih0
+        Jw = s.J
+        if s.wall_kinetics is not None:
+            phi0 = y[0, S + 1] if self.stern else s.phi_wall
+            Jw = s.J + s.wall_kinetics(c[0], phi0)
+        F[0, :S] = (s.D * ((c[2] - c[0]) * self.w0 + s.beta * s.q * c[1] * g[1]) + Jw) * self.ih0
         F[n - 1, :S] = s.c_bulk - c[n - 1]            # bulk Dirichlet (frozen node, :886)
         gg = y[:, S]
         if s.use_migration:
@@ -185,6 +189,11 @@ class LocalForm(object):
             Dg[I, :S, :S] += dR[I]
         # wall transport rows
         Dg[0, iS, iS] = -s.D * self.w0 * self.ih0
+        if s.wall_kinetics is not None:
+            dJc, dJphi = s.wall_kinetics.jacobian(c[0], y[0, S + 1] if self.stern else s.phi_wall)
+            Dg[0, :S, :S] += dJc * self.ih0
+            if self.stern:
+                Dg[0, :S, S + 1] += dJphi * self.ih0
         E0[iS, iS] = s.D * self.w0 * self.ih0
         U[0, iS, iS] = s.D * s.beta * s.q * g[1] * self.ih0
         if s.use_migration:

@@ -80,7 +80,7 @@ class PnpSystem(object):
                  rate_mode='summed', use_migration=True,
                  poisson_bc='dirichlet_wall_neumann_bulk',
                  phi_wall=0.0, g_bulk=0.0, phiM=0.0, phiPZC=0.0, C_stern=0.2,
-                 uniform=None):
+                 uniform=None, wall_kinetics=None):
         self.z = np.asarray(z, dtype=float)
         self.q = self.z * UNIT_F
         self.D = np.asarray(D, dtype=float)
@@ -107,6 +107,15 @@ class PnpSystem(object):
         # the reference works with the scalar dx=xmax/nx (transport.py:452)
         self.dx = float(self.h[0])
         self.b = self.S + (2 if poisson_bc == 'stern_robin' else 1)
+        # optional flux equations (oracle/flux_expr.py: WallKinetics): J = self.J + wall_kinetics(c(0), phi(0))
+        self.wall_kinetics = wall_kinetics
+
+    def wall_flux(self, C, v):
+        """inward wall flux of the state C[S,n] (v: potential, only its wall value is used)"""
+        if self.wall_kinetics is None:
+            return self.J
+        phi0 = v[0] if self.use_migration else self.phi_wall
+        return self.J + self.wall_kinetics(C[:, 0], phi0)
 
     # ------------------------------------------------------------------
     def c0_flat(self):
@@ -216,7 +225,7 @@ class PnpSystem(object):
             dC[:, 1:-1] = D * (d2 + bq * dcg) + R[:, 1:-1]                       # :920-927
             # wall node, one-sided stencil reaching node 2, no reaction term (:902-915)
             dC[:, 0] = (self.D * ((C[:, 2] - C[:, 0]) / (2. * dx)
-                                  + self.beta * self.q * C[:, 1] * g[1]) + self.J) / dx
+                                  + self.beta * self.q * C[:, 1] * g[1]) + self.wall_flux(C, v)) / dx
         else:
             h = self.h
             hm = h[:-1][None, :]
@@ -225,7 +234,7 @@ class PnpSystem(object):
             dcg = (Cg[:, 2:] - Cg[:, :-2]) / (hm + hp)
             dC[:, 1:-1] = D * (d2 + bq * dcg) + R[:, 1:-1]
             dC[:, 0] = (self.D * ((C[:, 2] - C[:, 0]) / (h[0] + h[1])
-                                  + self.beta * self.q * C[:, 1] * g[1]) + self.J) / h[0]
+                                  + self.beta * self.q * C[:, 1] * g[1]) + self.wall_flux(C, v)) / h[0]
         dC[:, n - 1] = 0.0                                                       # :886
         if with_field:
             return dC.reshape(-1), v, g, lapl

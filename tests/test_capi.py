@@ -43,8 +43,11 @@ def test_header_cites_the_reference():
 def test_version_and_struct_layout(lib):
     assert lib.catint_pnp_version() >= 100
     # the ctypes mirrors must have the C layout: 6 int32 + 14 int32 + 2*12*4 int32 + 2*12 + 14*12 doubles
-    assert ctypes.sizeof(be.CatintPnpShared) == 4 * (6 + 14 + 96) + 8 * (24 + 168)
-    assert ctypes.sizeof(be.CatintPnpCells) == 4 * ctypes.sizeof(ctypes.c_void_p)
+    # + the host pointer to the flux equations
+    assert ctypes.sizeof(be.CatintPnpShared) == 4 * (6 + 14 + 96) + 8 * (24 + 168) + ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(be.CatintPnpCells) == 5 * ctypes.sizeof(ctypes.c_void_p)
+    # flux equations: 2 + 4 int32, 4 x 96 int32 code words, 4 x 32 constants, 14 x 4 coefficients
+    assert ctypes.sizeof(be.CatintPnpFluxEq) == 4 * (2 + 4 + 4 * 96) + 8 * (4 * 32 + 14 * 4)
     assert ctypes.sizeof(be.CatintPnpControl) == 16 + 32 + ctypes.sizeof(ctypes.c_void_p)
 
 
@@ -55,7 +58,7 @@ def test_workspace_query_is_host_only(lib):
     three = lib.catint_pnp_workspace_bytes(ctypes.byref(sh), 3)
     nb, n = 9, 101
     per_cell = (6 * n * nb + n * nb + n * nb * nb + nb * nb + 3 * n * nb) * 8
-    assert one >= per_cell and three - one == 2 * (one - 64 * 8)
+    assert one >= per_cell and three - one == 2 * (one - be.MAX_OUTPUT_TIMES * 8)
     assert lib.catint_pnp_workspace_bytes(None, 3) == 0
 
 
