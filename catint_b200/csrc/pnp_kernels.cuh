@@ -214,7 +214,7 @@ __device__ void decrease_coef(const Bdf<NB, ST>& B, double* l) {
 // barrier.  ring_doubles<NB,ST>() is the ring's size; small blocks (ring too short) load directly.
 template <int NB, bool ST>
 __host__ __device__ constexpr int ring_doubles() {
-    return RING * (fac_rec<NB, ST>() + 2 * padded<NB, ST>());
+    return RING * SweepRing<NB, ST>::SLOT;
 }
 template <int NB, bool ST, int NARR>
 __host__ __device__ constexpr int stream_depth() {
@@ -339,13 +339,12 @@ __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid,
     double dmax = 0.0, amax = 0.0;
     // twisted factors: both chains advance in the two halves of the warp
     long long t0 = prof_on ? clock64() : 0;
-    forward_solve<NB, ST>(ws, Chain{0, mid, +1}, Chain{n - 1, n - 1 - mid, -1});
+    forward_solve<NB, ST>(ws, mid);
     solve_middle<NB, ST>(ws, mid);
     if (prof_on) pc[2] += clock64() - t0;
     t0 = prof_on ? clock64() : 0;
     apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
-    backward_solve<NB, ST>(ws, scale, Chain{mid - 1, mid, -1}, Chain{mid + 1, n - 1 - mid, +1},
-                           dmax, amax, wmode, prtol, patol);
+    backward_solve<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
     del = warp_max(dmax);
     acn = warp_max(amax);
     if (prof_on) pc[3] += clock64() - t0;

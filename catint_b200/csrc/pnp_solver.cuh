@@ -56,6 +56,9 @@ __host__ __device__ constexpr int padded() { return NB + (NB & 1); }
 // doubles per node of the stored factors: inverse block (padded rows) + 4 coefficients per row
 template <int NB, bool ST>
 __host__ __device__ constexpr int fac_rec() { return NB * padded<NB, ST>() + NB * 4; }
+// position of inv_i[r][c] inside a node record: [chunk c/2][row r] pairs of columns
+template <int NB, bool ST>
+__host__ __device__ constexpr int inv_off(int r, int c) { return ((c >> 1) * NB + r) * 2 + (c & 1); }
 // Node records in flight in the solve sweeps: four per chain (three iterations of look-ahead).  One warp
 // per cell walks two chains (8 slots).
 constexpr int RING_CHAIN = 4;
@@ -296,6 +299,11 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
 }
 __device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
+}
+// predicated copy (no branch): pred != 0 -> copy
+__device__ __forceinline__ void cp_async16_if(unsigned saddr, const void* g, unsigned pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 :: "r"(saddr), "l"(__cvta_generic_to_global(g)), "r"(pred) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -546,9 +554,8 @@ __device__ __forceinline__ bool eliminate_pair(const WarpState<NB, ST>& ws, doub
     // ---- store the inverse, form the W column for the next node ----
     double* rec = ws.fac + (size_t)i * REC;
     if (isD && live) {
-        double* invcol = rec + j;
 #pragma unroll
-        for (int r = 0; r < NB; ++r) invcol[r * NBP] = A[r];
+        for (int r = 0; r < NB; ++r) rec[inv_off<NB, ST>(r, 0) + ((j >> 1) * NB * 2 + (j & 1))] = A[r];
     }
     if (SPECIAL && wall && isD) {
         // V_0 = inv_0*A_E, A_E = diag(-l): needed for the modified A_U of node 1 and by the back substitution
@@ -570,7 +577,7 @@ __device__ __forceinline__ bool eliminate_pair(const WarpState<NB, ST>& ws, doub
             for (int r = 0; r < NB; ++r) {
                 double s_ = 0.0;
 #pragma unroll
-                for (int c = 0; c < NB; ++c) s_ = fma(__ldcg(rec + r * NBP + c), U1[c], s_);
+                for (int c = 0; c < NB; ++c) s_ = fma(__ldcg(rec + inv_off<NB, ST>(r, c)), U1[c], s_);
                 Wp[r] = s_;
             }
             double* w1col = ws.W1 + j;
@@ -730,112 +737,145 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
 }
 
 // ---------------------------------------------------------------------------
-// Solve sweeps with the stored factors.  The node records stream from global memory (L2/HBM)
-// into a shared-memory ring by cp.async, RING-1 nodes ahead of use, so that the sequential
-// chain over the nodes never waits for DRAM.  Lane r (< NB) owns row r.
+// Solve sweeps with the stored factors.  Both chains of the twisted factorisation advance in the same
+// instruction stream: the lower half warp (lanes 0..15) walks the wall-side chain, the upper half warp
+// (lanes 16..31) the bulk-side chain; lane l = lane & 15 (< NB) owns row l of its chain's node.
 //
-// All sweeps take node ranges and directions (Chain): with the twisted factors the lower half warp
-// walks nodes 0..m-1 downwards and the upper half warp nodes n-1..m+1 upwards, node m couples them.
+// The node records stream from global memory (L2/HBM) into a shared-memory ring by cp.async, three
+// iterations ahead of use, so that the sequential chain over the nodes never waits for DRAM.  (Loading the
+// rows straight into registers with a software pipeline does not work: ptxas puts all the loads of all
+// stages on one scoreboard, so the first use waits for the youngest load -- measured 1.8x slower.)
+// Each half warp copies the records of its own chain (lane l: 16-byte chunks l, l+16, ...), with
+// predicated copies instead of branches (unrolling the loop by the ring depth to get immediate slot offsets
+// was measured slower: instruction-cache footprint).  One commit group and one warp barrier per iteration; the barrier
+// publishes the right-hand sides tt (double buffered), makes the NEXT record visible (every lane has
+// just waited for its own copies of it) and tells that all lanes are done with the previous one.  The
+// predecessor's solution travels in registers (own row) and by one shuffle (g row).
 template <int NB, bool ST>
-struct FactorRow {
-    double v[NB];
-    double4 co;      // l, a (A_L) and ud, ua (A_U) of this row
+struct SweepRing {
+    static constexpr int NBP = padded<NB, ST>();
+    static constexpr int REC = fac_rec<NB, ST>();
+    static constexpr int CH = REC / 2;                    // 16-byte chunks per record
+    static constexpr int R16 = (CH + 15) / 16;            // copy rounds of a half warp per record
+    static constexpr int SLOT = R16 * 32 + 2 * NBP;       // doubles per slot: record (padded) | weights | zn0
+    const double* src;                                    // my first chunk of the next record to copy
+    const double* wsrc; const double* zsrc;               // backward sweep: error weight and zn0 of my unknown
+    unsigned dst, wdst;                                   // shared address of my first chunk / my weight in slot (0, grp)
+    int rstride, zstep, left;                             // doubles between records / unknowns; records left to copy
+    unsigned lastp;                                       // copy predicate of the last round
+    bool wl;
+    __device__ __forceinline__ void init(const WarpState<NB, ST>& ws, int first, int dir, int count, bool weights, int r,
+                                         bool rowlane) {
+        const int l = ws.lane & 15, grp = ws.lane >> 4;
+        src = ws.fac + (size_t)first * REC + 2 * l;
+        rstride = dir * REC;
+        zstep = dir * NB;
+        left = count;
+        dst = (unsigned)__cvta_generic_to_shared(ws.ring) + (unsigned)(grp * SLOT * 8 + 16 * l);
+        wdst = (unsigned)__cvta_generic_to_shared(ws.ring) + (unsigned)((grp * SLOT + R16 * 32 + l) * 8);
+        lastp = (l + 16 * (R16 - 1) < CH) ? 1u : 0u;
+        wl = weights && rowlane;
+        wsrc = ws.ewt + (size_t)first * NB + r;
+        zsrc = ws.zn + (size_t)first * NB + r;
+    }
+    // copy the next record of my chain into ring slot `slot` (0..RING_CHAIN-1); past the end of the chain
+    // the last record is copied again (never consumed by a live iteration)
+    __device__ __forceinline__ void issue(int slot) {
+        const unsigned d = dst + (unsigned)(slot * 2 * SLOT * 8);
+#pragma unroll
+        for (int q = 0; q < R16; ++q) {
+            if (q + 1 < R16) cp_async16(d + 256u * q, src + 32 * q);
+            else cp_async16_if(d + 256u * q, src + 32 * q, lastp);
+        }
+        if (wl) {
+            const unsigned dw = wdst + (unsigned)(slot * 2 * SLOT * 8);
+            cp_async8(dw, wsrc);
+            cp_async8(dw + 8u * NBP, zsrc);
+        }
+        cp_commit();
+        --left;
+        if (left > 0) { src += rstride; wsrc += zstep; zsrc += zstep; }
+    }
 };
 
 template <int NB, bool ST>
-__device__ __forceinline__ void ring_row(const WarpState<NB, ST>& ws, int slot, int r, FactorRow<NB, ST>& f) {
-    constexpr int NBP = padded<NB, ST>();
-    const double* rec = ws.ring + (size_t)slot * fac_rec<NB, ST>();
-    const double2* p = reinterpret_cast<const double2*>(rec + r * NBP);
+__device__ __forceinline__ double row_dot(const double2 (&m)[padded<NB, ST>() / 2], const double* tt) {
+    constexpr int H = padded<NB, ST>() / 2;
+    const double2* t2 = reinterpret_cast<const double2*>(tt);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-    for (int c = 0; c < NBP / 2; ++c) {
-        const double2 t = p[c];
-        f.v[2 * c] = t.x;
-        if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
+    for (int c = 0; c < H; ++c) {
+        const double2 t = t2[c];
+        if (c % 3 == 0) s0 = fma(m[c].x, t.x, s0);
+        else if (c % 3 == 1) s1 = fma(m[c].x, t.x, s1);
+        else s2 = fma(m[c].x, t.x, s2);
+        if (2 * c + 1 < NB) {
+            if (c % 3 == 0) s1 = fma(m[c].y, t.y, s1);
+            else if (c % 3 == 1) s2 = fma(m[c].y, t.y, s2);
+            else s0 = fma(m[c].y, t.y, s0);
+        }
     }
-    f.co = reinterpret_cast<const double4*>(rec + NB * NBP)[r];
+    return (s0 + s1) + s2;
 }
 
+// elimination of the right-hand side along both chains (zb <- z):
+//   wall side,  nodes 0..mid-1 upwards:      z_i = inv_i*(rhs_i - A_L z_{i-1})
+//   bulk side,  nodes n-1..mid+1 downwards:  z_i = inv_i*(rhs_i - A_U z_{i+1})
+// (the first node of a chain has no predecessor).  Lanes without a row and the shorter chain in its
+// missing last iteration run the same arithmetic on valid dummy operands and only skip the stores.
 template <int NB, bool ST>
-__device__ __forceinline__ double row_dot(const FactorRow<NB, ST>& f, const double* tt) {
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int c = 0; c < NB; c += 2) {
-        s0 = fma(f.v[c], tt[c], s0);
-        if (c + 1 < NB) s1 = fma(f.v[c + 1], tt[c + 1], s1);
-    }
-    return s0 + s1;
-}
-
-// elimination of the right-hand side along a chain:
-//   dir=+1:  z_i = inv_i*(rhs_i - A_L z_{i-1})      (the first node of a chain has no predecessor
-//   dir=-1:  z_i = inv_i*(rhs_i - A_U z_{i+1})       inside the chain: its coupling term is skipped)
-// zb <- z.  c1.count may be 0 (single chain).  Lanes without a row (r >= NB) and the shorter chain in
-// its missing last iteration run the same arithmetic on valid dummy operands and only skip the stores,
-// so the loop body is free of divergent branches.
-template <int NB, bool ST>
-__device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
+__device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
-    constexpr int REC = fac_rec<NB, ST>();
+    constexpr int H = NBP / 2;
+    constexpr int SLOT = SweepRing<NB, ST>::SLOT;
     static_assert(NB <= 16, "a chain occupies half a warp");
-    const int lane = ws.lane;
-    const int grp = lane >> 4;
-    const int r0 = lane & 15;
-    const bool dual = c1.count > 0;
-    const Chain me = (grp && dual) ? c1 : c0;       // one chain: the upper half warp shadows the lower one
+    const int lane = ws.lane, n = ws.cs.n;
+    const int grp = lane >> 4, r0 = lane & 15;
     const bool rowlane = r0 < NB;
     const int r = rowlane ? r0 : 0;
-    const int iters = max(c0.count, c1.count);
-    constexpr int ahead = RING_CHAIN - 1;                // iterations of look-ahead
-    RecordFeed<NB, ST> feed;
-    feed.init(ws.fac, ws.ring, lane, c0, c1);
-#pragma unroll 1
-    for (int p = 0; p < ahead; ++p) { feed.issue(p); cp_commit(); }
+    const int cnt0 = mid, cnt1 = n - 1 - mid;
+    const int count = grp ? cnt1 : cnt0;
+    const int iters = max(cnt0, cnt1);
+    const int dir = grp ? -1 : 1;
+    const int first = grp ? n - 1 : 0;
+    SweepRing<NB, ST> feed;
+    feed.init(ws, first, dir, count, false, r, rowlane);
+#pragma unroll
+    for (int p = 0; p < RING_CHAIN - 1; ++p) feed.issue(p);
+    // my row of the record in slot (0, grp): chunk c at [c][r]; coupling coefficients (diagonal, g column)
+    // A_L = -(diag l + a e_g^T) on the wall side, A_U = -(diag ud + ua e_g^T) on the bulk side
+    const double2* rowp = reinterpret_cast<const double2*>(ws.ring + grp * SLOT) + r;
+    const double2* cop = reinterpret_cast<const double2*>(ws.ring + grp * SLOT + NB * NBP + 4 * r + (grp ? 2 : 0));
     double* tbuf = ws.scratch + grp * 2 * NBP;           // [parity][NBP] per chain
-    const double* ringrow = ws.ring + r * NBP;
-    const double* ringco = ws.ring + NB * NBP + 4 * r;
-    const int zstep = me.dir * NB;
+    const int zstep = dir * NB;
     const int gsrc = (lane & 16) + S;                    // lane that owns the g component of my chain
-    int zo = me.first * NB + r;                          // this lane's unknown of the current node
+    int zo = first * NB + r;                             // this lane's unknown of the current node
     double zprev = 0.0, zs = 0.0;                        // my row / the g row of the previous node (none at k = 0)
+    double rhs = ws.zb[zo];
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
-    // One warp barrier per iteration: it publishes the right-hand sides tt, makes the NEXT record (whose
-    // copies every lane has just waited for) visible, and tells that all lanes are done with the
-    // previous one.  The predecessor's solution travels in registers (own row) and by shuffle (g row).
-    // The coupling coefficients and the right-hand side of the next node are fetched right after the
-    // barrier, so that no shared-memory latency sits at the head of the next iteration's dependency chain.
-    auto slot_of = [&](int k) { return dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1)); };
-    double4 co = *reinterpret_cast<const double4*>(ringco + slot_of(0) * REC);
-    double rhs = ws.zb[zo];
+    int rs = 0, is = RING_CHAIN - 1, tp = 0;             // ring slot read / refilled in this iteration, tt parity offset
+#pragma unroll 1
     for (int k = 0; k < iters; ++k) {
-        feed.issue(k + ahead);                           // refills the slot of record k-1
-        cp_commit();
-        const bool live = k < me.count;
-        const int slot = slot_of(k);
-        FactorRow<NB, ST> f;
-        {
-            const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
+        feed.issue(is);                                  // refills the slot of record k-1
+        is = (is + 1) & (RING_CHAIN - 1);
+        double2 m[H];
 #pragma unroll
-            for (int c = 0; c < NBP / 2; ++c) {
-                const double2 t = p[c];
-                f.v[2 * c] = t.x;
-                if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
-            }
-        }
-        const double ca = me.dir > 0 ? co.x : co.z;                  // -A_L or -A_U: diagonal ...
-        const double cb = me.dir > 0 ? co.y : co.w;                  // ... and g column
-        const double t = fma(ca, zprev, fma(cb, zs, rhs));
-        double* tt = tbuf + (k & 1) * NBP;
+        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
+        const double2 cf = cop[rs * SLOT];
+        rs = (rs + 1) & (RING_CHAIN - 1);
+        const double t = fma(cf.y, zs, fma(cf.x, zprev, rhs));
+        double* tt = tbuf + tp;
+        tp ^= NBP;
         if (rowlane) tt[r] = t;
         cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 have landed
         __syncwarp();
+        const bool live = k < count;
         const int zo_now = zo;
-        if (k + 1 < me.count) zo += zstep;
-        co = *reinterpret_cast<const double4*>(ringco + slot_of(k + 1) * REC);
+        if (k + 1 < count) zo += zstep;
         rhs = ws.zb[zo];
-        const double z = row_dot<NB, ST>(f, tt);
+        const double z = row_dot<NB, ST>(m, tt);
         if (rowlane && live) ws.zb[zo_now] = z;
         zprev = z;
         zs = __shfl_sync(FULL, z, gsrc);
@@ -844,105 +884,79 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, Chain c0, Chain c1) {
     __syncwarp();
 }
 
-// Back substitution along a chain, the solution of the node before its first node (first-dir) being
-// final already in zb:
-//   dir=-1:  d_i = z_i - inv_i*(A_U d_{i+1})   (node 1: dense W_1; node 0: extra wall block V_0)
-//   dir=+1:  d_i = z_i - inv_i*(A_L d_{i-1})
+// Back substitution along both chains, the solution of the coupling node `mid` being final already in zb:
+//   wall side,  nodes mid-1..0 downwards:   d_i = z_i - inv_i*(A_U d_{i+1})   (node 1: dense W_1; node 0: extra wall block V_0)
+//   bulk side,  nodes mid+1..n-1 upwards:   d_i = z_i - inv_i*(A_L d_{i-1})
 // y += scale*d, zb <- d.  Fused with the weighted max norms of the Newton update (|scale*d|*w)
 // and of the accumulated correction (|y-zn0|*w) over the error-controlled unknowns
 // (concentrations of nodes 0..n-2), accumulated into dmax/amax (per lane, reduce afterwards):
-// the weights and zn0 of each node ride in a second cp.async ring.
-// wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
+// the weight and zn0 of each unknown ride in the ring slot of their node (a lane reads back only what it
+// copied itself).  wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
 template <int NB, bool ST>
-__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Chain c1,
+__device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
                                double& dmax, double& amax, int wmode, double prtol, double patol) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
-    constexpr int REC = fac_rec<NB, ST>();
-    constexpr int R2 = 2 * NBP;                  // doubles per node in the weight ring
-    const int lane = ws.lane;
-    const int n = ws.cs.n;
-    const int grp = lane >> 4;
-    const int r0 = lane & 15;
-    const bool dual = c1.count > 0;
-    const Chain me = (grp && dual) ? c1 : c0;       // one chain: the upper half warp shadows the lower one
+    constexpr int H = NBP / 2;
+    constexpr int SLOT = SweepRing<NB, ST>::SLOT;
+    constexpr int WOFF = SweepRing<NB, ST>::R16 * 32;    // weights / zn0 inside a slot
+    const int lane = ws.lane, n = ws.cs.n;
+    const int grp = lane >> 4, r0 = lane & 15;
     const bool rowlane = r0 < NB;
     const int r = rowlane ? r0 : 0;
-    const int iters = max(c0.count, c1.count);
-    constexpr int ahead = RING_CHAIN - 1;
-    RecordFeed<NB, ST> feed;
-    feed.init(ws.fac, ws.ring, lane, c0, c1);
-    // weight ring: every row lane fetches the weight and zn0 of its own unknown and reads them back
-    // itself (its own wait_group is all the synchronisation that needs)
-    const double* ring2 = ws.ring + (size_t)(dual ? RING : RING_CHAIN) * REC;
-    const bool wl = wmode == 0 && rowlane;
-    const double* wsrc = ws.ewt + (long long)me.first * NB + r;
-    const double* zsrc = ws.zn + (long long)me.first * NB + r;
-    const unsigned wdst = (unsigned)__cvta_generic_to_shared(ring2) + 8u * r;
-    const int wstep = me.dir * NB;
-    auto issue = [&](int k) {
-        feed.issue(k);
-        if (wl && k < me.count) {
-            const int rs = dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1));
-            cp_async8(wdst + (unsigned)(rs * R2 * 8), wsrc);
-            cp_async8(wdst + (unsigned)((rs * R2 + NBP) * 8), zsrc);
-            wsrc += wstep; zsrc += wstep;
-        }
-        cp_commit();
-    };
-#pragma unroll 1
-    for (int p = 0; p < ahead; ++p) issue(p);
+    const int cnt0 = mid, cnt1 = n - 1 - mid;
+    const int count = grp ? cnt1 : cnt0;
+    const int iters = max(cnt0, cnt1);
+    const int dir = grp ? 1 : -1;
+    const int first = grp ? mid + 1 : mid - 1;
+    const bool wl = wmode == 0;
+    SweepRing<NB, ST> feed;
+    feed.init(ws, first, dir, count, wl, r, rowlane);
+#pragma unroll
+    for (int p = 0; p < RING_CHAIN - 1; ++p) feed.issue(p);
+    const double2* rowp = reinterpret_cast<const double2*>(ws.ring + grp * SLOT) + r;
+    const double2* cop = reinterpret_cast<const double2*>(ws.ring + grp * SLOT + NB * NBP + 4 * r + (grp ? 0 : 2));
+    const double* wp = ws.ring + grp * SLOT + WOFF + r;
     double* tbuf = ws.scratch + grp * 2 * NBP;
-    const double* ringrow = ws.ring + r * NBP;
-    const double* ringco = ws.ring + NB * NBP + 4 * r;
-    const int zstep = me.dir * NB;
+    const int zstep = dir * NB;
     const int gsrc = (lane & 16) + S;
-    int zo = me.first * NB + r;
+    int zo = first * NB + r;
     const bool crow = rowlane && r < S;                  // this lane owns a concentration unknown
     // final solution of the node before the chain (the coupling node): my row and its g row
     double dprev = ws.zb[zo - zstep];
     double dg = ws.zb[zo - zstep + (S - r)];
+    double zcur = ws.zb[zo];                             // forward-eliminated value of the current node
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
-    auto slot_of = [&](int k) { return dual ? ((2 * k + grp) & (RING - 1)) : (k & (RING_CHAIN - 1)); };
-    double4 co = *reinterpret_cast<const double4*>(ringco + slot_of(0) * REC);
-    double zcur = ws.zb[zo];                             // forward-eliminated value of the current node
-    for (int k = 0; k < iters; ++k) {                    // one warp barrier per iteration, see forward_solve
-        issue(k + ahead);
-        const bool live = k < me.count;
-        const int i = me.first + me.dir * k;
-        const int slot = slot_of(k);
-        FactorRow<NB, ST> f;
-        {
-            const double2* p = reinterpret_cast<const double2*>(ringrow + slot * REC);
+    int rs = 0, is = RING_CHAIN - 1, tp = 0;
+#pragma unroll 1
+    for (int k = 0; k < iters; ++k) {
+        feed.issue(is);
+        is = (is + 1) & (RING_CHAIN - 1);
+        double2 m[H];
 #pragma unroll
-            for (int c = 0; c < NBP / 2; ++c) {
-                const double2 t = p[c];
-                f.v[2 * c] = t.x;
-                if (2 * c + 1 < NB) f.v[2 * c + 1] = t.y;
-            }
-        }
-        double* tt = tbuf + (k & 1) * NBP;
-        {
-            const double ca = me.dir < 0 ? co.z : co.x;              // A_U (dir<0) or A_L (dir>0)
-            const double cb = me.dir < 0 ? co.w : co.y;
-            if (rowlane) tt[r] = -(ca * dprev + cb * dg);
-        }
-        cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 (and my weights of node k)
+        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
+        const double2 cf = cop[rs * SLOT];
+        double w = 0.0, z0 = 0.0;
+        if (wl) { w = wp[rs * 2 * SLOT]; z0 = wp[rs * 2 * SLOT + NBP]; }
+        rs = (rs + 1) & (RING_CHAIN - 1);
+        double* tt = tbuf + tp;
+        tp ^= NBP;
+        if (rowlane) tt[r] = -fma(cf.x, dprev, cf.y * dg);
+        cp_wait<RING_CHAIN - 2>();                       // my copies of record k+1 (my weights of node k landed earlier)
         __syncwarp();
+        const bool live = k < count;
+        const int i = first + dir * k;
         const int zo_now = zo;
-        if (k + 1 < me.count) zo += zstep;
-        co = *reinterpret_cast<const double4*>(ringco + slot_of(k + 1) * REC);
+        if (k + 1 < count) zo += zstep;
         const double znext = ws.zb[zo];
         const double yold = ws.y[zo_now];
-        double w = 0.0, z0 = 0.0;
-        if (wmode == 0) { w = ring2[slot * R2 + r]; z0 = ring2[slot * R2 + NBP + r]; }
-        double d = zcur - row_dot<NB, ST>(f, tt);
-        // wall side of the upper chain (warp-uniform test): node 1 couples through the dense W_1,
+        double d = zcur - row_dot<NB, ST>(m, tt);
+        // wall end of the wall-side chain (warp-uniform test): node 1 couples through the dense W_1,
         // node 0 has the extra block V_0 towards node 2
-        const int i0 = c0.first + c0.dir * k;
-        if (c0.dir < 0 && i0 <= 1 && k < c0.count) {
-            if ((grp == 0 || !dual) && rowlane) {        // (a shadowing half warp must take the same path)
+        const int i0 = mid - 1 - k;
+        if (i0 <= 1 && i0 >= 0) {
+            if (grp == 0 && rowlane) {
                 const double* d2 = ws.zb + 2 * NB;
                 const double* Mr = (i0 == 1 ? ws.W1 : ws.V0) + (size_t)r * NBP;
                 double s_ = 0.0;
@@ -958,12 +972,12 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, Chain c0, Ch
         dg = __shfl_sync(FULL, d, gsrc);
         zcur = znext;
         {
-            if (wmode != 0) w = 1.0 / (prtol * fabs(yn) + patol);
+            if (!wl) w = 1.0 / (prtol * fabs(yn) + patol);
             double ad = fabs(ds) * w;
             if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
             const bool counted = crow && live && i < n - 1;
             dmax = fmax(dmax, counted ? ad : 0.0);
-            if (wmode == 0) amax = fmax(amax, counted ? fabs(yn - z0) * w : 0.0);
+            if (wl) amax = fmax(amax, counted ? fabs(yn - z0) * w : 0.0);
         }
     }
     cp_wait<0>();
@@ -1008,7 +1022,7 @@ __device__ void solve_middle(WarpState<NB, ST>& ws, int m) {
     double4 co = make_double4(0, 0, 0, 0);
     if (act) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) row[c] = rec[r * NBP + c];
+        for (int c = 0; c < NB; ++c) row[c] = rec[inv_off<NB, ST>(0, c) + 2 * r];
         co = reinterpret_cast<const double4*>(rec + NB * NBP)[r];
         const double* zm = ws.zb + (size_t)(m - 1) * NB;
         const double* zp = ws.zb + (size_t)(m + 1) * NB;
