@@ -18,6 +18,7 @@ BC_DIRICHLET_WALL_NEUMANN_BULK = 0
 BC_STERN_ROBIN = 1
 MODE_TRANSIENT = 0
 MODE_STEADY = 1
+MODE_KEEP_ALL = 0x100   # flag: no elimination of passive species (see include/catint_pnp.h)
 
 CELL_STATUS = {0: 'converged', 1: 'max_steps', 2: 'corrector_failed', 3: 'error_test_failed',
                4: 'not_finite', 5: 'polish_failed', 6: 'step_underflow', 7: 'bad_input'}
@@ -74,7 +75,8 @@ EXPORTS = ['catint_pnp_version', 'catint_pnp_last_error', 'catint_pnp_device_cou
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # CATINT_PNP_LIB: development hook for A/B measurements of variant builds (scripts/build_variant.sh)
+    return os.environ.get('CATINT_PNP_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library():

@@ -57,6 +57,8 @@ static int build_tables(const CatintPnpShared* sh, DevTables& tb) {
     if (sh->R < 0 || sh->R > CATINT_PNP_MAX_REACTIONS) return fail(CATINT_PNP_EINVAL, "R out of range");
     if (sh->nx_max < 4) return fail(CATINT_PNP_EINVAL, "nx_max must be >= 4");
     tb.S = sh->S; tb.R = sh->R; tb.nx_max = sh->nx_max;
+    tb.S_full = sh->S; tb.npas = 0;
+    for (int k = 0; k < MAXS; ++k) tb.cmap[k] = (int8_t)k;
     tb.stern = sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN;
     tb.use_migration = sh->use_migration != 0;
     for (int k = 0; k < sh->S; ++k) tb.z[k] = (double)sh->z[k];
@@ -132,6 +134,64 @@ static int build_tables(const CatintPnpShared* sh, DevTables& tb) {
         tb.fq = fq;
     }
     return CATINT_PNP_OK;
+}
+
+// Steady-mode elimination of PASSIVE species.  A species is passive when nothing depends on its concentration
+// but its own diffusion: no charge (or migration switched off), no part in any homogeneous reaction (neither
+// stoichiometry nor rate law), not read by any flux equation.  Its equations c_t = D c_xx decouple from the block
+// system, and at the steady state of a finite boundary layer (Dirichlet bulk node, flux wall) their discrete
+// solution is exactly linear -- the kernel writes it in closed form (pnp_bdf_kernel, final outputs).  The block
+// system shrinks from S_full+1 to S+1 unknowns per node (C2: 9 -> 7, C4: 11 -> 8), which is ~b^2 in the solve
+// sweeps and ~b^3 in the factorisation.  Only in CATINT_PNP_MODE_STEADY with one output time (transient
+// outputs need the passive species' history); CATINT_PNP_MODE_KEEP_ALL switches it off.
+static bool reduce_passive(const DevTables& full, DevTables& out) {
+    bool passive[MAXS];
+    const int SF = full.S;
+    for (int k = 0; k < SF; ++k) passive[k] = (full.z[k] == 0.0) || !full.use_migration;
+    for (int r = 0; r < full.R; ++r) {
+        for (int e = 0; e < full.ned[r]; ++e) passive[full.ed[r][e]] = false;
+        for (int e = 0; e < full.npr[r]; ++e) passive[full.pr[r][e]] = false;
+        for (int k = 0; k < SF; ++k) if (full.nu[r][k] != 0.0) passive[k] = false;
+    }
+    for (int e = 0; e < full.fq.n_eq; ++e)
+        for (int w = 0; w < full.fq.n_code[e]; ++w)
+            if ((full.fq.code[e][w] & 0xff) == 2) passive[full.fq.code[e][w] >> 8] = false;
+    int nc = 0, np = 0, idx[MAXS];
+    for (int k = 0; k < SF; ++k) { idx[k] = passive[k] ? -1 : nc; if (passive[k]) ++np; else ++nc; }
+    if (np == 0 || nc == 0) return false;
+    out = full;
+    out.S = nc; out.S_full = SF; out.npas = np;
+    memset(out.z, 0, sizeof(out.z)); memset(out.nu, 0, sizeof(out.nu));
+    memset(out.fq.coef, 0, sizeof(out.fq.coef)); memset(out.pcoef, 0, sizeof(out.pcoef));
+    int ip = 0;
+    for (int k = 0; k < SF; ++k) {
+        if (passive[k]) {
+            out.pmap[ip] = (int8_t)k;
+            for (int e = 0; e < full.fq.n_eq; ++e) out.pcoef[ip][e] = full.fq.coef[k][e];
+            ++ip;
+            continue;
+        }
+        const int kc = idx[k];
+        out.cmap[kc] = (int8_t)k;
+        out.z[kc] = full.z[k];
+        for (int r = 0; r < full.R; ++r) out.nu[r][kc] = full.nu[r][k];
+        for (int e = 0; e < full.fq.n_eq; ++e) out.fq.coef[kc][e] = full.fq.coef[k][e];
+        out.tbeg[kc] = full.tbeg[k];              // passive species own no derivative terms: the ranges stay contiguous
+    }
+    for (int j = nc; j <= MAXS; ++j) out.tbeg[j] = (int8_t)full.T;
+    for (int r = 0; r < full.R; ++r) {
+        for (int e = 0; e < full.ned[r]; ++e) out.ed[r][e] = (int8_t)idx[full.ed[r][e]];
+        for (int e = 0; e < full.npr[r]; ++e) out.pr[r][e] = (int8_t)idx[full.pr[r][e]];
+    }
+    for (int t = 0; t < full.T; ++t) {
+        if (full.ti1[t] >= 0) out.ti1[t] = (int8_t)idx[full.ti1[t]];
+        if (full.ti2[t] >= 0) out.ti2[t] = (int8_t)idx[full.ti2[t]];
+        if (full.ti3[t] >= 0) out.ti3[t] = (int8_t)idx[full.ti3[t]];
+    }
+    for (int e = 0; e < full.fq.n_eq; ++e)
+        for (int w = 0; w < full.fq.n_code[e]; ++w)
+            if ((full.fq.code[e][w] & 0xff) == 2) out.fq.code[e][w] = 2 | (idx[full.fq.code[e][w] >> 8] << 8);
+    return true;
 }
 
 // per-cell parameters of the flux equations
@@ -278,9 +338,15 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
     rc = attach_fpar(P.tb, cells);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int mode = ctl->mode & CATINT_PNP_MODE_MASK;
+    int nb = block_size_of(sh);
+    if (mode == CATINT_PNP_MODE_STEADY && ctl->n_out == 1 && !(ctl->mode & CATINT_PNP_MODE_KEEP_ALL)) {
+        DevTables red;
+        if (reduce_passive(P.tb, red)) { P.tb = red; nb -= red.npas; }
+    }
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
     P.y0 = y0; P.n_cells = n_cells;
-    P.mode = ctl->mode; P.max_steps = ctl->max_steps > 0 ? ctl->max_steps : 100000;
+    P.mode = mode; P.max_steps = ctl->max_steps > 0 ? ctl->max_steps : 100000;
     P.n_out = ctl->n_out; P.polish_max_iter = ctl->polish_max_iter > 0 ? ctl->polish_max_iter : 8;
     P.rtol = ctl->rtol; P.atol = ctl->atol; P.h0 = ctl->h0;
     P.polish_rtol = ctl->polish_rtol > 0.0 ? ctl->polish_rtol : 1e-10;
@@ -296,9 +362,9 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
     P.state_in_smem = 1;
     P.prof = g_prof;
     if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN) {
-        DISPATCH_NB(block_size_of(sh), launch_bdf, true, P, st);
+        DISPATCH_NB(nb, launch_bdf, true, P, st);
     } else {
-        DISPATCH_NB(block_size_of(sh), launch_bdf, false, P, st);
+        DISPATCH_NB(nb, launch_bdf, false, P, st);
     }
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
     return rc;

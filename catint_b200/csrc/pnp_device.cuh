@@ -41,6 +41,13 @@ struct DevTables {
     // wall kinetics (flux equations): programs + coefficient table (by value), per-cell parameters (device)
     const double* fpar;
     CatintPnpFluxEq fq;
+    // Steady-mode elimination of PASSIVE species (pnp_capi.cu: reduce_passive): the tables above describe the
+    // S coupled species the kernel integrates; the caller's model has S_full >= S species.  cmap: kernel species
+    // -> caller's species; pmap: the npas eliminated species (caller's indices); pcoef: their flux-equation
+    // coefficients.  Without elimination S_full == S and cmap is the identity.
+    int S_full, npas;
+    int8_t cmap[MAXS], pmap[MAXS];
+    double pcoef[MAXS][CATINT_PNP_MAX_FLUX_EQ];
 };
 
 // Per-cell parameters held in registers by every lane (uniform across the warp).
@@ -133,7 +140,7 @@ __device__ __forceinline__ double net_rate(const DevTables& tb, int r, const dou
 __device__ __forceinline__ void load_cell_scalars(const DevTables& tb, const double* par, const int* nx,
                                                   const int* mesh_id, const double* mesh_xi, long long cell,
                                                   CellScalars& cs) {
-    const int S = tb.S;
+    const int S = tb.S_full;
     const double* p = par + (size_t)cell * (3 * S + 8);
     cs.n = nx[cell];
     const int mid = mesh_id ? mesh_id[cell] : -1;
@@ -155,7 +162,7 @@ __device__ __forceinline__ void load_cell_scalars(const DevTables& tb, const dou
 __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par, const int* nx,
                                           const int* mesh_id, const double* mesh_xi, long long cell,
                                           int lane, CellScalars& cs, CellSpecies* sp) {
-    const int S = tb.S;
+    const int S = tb.S_full;                 // layout of the caller's parameter record
     const int NPAR = 3 * S + 8;
     const double* p = par + (size_t)cell * NPAR;
     cs.n = nx[cell];
@@ -172,11 +179,12 @@ __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par
     cs.u_am = 1.0 / (cs.dx * cs.dx);
     cs.u_ac = 1.0 / (2.0 * cs.dx);
     cs.u_sg = cs.eps / (cs.dx * UNIT_F);
-    if (lane < S) {
-        sp->cb[lane] = p[lane];
-        sp->J[lane] = p[S + lane];
-        sp->Jfix[lane] = p[S + lane];
-        sp->D[lane] = p[2 * S + lane];
+    if (lane < tb.S) {
+        const int k = tb.cmap[lane];         // caller's index of kernel species `lane`
+        sp->cb[lane] = p[k];
+        sp->J[lane] = p[S + k];
+        sp->Jfix[lane] = p[S + k];
+        sp->D[lane] = p[2 * S + k];
         const double q = tb.z[lane] * UNIT_F;
         sp->q[lane] = q;
         sp->bq[lane] = tb.use_migration ? cs.beta * q : 0.0;

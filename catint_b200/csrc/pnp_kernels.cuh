@@ -245,7 +245,10 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
             const unsigned d = sb + (unsigned)(islot * LMAX * 256);
 #pragma unroll
             for (int j = 0; j < LMAX; ++j)
-                if (j <= q_old) cp_async8(d + 256u * j, ws.zn + (size_t)j * N + idx);
+                if (j <= q_old) {
+                    if (j == 0) cp_async8(d, ws.zn + idx);
+                    else cp_async8_hint(d + 256u * j, ws.zn + (size_t)j * N + idx, ws.stream);
+                }
         }
         cp_commit();
         ++ichunk;
@@ -310,7 +313,10 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
         }
 #pragma unroll
         for (int j = 0; j < LMAX; ++j)
-            if (j <= q_new) ws.zn[(size_t)j * N + idx] = z[j];
+            if (j <= q_new) {
+                if (j == 0) ws.zn[idx] = z[0];
+                else st_hint(ws.zn + (size_t)j * N + idx, z[j], ws.stream);
+            }
         if (predict) {
             ws.y[idx] = z[0];
             ws.psi[idx] = rl1 * z[1] - z[0];
@@ -370,6 +376,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     __syncthreads();
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     const int nxm = P.tb.nx_max;
+    const int SF = P.tb.S_full;                            // species of the caller's model (outputs, y0)
     // per cell: CellSpecies | scratch | ring | [y zb]
     constexpr size_t RINGD = (size_t)ring_doubles<NB, ST>();
     constexpr size_t WARPD = scratch_doubles<NB, ST>() + RINGD;          // doubles private to the warp
@@ -382,6 +389,8 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     WarpState<NB, ST> ws;
     ws.lane = lane;
     ws.tb = tb;
+    ws.keep = l2_policy_keep();
+    ws.stream = l2_policy_stream();
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
     ws.sp = sp;
     double* cellbase = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));
@@ -428,7 +437,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     for (int idx = vlane; idx < N; idx += vstride) {
         const int i = idx / NB, r = idx - i * NB;
         double v = 0.0;
-        if (r < S) v = P.y0 ? P.y0[((size_t)cell * nxm + i) * S + r] : sp->cb[r];
+        if (r < S) v = P.y0 ? P.y0[((size_t)cell * nxm + i) * SF + tb->cmap[r]] : sp->cb[r];
         ws.y[idx] = v;
         ws.psi[idx] = 0.0;
     }
@@ -644,7 +653,10 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                     const unsigned d = sb + (unsigned)(islot * NARR * 256);
 #pragma unroll
                     for (int j = 0; j < LMAX; ++j)
-                        if (j <= q || (j == QMAX && want_up)) cp_async8(d + 256u * j, zn + (size_t)j * N + ii);
+                        if (j <= q || (j == QMAX && want_up)) {
+                            if (j == 0) cp_async8(d, zn + ii);
+                            else cp_async8_hint(d + 256u * j, zn + (size_t)j * N + ii, ws.stream);
+                        }
                     cp_async8(d + 256u * LMAX, ewt + ii);
                 }
                 cp_commit();
@@ -682,11 +694,11 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                     for (int j = 1; j <= QMAX; ++j) {
                         if (j <= q) {
                             const double v = zj[j] + lreg[j] * ac;
-                            zn[(size_t)j * N + ii] = v;
+                            st_hint(zn + (size_t)j * N + ii, v, ws.stream);
                             if (j == q && want_eta && mass) ddn = fmax(ddn, fabs(v) * w);
                         }
                     }
-                    if (save_acor) zn[(size_t)QMAX * N + ii] = ac;
+                    if (save_acor) st_hint(zn + (size_t)QMAX * N + ii, ac, ws.stream);
                     ws.zb[ii] = ac;
                     ewt[ii] = 1.0 / (rtol * fabs(yv) + atol);
                 }
@@ -739,7 +751,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         while (iout < P.n_out && B.t >= P.t_out[iout] * (1.0 - 1e-14)) {
             const double s = (P.t_out[iout] - B.t) / B.h;
             const bool last = (iout == P.n_out - 1);
-            double* co = P.c_out + ((size_t)iout * P.n_cells + cell) * nxm * S;
+            double* co = P.c_out + ((size_t)iout * P.n_cells + cell) * nxm * SF;
             double* go = P.g_out ? P.g_out + ((size_t)iout * P.n_cells + cell) * nxm : nullptr;
             for (int idx = vlane; idx < N; idx += vstride) {
                 const int i = idx / NB, r = idx - i * NB;
@@ -749,7 +761,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
                     if (j <= q) v = v * s + ws.zn[(size_t)j * N + idx];
                 if (last) ws.y[idx] = v;           // kept for the steady polish / final outputs
                 if (!(last && P.mode == CATINT_PNP_MODE_STEADY)) {
-                    if (r < S) co[(size_t)i * S + r] = v;
+                    if (r < S) co[(size_t)i * SF + tb->cmap[r]] = v;
                     else if (r == S) { if (go) go[i] = v; }
                     else if (P.phi_out) P.phi_out[((size_t)iout * P.n_cells + cell) * nxm + i] = v;
                 }
@@ -808,17 +820,35 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     // ---------------------------------------------------- final outputs
     {
         const int io = P.n_out - 1;
-        double* co = P.c_out + ((size_t)io * P.n_cells + cell) * nxm * S;
+        double* co = P.c_out + ((size_t)io * P.n_cells + cell) * nxm * SF;
         double* go = P.g_out ? P.g_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
         double* po = P.phi_out ? P.phi_out + ((size_t)io * P.n_cells + cell) * nxm : nullptr;
         if (P.mode == CATINT_PNP_MODE_STEADY || status != CATINT_PNP_CELL_CONVERGED) {
             for (int idx = vlane; idx < N; idx += vstride) {
                 const int i = idx / NB, r = idx - i * NB;
                 const double v = ws.y[idx];
-                if (r < S) co[(size_t)i * S + r] = v;
+                if (r < S) co[(size_t)i * SF + tb->cmap[r]] = v;
                 else if (r == S) { if (go) go[i] = v; }
                 else if (po) po[i] = v;
             }
+        }
+        // passive species (neutral, no homogeneous reaction, not read by any flux equation; eliminated from the
+        // block system in steady mode, pnp_capi.cu: reduce_passive): their discrete steady equations
+        // D*(second difference) = 0 with the flux wall condition and the Dirichlet bulk node have the exactly
+        // linear solution c(x_i) = c_bulk + (J/D)*(x_{n-1} - x_i) on any mesh
+        for (int pp = 0; pp < tb->npas; ++pp) {
+            const int k = tb->pmap[pp];
+            const double* par = P.par + (size_t)cell * (3 * SF + 8);
+            double Jp = par[SF + k];
+            for (int e = 0; e < tb->fq.n_eq; ++e)
+                Jp += tb->pcoef[pp][e] * fluxeq_eval(&tb->fq, e, ws.cs.fpar, ws.y, ST ? ws.y[S + 1] : ws.cs.phi_wall, -1, S, nullptr);
+            const double slope = Jp / par[2 * SF + k];
+            const double xl = ws.cs.uniform ? ws.cs.dx * (n - 1) : ws.cs.dx * ws.cs.xi[n - 1];
+            for (int i = lane; i < n; i += 32) {
+                const double x = ws.cs.uniform ? ws.cs.dx * i : ws.cs.dx * ws.cs.xi[i];
+                co[(size_t)i * SF + k] = i == n - 1 ? par[k] : par[k] + slope * (xl - x);
+            }
+            if (P.flux_out && lane == 0) P.flux_out[(size_t)cell * SF + k] = Jp;
         }
         __syncwarp();
         // potential by the forward cumulative sum of the reference (calculator_old.py:798-800);
@@ -842,7 +872,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
         if (P.flux_out && lane < S) {
             const WallCoef w = wall_coef(ws.cs);
             const double bq = tb->use_migration ? sp->bq[lane] : 0.0;
-            P.flux_out[(size_t)cell * S + lane] =
+            P.flux_out[(size_t)cell * SF + tb->cmap[lane]] =
                 -sp->D[lane] * ((ws.y[2 * NB + lane] - ws.y[lane]) * w.w0 + bq * ws.y[NB + lane] * ws.y[NB + S]);
         }
         if (lane == 0) {
@@ -889,6 +919,7 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
     if (cell >= P.n_cells) return;
     WarpState<NB, ST> ws;
     ws.lane = lane; ws.tb = tb;
+    ws.keep = 0; ws.stream = 0;
     CellSpecies* sp = reinterpret_cast<CellSpecies*>(mine);
     ws.sp = sp;
     ws.scratch = reinterpret_cast<double*>(mine + ((sizeof(CellSpecies) + 15) & ~size_t(15)));

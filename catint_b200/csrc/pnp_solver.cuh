@@ -42,6 +42,7 @@ struct WarpState {
     const CellSpecies* sp;      // shared, per warp
     const DevTables* tb;        // shared, per block
     CellScalars cs;
+    unsigned long long keep, stream;   // L2 cache policies: node records (evict_last) / Nordsieck history (evict_first)
     int N;          // n*NB
     int lane;
 };
@@ -300,10 +301,66 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
 __device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(__cvta_generic_to_global(g)) : "memory");
 }
+// ---- L2 eviction priorities ------------------------------------------------------------------------
+// The per-cell workspace of a full launch (C2: 162 KB x 1024 cells = 166 MB) exceeds the 126 MB L2.  The node
+// records are read by every solve sweep (twice per Newton iteration, by a sequential chain whose look-ahead is
+// three nodes: a DRAM miss stalls the chain), the higher Nordsieck vectors only once per step by passes with
+// independent, deeply prefetched chunks.  So the records are loaded and stored with L2::evict_last and the
+// Nordsieck vectors zn[1..5] with L2::evict_first: the L2 then holds the records (104 MB) and the history
+// streams from DRAM, where its latency is hidden.  CATINT_L2_HINTS=0 turns the hints off (A/B measurements).
+#ifndef CATINT_L2_HINTS
+#define CATINT_L2_HINTS 1
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(unsigned saddr, const void* g, unsigned long long pol) {
+#if CATINT_L2_HINTS
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;"
+                 :: "r"(saddr), "l"(__cvta_generic_to_global(g)), "l"(pol) : "memory");
+#else
+    cp_async16(saddr, g);
+#endif
+}
+__device__ __forceinline__ void cp_async8_hint(unsigned saddr, const void* g, unsigned long long pol) {
+#if CATINT_L2_HINTS
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;"
+                 :: "r"(saddr), "l"(__cvta_generic_to_global(g)), "l"(pol) : "memory");
+#else
+    cp_async8(saddr, g);
+#endif
+}
+__device__ __forceinline__ void st_hint(double* p, double v, unsigned long long pol) {
+#if CATINT_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(__cvta_generic_to_global(p)), "d"(v), "l"(pol) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_hint4(double* p, double4 v, unsigned long long pol) {
+#if CATINT_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(__cvta_generic_to_global(p)), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(__cvta_generic_to_global(p + 2)), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+#else
+    *reinterpret_cast<double4*>(p) = v;
+#endif
+}
 // predicated copy (no branch): pred != 0 -> copy
-__device__ __forceinline__ void cp_async16_if(unsigned saddr, const void* g, unsigned pred) {
+__device__ __forceinline__ void cp_async16_if(unsigned saddr, const void* g, unsigned pred, unsigned long long pol) {
+#if CATINT_L2_HINTS
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %3;\n\t}"
+                 :: "r"(saddr), "l"(__cvta_generic_to_global(g)), "r"(pred), "l"(pol) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
                  :: "r"(saddr), "l"(__cvta_generic_to_global(g)), "r"(pred) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -327,6 +384,7 @@ struct RecordFeed {
     unsigned dst;                                        // shared address of this lane's first chunk in slot 0
     int n0, n1, two;
     int lane;
+    unsigned long long pol;
     __device__ __forceinline__ void init(const double* fac, const double* ring, int lane, Chain c0, Chain c1) {
         s0 = fac + (long long)c0.first * REC + 2 * lane; st0 = (long long)c0.dir * REC;
         s1 = fac + (long long)c1.first * REC + 2 * lane; st1 = (long long)c1.dir * REC;
@@ -340,14 +398,14 @@ struct RecordFeed {
             const unsigned d = dst + (unsigned)(((two * k) & (RING_CHAIN * two - 1)) * REC * 8);
 #pragma unroll
             for (int q = 0; q < ROUNDS; ++q)
-                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s0 + 64 * q);
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16_hint(d + 512u * q, s0 + 64 * q, pol);
             s0 += st0;
         }
         if (k < n1) {
             const unsigned d = dst + (unsigned)(((2 * k + 1) & (RING - 1)) * REC * 8);
 #pragma unroll
             for (int q = 0; q < ROUNDS; ++q)
-                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16(d + 512u * q, s1 + 64 * q);
+                if (q + 1 < ROUNDS || lane + 32 * q < CH) cp_async16_hint(d + 512u * q, s1 + 64 * q, pol);
             s1 += st1;
         }
     }
@@ -555,7 +613,7 @@ __device__ __forceinline__ bool eliminate_pair(const WarpState<NB, ST>& ws, doub
     double* rec = ws.fac + (size_t)i * REC;
     if (isD && live) {
 #pragma unroll
-        for (int r = 0; r < NB; ++r) rec[inv_off<NB, ST>(r, 0) + ((j >> 1) * NB * 2 + (j & 1))] = A[r];
+        for (int r = 0; r < NB; ++r) st_hint(rec + inv_off<NB, ST>(r, 0) + ((j >> 1) * NB * 2 + (j & 1)), A[r], ws.keep);
     }
     if (SPECIAL && wall && isD) {
         // V_0 = inv_0*A_E, A_E = diag(-l): needed for the modified A_U of node 1 and by the back substitution
@@ -633,9 +691,9 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
             double C[NB];
             interior_diag_column<NB, ST>(ws, y + (size_t)i * NB, r, k, inv_gamma, sg, C);
 #pragma unroll
-            for (int rr = 0; rr < NB; ++rr) rec[rr * NBP + r] = C[rr];
+            for (int rr = 0; rr < NB; ++rr) st_hint(rec + rr * NBP + r, C[rr], ws.keep);
         }
-        reinterpret_cast<double4*>(rec + NB * NBP)[r] = co;
+        st_hint4(rec + NB * NBP + 4 * r, co, ws.keep);
     }
     __syncwarp();
 
@@ -649,6 +707,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
     bool ok = true;
     RecordFeed<NB, ST> feed;
     feed.init(ws.fac, ws.ring, lane, Chain{0, iters, +1}, Chain{n - 1, nbot, -1});
+    feed.pol = ws.keep;
 #pragma unroll 1
     for (int p_ = 0; p_ < RING_CHAIN - 1; ++p_) { feed.issue(p_); cp_commit(); }
 #pragma unroll 1
@@ -763,6 +822,7 @@ struct SweepRing {
     unsigned dst, wdst;                                   // shared address of my first chunk / my weight in slot (0, grp)
     int rstride, zstep, left;                             // doubles between records / unknowns; records left to copy
     unsigned lastp;                                       // copy predicate of the last round
+    unsigned long long pol;
     bool wl;
     __device__ __forceinline__ void init(const WarpState<NB, ST>& ws, int first, int dir, int count, bool weights, int r,
                                          bool rowlane) {
@@ -775,6 +835,7 @@ struct SweepRing {
         wdst = (unsigned)__cvta_generic_to_shared(ws.ring) + (unsigned)((grp * SLOT + R16 * 32 + l) * 8);
         lastp = (l + 16 * (R16 - 1) < CH) ? 1u : 0u;
         wl = weights && rowlane;
+        pol = ws.keep;
         wsrc = ws.ewt + (size_t)first * NB + r;
         zsrc = ws.zn + (size_t)first * NB + r;
     }
@@ -784,8 +845,8 @@ struct SweepRing {
         const unsigned d = dst + (unsigned)(slot * 2 * SLOT * 8);
 #pragma unroll
         for (int q = 0; q < R16; ++q) {
-            if (q + 1 < R16) cp_async16(d + 256u * q, src + 32 * q);
-            else cp_async16_if(d + 256u * q, src + 32 * q, lastp);
+            if (q + 1 < R16) cp_async16_hint(d + 256u * q, src + 32 * q, pol);
+            else cp_async16_if(d + 256u * q, src + 32 * q, lastp, pol);
         }
         if (wl) {
             const unsigned dw = wdst + (unsigned)(slot * 2 * SLOT * 8);

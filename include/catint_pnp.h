@@ -64,7 +64,13 @@ enum {
 };
 
 enum { CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK = 0, CATINT_PNP_BC_STERN_ROBIN = 1 };
-enum { CATINT_PNP_MODE_TRANSIENT = 0, CATINT_PNP_MODE_STEADY = 1 };
+enum { CATINT_PNP_MODE_TRANSIENT = 0, CATINT_PNP_MODE_STEADY = 1,
+       CATINT_PNP_MODE_MASK = 0xff,
+       /* flag, OR-ed into CatintPnpControl.mode: keep every species in the block system.  By default a steady solve
+          with one output time takes PASSIVE species (no charge or migration off, no part in any homogeneous
+          reaction, not read by a flux equation) out of the block system -- their equations decouple and their
+          discrete steady profile c_bulk + (J/D)(L - x) is written in closed form.                              */
+       CATINT_PNP_MODE_KEEP_ALL = 0x100 };
 
 /* per-cell status written by catint_pnp_solve_batch */
 enum {

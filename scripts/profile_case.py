@@ -23,7 +23,7 @@ def main():
         bk.lib.catint_pnp_debug_profile_buffer(prof.data_ptr())
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.time()
-        bk.solve(db, [bench.T_END], mode=be.MODE_STEADY, max_steps=max_steps, out=out)
+        bk.solve(db, [bench.T_END], mode=be.MODE_STEADY | (be.MODE_KEEP_ALL if os.environ.get('CATINT_KEEP_ALL') else 0), max_steps=max_steps, out=out)
         torch.cuda.synchronize(); dt = time.time() - t0
         nn = float(out['n_newton'].double().sum())
         ns = float(out['n_setups'].double().sum()); st = float(out['n_steps'].double().sum())

@@ -441,6 +441,36 @@ def test_stern_boundary_on_graded_mesh(bk, resultsdir, nn):
             assert relerr(got, go['odeint_c_end_%d' % c], cs, floor=1e-9) < RTOL_PROFILE, c
 
 
+def test_passive_species_elimination_is_exact(bk, resultsdir):
+    """Steady solves take passive species (CO, H2: neutral, no homogeneous reaction) out of the block system and
+    write their linear steady profile in closed form (include/catint_pnp.h: CATINT_PNP_MODE_KEEP_ALL).  The result
+    must agree with the full block system to rounding -- same discrete root -- on cells from the kinetic to the
+    transport-limited end of the C2 sweep, and the passive profiles must be exactly linear with slope -J/D."""
+    from catint_b200 import backend as be, workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import build_cell_batch
+    tp = Transport(resultsdir=resultsdir, **workloads.c2(n_potentials=8))
+    batch, _ = build_cell_batch(tp)
+    db = bk.upload(batch)
+    red = bk.solve(db, [200.0], mode=be.MODE_STEADY)
+    red = {k: v.clone() for k, v in red.items()}
+    full = bk.solve(db, [200.0], mode=be.MODE_STEADY | be.MODE_KEEP_ALL)
+    assert red['status'].tolist() == [0] * 8 and full['status'].tolist() == [0] * 8
+    S = batch.S
+    cs = np.max(np.abs(batch.par[0, :S]))
+    a, b = red['c'][-1].cpu().numpy(), full['c'][-1].cpu().numpy()
+    assert relerr(a, b, cs, floor=1e-9) < 1e-8
+    assert np.max(np.abs(red['flux'].cpu().numpy() - full['flux'].cpu().numpy())) < 1e-8 * np.max(np.abs(batch.par[:, S:2 * S]))
+    assert np.max(np.abs(red['phi'][-1].cpu().numpy() - full['phi'][-1].cpu().numpy())) < 1e-9
+    x = np.arange(batch.nx_max) * batch.par[0, 3 * S + 5]
+    for name in ('CO', 'H2'):
+        k = batch.species.index(name)
+        for c in range(8):
+            J, D = batch.par[c, S + k], batch.par[c, 2 * S + k]
+            want = batch.par[c, k] + J / D * (x[-1] - x)
+            assert np.max(np.abs(a[c, :, k] - want)) <= 1e-13 * max(np.max(np.abs(want)), 1e-300)
+
+
 def test_warm_start_from_results_folder(bk, resultsdir):
     """system['init_folder']: a previous results folder initialises every cell (reference: calculator.py:303-309);
     restarting from the converged sweep must reproduce it with a fraction of the steps."""
