@@ -345,7 +345,7 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
         if (reduce_passive(P.tb, red)) { P.tb = red; nb -= red.npas; }
     }
     P.par = cells->par; P.nx = cells->nx; P.mesh_id = cells->mesh_id; P.mesh_xi = cells->mesh_xi;
-    P.y0 = y0; P.n_cells = n_cells;
+    P.y0 = y0; P.n_cells = n_cells; P.order = cells->order;
     P.mode = mode; P.max_steps = ctl->max_steps > 0 ? ctl->max_steps : 100000;
     P.n_out = ctl->n_out; P.polish_max_iter = ctl->polish_max_iter > 0 ? ctl->polish_max_iter : 8;
     P.rtol = ctl->rtol; P.atol = ctl->atol; P.h0 = ctl->h0;

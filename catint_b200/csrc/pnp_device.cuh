@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "pnp_fluxeq.cuh"
 
 namespace catint {
@@ -38,17 +39,24 @@ struct DevTables {
     int8_t tr[MAXT], ti1[MAXT], ti2[MAXT], ti3[MAXT];
     double tcoef[MAXT];
     int8_t tbeg[MAXS + 1];
-    // wall kinetics (flux equations): programs + coefficient table (by value), per-cell parameters (device)
-    const double* fpar;
-    CatintPnpFluxEq fq;
     // Steady-mode elimination of PASSIVE species (pnp_capi.cu: reduce_passive): the tables above describe the
     // S coupled species the kernel integrates; the caller's model has S_full >= S species.  cmap: kernel species
-    // -> caller's species; pmap: the npas eliminated species (caller's indices); pcoef: their flux-equation
+    // -> caller's species; pmap: the npas eliminated species (caller's indices); pcoef (below): their flux-equation
     // coefficients.  Without elimination S_full == S and cmap is the identity.
     int S_full, npas;
     int8_t cmap[MAXS], pmap[MAXS];
+    // wall kinetics (flux equations): programs + coefficient table (by value), per-cell parameters (device).
+    // LAST members: a kernel copies only tables_prefix_bytes() to shared memory when there are no flux equations.
+    const double* fpar;
+    CatintPnpFluxEq fq;
     double pcoef[MAXS][CATINT_PNP_MAX_FLUX_EQ];
 };
+
+// bytes of the tables a kernel needs in shared memory: without flux equations everything up to fq.n_eq / n_par
+__host__ __device__ inline size_t tables_prefix_bytes(const DevTables& tb) {
+    return tb.fq.n_eq > 0 ? sizeof(DevTables) : (offsetof(DevTables, fq) + 16);
+}
+
 
 // Per-cell parameters held in registers by every lane (uniform across the warp).
 struct CellScalars {

@@ -41,6 +41,7 @@ struct SolveParams {
     // per-cell inputs
     const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
     const double* y0;          // optional [B][nx_max][S]
+    const int* order;          // optional [B]: cell handled by launch slot k (expensive cells first), or nullptr
     long long n_cells;
     // control
     int mode, max_steps, n_out, polish_max_iter;
@@ -356,25 +357,36 @@ __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid,
     if (prof_on) pc[3] += clock64() - t0;
 }
 
+// Cells (warps) per block.  Measured on the 1024-cell C2 launch: 1 cell per block (cells spread 6..7 per SM instead
+// of 8 on 108 SMs and 4 on 40, expensive cells first via CatintPnpCells.order) is not faster than 4 (159.8 vs
+// 160.4 ms) -- the launch lasts as long as its slowest cell either way -- and costs a table copy per cell.
+#ifndef CATINT_CELLS_PER_BLOCK
+#define CATINT_CELLS_PER_BLOCK 4
+#endif
+constexpr int BDF_WARPS = CATINT_CELLS_PER_BLOCK;
+
 template <int NB, bool ST, bool SMEM>
-__global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
+__global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(SolveParams P) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
-    constexpr int WARPS = 4;                               // cells per block
+    constexpr int WARPS = BDF_WARPS;                       // cells per block
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = warp;                                 // cell slot inside the block
-    const long long cell = (long long)blockIdx.x * WARPS + slot;
+    const long long launch_slot = (long long)blockIdx.x * WARPS + slot;
+    // launch order: expensive cells first (optional permutation from the host)
+    const long long cell = (P.order && launch_slot < P.n_cells) ? P.order[launch_slot] : launch_slot;
 
     // shared layout: tables | per warp { CellSpecies | scratch | [y psi zb] }
     DevTables* tb = reinterpret_cast<DevTables*>(smem_raw);
+    const size_t tbytes = (tables_prefix_bytes(P.tb) + 15) & ~size_t(15);
     {
-        const int words = (int)(sizeof(DevTables) / 4);
+        const int words = (int)(tbytes / 4);
         const int* src = reinterpret_cast<const int*>(&P.tb);
         int* dst = reinterpret_cast<int*>(tb);
         for (int w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
     }
     __syncthreads();
-    size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
+    size_t off = tbytes;
     const int nxm = P.tb.nx_max;
     const int SF = P.tb.S_full;                            // species of the caller's model (outputs, y0)
     // per cell: CellSpecies | scratch | ring | [y zb]
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(128, 2) pnp_bdf_kernel(SolveParams P) {
     const size_t cell_doubles = WARPD + (SMEM ? (size_t)2 * nxm * NB : 0);
     const size_t per_cell = ((sizeof(CellSpecies) + 15) & ~size_t(15)) + cell_doubles * sizeof(double);
     unsigned char* mine = smem_raw + off + (size_t)slot * per_cell;
-    if (cell >= P.n_cells) return;
+    if (launch_slot >= P.n_cells) return;
 
     const long long t_kernel0 = clock64();
     WarpState<NB, ST> ws;
@@ -1005,7 +1017,7 @@ __global__ void __launch_bounds__(128) pnp_jacobian_kernel(JacParams P) {
 namespace catint {
 template <int NB, bool ST>
 int launch_bdf(SolveParams& P, cudaStream_t st) {
-    const size_t base = ((sizeof(DevTables) + 15) & ~size_t(15));
+    const size_t base = (tables_prefix_bytes(P.tb) + 15) & ~size_t(15);
     const size_t species = ((sizeof(CellSpecies) + 15) & ~size_t(15));
     const size_t warpd = (size_t)scratch_doubles<NB, ST>() + (size_t)ring_doubles<NB, ST>();
     const size_t state = (size_t)2 * P.tb.nx_max * NB;
@@ -1016,17 +1028,19 @@ int launch_bdf(SolveParams& P, cudaStream_t st) {
     // one warp per cell, four cells per block; the Newton iterate and the update vector live in shared
     // memory when they fit (SMEM = true), else in the workspace.  The shared-memory opt-in is a
     // per-device function attribute: it is set on every launch (cheap, no cached state to race on).
-    const size_t smem_single = base + 4 * (species + (warpd + state) * sizeof(double));
-    const unsigned grid = (unsigned)((P.n_cells + 3) / 4);
-    if (smem_single <= (size_t)max_optin) {
+    constexpr int W = BDF_WARPS;
+    const size_t smem_single = base + W * (species + (warpd + state) * sizeof(double));
+    const unsigned grid = (unsigned)((P.n_cells + W - 1) / W);
+    // the state stays in shared memory as long as at least 4 cells per SM fit that way
+    if (smem_single * (4 / W > 0 ? 4 / W : 1) + 4096 <= (size_t)max_optin) {
         P.state_in_smem = 1;
         cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single);
-        pnp_bdf_kernel<NB, ST, true><<<grid, 128, smem_single, st>>>(P);
+        pnp_bdf_kernel<NB, ST, true><<<grid, 32 * W, smem_single, st>>>(P);
     } else {
         P.state_in_smem = 0;
-        const size_t smem = base + 4 * (species + warpd * sizeof(double));
+        const size_t smem = base + W * (species + warpd * sizeof(double));
         cudaFuncSetAttribute(pnp_bdf_kernel<NB, ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        pnp_bdf_kernel<NB, ST, false><<<grid, 128, smem, st>>>(P);
+        pnp_bdf_kernel<NB, ST, false><<<grid, 32 * W, smem, st>>>(P);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }

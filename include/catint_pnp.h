@@ -153,6 +153,9 @@ typedef struct CatintPnpCells {
     const int32_t* mesh_id;    /* [B] row of mesh_xi, or -1 = uniform mesh x_i = i*scale             */
     const double*  mesh_xi;    /* [n_mesh][nx_max] normalised node positions (may be NULL)           */
     const double*  fpar;       /* [B][flux_eq->n_par] per-cell parameters of the flux equations, or NULL */
+    const int32_t* order;      /* [B] optional launch order for catint_pnp_solve_batch: a permutation of 0..B-1,
+                                  expensive cells first (launch slot k works on cell order[k]); NULL = 0..B-1.
+                                  A scheduling hint only: results and their layout do not depend on it.  */
 } CatintPnpCells;
 
 /* Integrator control (HOST). */

@@ -45,7 +45,7 @@ def test_version_and_struct_layout(lib):
     # the ctypes mirrors must have the C layout: 6 int32 + 14 int32 + 2*12*4 int32 + 2*12 + 14*12 doubles
     # + the host pointer to the flux equations
     assert ctypes.sizeof(be.CatintPnpShared) == 4 * (6 + 14 + 96) + 8 * (24 + 168) + ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(be.CatintPnpCells) == 5 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(be.CatintPnpCells) == 6 * ctypes.sizeof(ctypes.c_void_p)
     # flux equations: 2 + 4 int32, 4 x 96 int32 code words, 4 x 32 constants, 14 x 4 coefficients
     assert ctypes.sizeof(be.CatintPnpFluxEq) == 4 * (2 + 4 + 4 * 96) + 8 * (4 * 32 + 14 * 4)
     assert ctypes.sizeof(be.CatintPnpControl) == 16 + 32 + ctypes.sizeof(ctypes.c_void_p)
