@@ -16,6 +16,12 @@ MAX_REACTANTS = 4
 
 BC_DIRICHLET_WALL_NEUMANN_BULK = 0
 BC_STERN_ROBIN = 1
+BC_DIRICHLET_BOTH = 2                 # the reference's other pb_bound pairs (calculator_old.py:776-803):
+BC_DIRICHLET_WALL_NEUMANN_WALL = 3    # available in potential() and in the fixed-step steppers (step())
+BC_DIRICHLET_BULK_NEUMANN_WALL = 4
+BC_DIRICHLET_BULK_NEUMANN_BULK = 5
+STEPPER_FTCS = 0
+STEPPER_CRANK_NICOLSON = 1
 MODE_TRANSIENT = 0
 MODE_STEADY = 1
 MODE_KEEP_ALL = 0x100   # flag: no elimination of passive species (see include/catint_pnp.h)
@@ -71,7 +77,8 @@ class CatintPnpControl(ctypes.Structure):
 
 EXPORTS = ['catint_pnp_version', 'catint_pnp_last_error', 'catint_pnp_device_count',
            'catint_pnp_workspace_bytes', 'catint_pnp_rhs_batch', 'catint_pnp_jacobian_batch',
-           'catint_pnp_solve_batch', 'catint_pnp_debug_profile_buffer']
+           'catint_pnp_solve_batch', 'catint_pnp_debug_profile_buffer', 'catint_pnp_potential_batch',
+           'catint_pnp_step_batch']
 
 
 def library_path():
@@ -105,6 +112,13 @@ def load_library():
     lib.catint_pnp_solve_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
                                            ctypes.c_int64, vp, ctypes.POINTER(CatintPnpControl),
                                            vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.catint_pnp_potential_batch.restype = ctypes.c_int
+    lib.catint_pnp_potential_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
+                                               ctypes.c_int64, vp, vp, vp, vp, vp]
+    lib.catint_pnp_step_batch.restype = ctypes.c_int
+    lib.catint_pnp_step_batch.argtypes = [ctypes.POINTER(CatintPnpShared), ctypes.POINTER(CatintPnpCells),
+                                          ctypes.c_int64, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                          ctypes.c_int32, vp, ctypes.c_int32, vp, vp, vp, vp]
     lib.catint_pnp_debug_profile_buffer.restype = None
     lib.catint_pnp_debug_profile_buffer.argtypes = [vp]
     _lib = lib
@@ -339,6 +353,46 @@ class PnpBackend(object):
         self._check(rc, 'catint_pnp_rhs_batch')
         self.launches += 1
         return dcdt, g, phi
+
+    # -- Poisson routine / K4 ----------------------------------------------
+    def potential(self, dbatch, c):
+        """get_potential_and_gradient for every pb_bound pair: c [B,nx_max,S] -> (v, grad_v, lapl_v) [B,nx_max]"""
+        torch = self.torch
+        b = dbatch.batch
+        assert c.shape == (b.B, b.nx_max, b.S) and c.dtype == torch.float64 and c.is_contiguous()
+        v = torch.zeros((b.B, b.nx_max), dtype=torch.float64, device=self.device)
+        g, lp = torch.zeros_like(v), torch.zeros_like(v)
+        with torch.cuda.device(self.device):
+            rc = self.lib.catint_pnp_potential_batch(ctypes.byref(dbatch.shared), ctypes.byref(dbatch.cells), b.B,
+                                                     c.data_ptr(), v.data_ptr(), g.data_ptr(), lp.data_ptr(),
+                                                     self._stream())
+        self._check(rc, 'catint_pnp_potential_batch')
+        self.launches += 1
+        return v, g, lp
+
+    def step(self, dbatch, stepper, dt, nt, itout, c0=None, lax_friedrich=False):
+        """the reference's fixed-step steppers (FTCS / Crank-Nicolson): nt steps of size dt; returns dict with
+        c [n_out,B,nx_max,S], phi, g [n_out,B,nx_max] after the steps listed in itout"""
+        torch = self.torch
+        b = dbatch.batch
+        itout = np.ascontiguousarray(itout, dtype=np.int32)
+        n_out = len(itout)
+        if c0 is None:
+            c0 = torch.as_tensor(np.ascontiguousarray(
+                np.broadcast_to(b.par[:, None, 0:b.S], (b.B, b.nx_max, b.S)))).to(self.device)
+        assert c0.shape == (b.B, b.nx_max, b.S) and c0.dtype == torch.float64 and c0.is_contiguous()
+        it_dev = torch.as_tensor(itout).to(self.device)
+        out = {'c': torch.zeros((n_out, b.B, b.nx_max, b.S), dtype=torch.float64, device=self.device),
+               'phi': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=self.device),
+               'g': torch.zeros((n_out, b.B, b.nx_max), dtype=torch.float64, device=self.device)}
+        with torch.cuda.device(self.device):
+            rc = self.lib.catint_pnp_step_batch(ctypes.byref(dbatch.shared), ctypes.byref(dbatch.cells), b.B,
+                                                c0.data_ptr(), int(stepper), int(bool(lax_friedrich)), float(dt),
+                                                int(nt), it_dev.data_ptr(), n_out, out['c'].data_ptr(),
+                                                out['phi'].data_ptr(), out['g'].data_ptr(), self._stream())
+        self._check(rc, 'catint_pnp_step_batch')
+        self.launches += 1
+        return out
 
     # -- K2 ---------------------------------------------------------------
     def jacobian(self, dbatch, y):

@@ -26,6 +26,32 @@ from . import backend as _be
 
 # finite-difference integrators of the reference that map onto the BDF/Newton GPU integrator
 FD_ODE_CALCS = ['odeint', 'lsoda', 'vode']
+# the reference's fixed-step steppers (calculator_old.py:976-1029, :457-564), K4 of the backend
+FD_STEP_CALCS = ['FTCS', 'Crank-Nicolson']
+
+
+def poisson_bc_code(pb_bound):
+    """pb_bound -> (backend code, wall potential, bulk potential, wall gradient, bulk gradient); the pairs the
+    reference's get_potential_and_gradient accepts (calculator_old.py:703-705, :776-803)"""
+    pw, pbk = pb_bound['potential']['wall'], pb_bound['potential']['bulk']
+    gw, gb = pb_bound['gradient']['wall'], pb_bound['gradient']['bulk']
+    if gw is not None and gb is not None:
+        return None
+    code = None
+    if pw is not None and pbk is not None and gw is None and gb is None:
+        code = _be.BC_DIRICHLET_BOTH
+    elif pw is not None and pbk is None and gb is not None:
+        code = _be.BC_DIRICHLET_WALL_NEUMANN_BULK
+    elif pw is not None and pbk is None and gw is not None:
+        code = _be.BC_DIRICHLET_WALL_NEUMANN_WALL
+    elif pbk is not None and pw is None and gw is not None:
+        code = _be.BC_DIRICHLET_BULK_NEUMANN_WALL
+    elif pbk is not None and pw is None and gb is not None:
+        code = _be.BC_DIRICHLET_BULK_NEUMANN_BULK
+    if code is None:
+        return None
+    f = lambda x: 0.0 if x is None else float(x)
+    return code, f(pw), f(pbk), f(gw), f(gb)
 
 
 def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet', mesh=None):
@@ -83,6 +109,7 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
     B = len(models)
     par = np.zeros((B, _be.npar(S)))
     nx = np.zeros(B, dtype=np.int32)
+    bc_code = None
     z = np.array([m0.species[s]['charge'] for s in names], dtype=np.int32)
     for c, m in enumerate(models):
         par[c, 0:S] = [m.species[s]['bulk_concentration'] for s in names]
@@ -94,14 +121,17 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
             par[c, 3 * S + 2] = m.system['phiM'] - m.system['phiPZC']
             par[c, 3 * S + 3] = 0.0
         else:
-            wall = m.pb_bound['potential']['wall']
-            gb = m.pb_bound['gradient']['bulk']
-            if wall is None or gb is None:
-                tp.logger.error('| CI | -- | the FD-PNP backend needs pb_bound with a wall potential and a bulk '
-                                'gradient (the reference default, transport.py:207-210)')
+            bc = poisson_bc_code(m.pb_bound)
+            if bc is None:
+                tp.logger.error('| CI | -- | pb_bound must give one potential and one gradient, or both potentials '
+                                '(calculator_old.py:703-705, :776-803)')
                 sys.exit()
-            par[c, 3 * S + 2] = wall
-            par[c, 3 * S + 3] = gb
+            if bc_code is None:
+                bc_code = bc[0]
+            elif bc_code != bc[0]:
+                tp.logger.error('| CI | -- | the kind of Poisson boundary changes along the descriptor grid; cannot batch')
+                sys.exit()
+            par[c, 3 * S + 2], par[c, 3 * S + 6], par[c, 3 * S + 7], par[c, 3 * S + 3] = bc[1:]
         par[c, 3 * S + 4] = m.system['Stern capacitance'] * 1e-2     # micro F/cm^2 -> F/m^2
         if mesh is None:
             par[c, 3 * S + 5] = m.dx
@@ -120,7 +150,7 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
         kw['flux_eq'] = m0.flux_eq
         kw['fpar'] = np.array([m.fpar for m in models], dtype=float).reshape(B, len(m0.flux_eq.par_names))
     batch = _be.CellBatch(z, reactions, nu, par, nx, use_migration=m0.use_migration, species=names,
-                          poisson_bc=_be.BC_STERN_ROBIN if poisson_bc == 'stern' else _be.BC_DIRICHLET_WALL_NEUMANN_BULK,
+                          poisson_bc=_be.BC_STERN_ROBIN if poisson_bc == 'stern' else bc_code,
                           **kw)
     return batch, models
 
@@ -174,12 +204,13 @@ class Calculator():
         if self.calc not in self.calc_list:
             self.tp.logger.error('No calculator found with this name. Aborting.')
             sys.exit()
-        if self.calc not in FD_ODE_CALCS:
+        if self.calc not in FD_ODE_CALCS + FD_STEP_CALCS:
             self.tp.logger.error('| CI | -- | calculator "{}" is outside the scope of the B200 FD-PNP backend '
-                                 '(available: {})'.format(self.calc, FD_ODE_CALCS))
+                                 '(available: {})'.format(self.calc, FD_ODE_CALCS + FD_STEP_CALCS))
             sys.exit()
-        if self.use_lax_friedrich:
-            self.tp.logger.error('| CI | -- | Lax-Friedrichs terms are not available in the FD-PNP backend')
+        if self.use_lax_friedrich and self.calc not in FD_STEP_CALCS:
+            self.tp.logger.error('| CI | -- | Lax-Friedrichs terms belong to the fixed-step steppers (FTCS--LF, '
+                                 'Crank-Nicolson--LF)')
             sys.exit()
         self.scale_pb_grid = scale_pb_grid
         self.tau_jacobi = tau_jacobi
@@ -252,6 +283,13 @@ class Calculator():
         if backend is None:
             backend = self._backend()
         db = backend.upload(batch, pinned=pinned)
+        if self.calc in FD_STEP_CALCS:
+            return self._step_batch_device(backend, db, y0)
+        if batch.poisson_bc not in (_be.BC_DIRICHLET_WALL_NEUMANN_BULK, _be.BC_STERN_ROBIN):
+            self.tp.logger.error('| CI | -- | the implicit integrator takes the default pb_bound pair (wall potential + '
+                                 'bulk gradient) or the Stern boundary; the other pairs run with calc=FTCS / '
+                                 'Crank-Nicolson')
+            sys.exit()
         mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT
         y0_dev = None
         if y0 is not None:
@@ -260,6 +298,33 @@ class Calculator():
                             max_steps=self.max_steps, y0=y0_dev)
         out = dict(out)
         out['h2d_bytes'] = db.h2d_bytes + (0 if y0 is None else int(y0_dev.numel() * 8))
+        return out
+
+    def _step_batch_device(self, backend, db, y0):
+        """calc = FTCS / Crank-Nicolson (calculator_old.py:1121-1140): the fixed time mesh of the reference, outputs
+        after the steps in tp.itout (FTCS counts from 0, Crank-Nicolson from 1, as the reference's loops do)"""
+        import torch
+        tp = self.tp
+        b = db.batch
+        stepper = _be.STEPPER_FTCS if self.calc == 'FTCS' else _be.STEPPER_CRANK_NICOLSON
+        first = 0 if stepper == _be.STEPPER_FTCS else 1
+        itout = [i for i in tp.itout if first <= i < tp.nt]
+        if not itout:
+            itout = [tp.nt - 1]
+        c0 = None
+        if y0 is not None:
+            c0 = torch.as_tensor(np.ascontiguousarray(y0, dtype=np.float64)).to(backend.device)
+        out = backend.step(db, stepper, tp.dt, tp.nt, itout, c0=c0, lax_friedrich=self.use_lax_friedrich)
+        B = b.B
+        dev = backend.device
+        finite = torch.isfinite(out['c'][-1]).reshape(B, -1).all(dim=1)
+        out = dict(out)
+        out['flux'] = torch.zeros((B, b.S), dtype=torch.float64, device=dev)
+        out['status'] = torch.where(finite, 0, 4).to(torch.int32)        # CATINT_PNP_CELL_NOT_FINITE
+        out['n_steps'] = torch.full((B,), tp.nt - first, dtype=torch.int32, device=dev)
+        out['n_newton'] = torch.zeros((B,), dtype=torch.int32, device=dev)
+        out['n_setups'] = torch.zeros((B,), dtype=torch.int32, device=dev)
+        out['h2d_bytes'] = db.h2d_bytes
         return out
 
     def solve_batch(self, batch, backend=None, pinned=None, y0=None):

@@ -7,6 +7,7 @@
 
 #include "pnp_kernels.cuh"
 #include "pnp_rhs.cuh"
+#include "pnp_explicit.cuh"
 
 namespace catint {
 #define X(NB) extern template int launch_bdf<NB, false>(SolveParams&, cudaStream_t); \
@@ -270,8 +271,9 @@ extern "C" int catint_pnp_rhs_batch(const CatintPnpShared* sh, const CatintPnpCe
                                     void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
-    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
-        return fail(CATINT_PNP_EINVAL, "catint_pnp_rhs_batch: Stern/Robin Poisson boundary not available (use catint_pnp_solve_batch)");
+    if (sh->poisson_bc != CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_rhs_batch: only the default Poisson boundary (wall potential + bulk gradient); "
+                                       "Stern: catint_pnp_solve_batch, other pb_bound pairs: catint_pnp_potential_batch / _step_batch");
     if (!c || !dcdt) return fail(CATINT_PNP_EINVAL, "c / dcdt are NULL");
     RhsParams P;
     rc = build_tables(sh, P.tb);
@@ -297,8 +299,8 @@ extern "C" int catint_pnp_jacobian_batch(const CatintPnpShared* sh, const Catint
                                          void* cuda_stream) {
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
-    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN)
-        return fail(CATINT_PNP_EINVAL, "catint_pnp_jacobian_batch: Stern/Robin Poisson boundary not available");
+    if (sh->poisson_bc != CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_jacobian_batch: only the default Poisson boundary");
     if (!y) return fail(CATINT_PNP_EINVAL, "y is NULL");
     JacParams P;
     rc = build_tables(sh, P.tb);
@@ -321,6 +323,9 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
     if (sh->nx_max < CATINT_PNP_MIN_NODES) return fail(CATINT_PNP_EINVAL, "nx_max must be >= CATINT_PNP_MIN_NODES");
+    if (sh->poisson_bc != CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK && sh->poisson_bc != CATINT_PNP_BC_STERN_ROBIN)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_solve_batch: Poisson boundary must be the default pair or Stern "
+                                       "(the other pb_bound pairs run in catint_pnp_step_batch)");
     if (!ctl || !ctl->t_out || ctl->n_out < 1) return fail(CATINT_PNP_EINVAL, "control / t_out missing");
     if (!c_out || !status || !n_steps || !n_newton) return fail(CATINT_PNP_EINVAL, "output pointers are NULL");
     if (!(ctl->rtol >= 0.0) || !(ctl->atol > 0.0)) return fail(CATINT_PNP_EINVAL, "need rtol >= 0 and atol > 0");
@@ -367,5 +372,55 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
         DISPATCH_NB(nb, launch_bdf, false, P, st);
     }
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
+    return rc;
+}
+
+static int check_explicit(const CatintPnpShared* sh, const CatintPnpCells* cells) {
+    if (sh->poisson_bc == CATINT_PNP_BC_STERN_ROBIN || sh->poisson_bc < 0 || sh->poisson_bc > CATINT_PNP_BC_DIRICHLET_BULK_NEUMANN_BULK)
+        return fail(CATINT_PNP_EINVAL, "Poisson boundary must be one of the reference's pb_bound pairs (not Stern)");
+    if (cells->mesh_id || sh->n_mesh > 0) return fail(CATINT_PNP_EINVAL, "the reference's Poisson routine and fixed-step steppers need a uniform mesh");
+    if (sh->flux_eq && sh->flux_eq->n_eq > 0) return fail(CATINT_PNP_EINVAL, "flux equations are not available in the fixed-step steppers");
+    return CATINT_PNP_OK;
+}
+
+extern "C" int catint_pnp_potential_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                          const double* c, double* v, double* grad_v, double* lapl_v, void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    rc = check_explicit(sh, cells);
+    if (rc) return rc;
+    if (!c) return fail(CATINT_PNP_EINVAL, "c is NULL");
+    PotentialParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.c = c; P.n_cells = n_cells;
+    P.v = v; P.grad = grad_v; P.lapl = lapl_v; P.bc = sh->poisson_bc;
+    rc = launch_potential(P, (cudaStream_t)cuda_stream);
+    if (rc == CATINT_PNP_EINVAL) return fail(rc, "pnp_potential_kernel: grid too large for shared memory");
+    if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_potential_kernel launch failed");
+    return rc;
+}
+
+extern "C" int catint_pnp_step_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                                     const double* c0, int32_t stepper, int32_t lax_friedrich, double dt, int32_t nt,
+                                     const int32_t* itout, int32_t n_out,
+                                     double* c_out, double* phi_out, double* g_out, void* cuda_stream) {
+    int rc = check_common(sh, cells, n_cells);
+    if (rc) return rc;
+    rc = check_explicit(sh, cells);
+    if (rc) return rc;
+    if (!c0 || !c_out || !itout) return fail(CATINT_PNP_EINVAL, "c0 / c_out / itout are NULL");
+    if (stepper != CATINT_PNP_STEPPER_FTCS && stepper != CATINT_PNP_STEPPER_CRANK_NICOLSON)
+        return fail(CATINT_PNP_EINVAL, "unknown stepper");
+    if (!(dt > 0.0) || nt < 1 || n_out < 1) return fail(CATINT_PNP_EINVAL, "need dt > 0, nt >= 1, n_out >= 1");
+    ExplicitParams P;
+    rc = build_tables(sh, P.tb);
+    if (rc) return rc;
+    P.par = cells->par; P.nx = cells->nx; P.c0 = c0; P.n_cells = n_cells;
+    P.method = stepper; P.lax_friedrich = lax_friedrich; P.nt = nt; P.n_out = n_out; P.dt = dt;
+    P.itout = itout; P.c_out = c_out; P.phi_out = phi_out; P.g_out = g_out; P.bc = sh->poisson_bc;
+    rc = launch_explicit(P, (cudaStream_t)cuda_stream);
+    if (rc == CATINT_PNP_EINVAL) return fail(rc, "pnp_explicit_kernel: grid too large for shared memory ((3S+3)*nx_max doubles per cell)");
+    if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_explicit_kernel launch failed");
     return rc;
 }

@@ -63,7 +63,16 @@ enum {
     CATINT_PNP_ENODEV = -4       /* no sm_100 device                     */
 };
 
-enum { CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK = 0, CATINT_PNP_BC_STERN_ROBIN = 1 };
+/* Poisson boundary conditions = the reference's pb_bound combinations (catint/calculator_old.py:776-803; exactly one
+   gradient and one potential, or both potentials).  0 is the reference default (catint/transport.py:1278-1322) and,
+   with 1 (Stern/Robin wall, phi carried as an unknown; extension), what K1-K3 handle; 2-5 are available in
+   catint_pnp_potential_batch and in the fixed-step steppers of catint_pnp_step_batch.                          */
+enum { CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK = 0, CATINT_PNP_BC_STERN_ROBIN = 1,
+       CATINT_PNP_BC_DIRICHLET_BOTH = 2,               /* potential at wall and bulk                           */
+       CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_WALL = 3,  /* potential and gradient at the wall                   */
+       CATINT_PNP_BC_DIRICHLET_BULK_NEUMANN_WALL = 4,  /* potential in the bulk, gradient at the wall          */
+       CATINT_PNP_BC_DIRICHLET_BULK_NEUMANN_BULK = 5   /* potential and gradient in the bulk                   */ };
+enum { CATINT_PNP_STEPPER_FTCS = 0, CATINT_PNP_STEPPER_CRANK_NICOLSON = 1 };
 enum { CATINT_PNP_MODE_TRANSIENT = 0, CATINT_PNP_MODE_STEADY = 1,
        CATINT_PNP_MODE_MASK = 0xff,
        /* flag, OR-ed into CatintPnpControl.mode: keep every species in the block system.  By default a steady solve
@@ -143,8 +152,8 @@ typedef struct CatintPnpFluxEq {
 #define CATINT_PNP_P_GBULK(S)   (3 * (S) + 3) /* Neumann bulk gradient      | Stern: unused           */
 #define CATINT_PNP_P_CSTERN(S)  (3 * (S) + 4) /* Stern capacitance F/m^2                              */
 #define CATINT_PNP_P_SCALE(S)   (3 * (S) + 5) /* uniform mesh: dx ; mesh table: x = scale*xi          */
-#define CATINT_PNP_P_RSV0(S)    (3 * (S) + 6)
-#define CATINT_PNP_P_RSV1(S)    (3 * (S) + 7)
+#define CATINT_PNP_P_PHIBULK(S) (3 * (S) + 6) /* Dirichlet bulk potential (BC modes 2, 4, 5)                */
+#define CATINT_PNP_P_GWALL(S)   (3 * (S) + 7) /* Neumann wall gradient    (BC modes 3, 4)                   */
 
 /* Per-cell structure-of-arrays (DEVICE pointers). */
 typedef struct CatintPnpCells {
@@ -205,6 +214,22 @@ int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnpCells* cell
                            double* c_out, double* phi_out, double* g_out, double* flux_out,
                            int32_t* status, int32_t* n_steps, int32_t* n_newton, int32_t* n_setups,
                            void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* get_potential_and_gradient (catint/calculator_old.py:680-819) for every pb_bound combination:
+ *   c [B][nx_max][S] -> v, grad_v, lapl_v [B][nx_max] (any output may be NULL).  Uniform meshes.               */
+int catint_pnp_potential_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                               const double* c, double* v, double* grad_v, double* lapl_v, void* cuda_stream);
+
+/* K4: the reference's fixed-step steppers, integrate_FTCS (catint/calculator_old.py:976-1029) and
+ * integrate_Crank_Nicolson (:457-564), dispatch :1121-1140: nt steps of size dt from c0 [B][nx_max][S] (NULL: bulk
+ * everywhere), the state after step itout[k] (DEVICE int32 [n_out], increasing; FTCS counts steps from 0,
+ * Crank-Nicolson from 1 as the reference does) goes to c_out [n_out][B][nx_max][S]; phi_out / g_out
+ * [n_out][B][nx_max] optional (the field the step was taken with).  Wall potential of the Robin condition
+ * ("vzeta") = CATINT_PNP_P_PHIWALL.  Uniform meshes, every pb_bound combination but Stern.                     */
+int catint_pnp_step_batch(const CatintPnpShared* sh, const CatintPnpCells* cells, int64_t n_cells,
+                          const double* c0, int32_t stepper, int32_t lax_friedrich, double dt, int32_t nt,
+                          const int32_t* itout, int32_t n_out,
+                          double* c_out, double* phi_out, double* g_out, void* cuda_stream);
 
 #ifdef __cplusplus
 }
