@@ -33,7 +33,8 @@ def test_calc_names(resultsdir):
     assert Calculator(transport=tp, dt=1, tmax=2, calc='lsoda').calc == 'lsoda'
     c = Calculator(transport=tp, dt=1, tmax=2, calc='vode--bdf')
     assert (c.calc, c.calc_method) == ('vode', 'bdf')
-    for bad in ('nonsense', 'comsol', 'FTCS', 'odeint--LF'):
+    assert Calculator(transport=tp, dt=1, tmax=2, calc='FTCS').calc == 'FTCS'        # K4 (tests/test_explicit.py)
+    for bad in ('nonsense', 'comsol', 'dopri5', 'odeint--LF'):
         with pytest.raises(SystemExit):
             Calculator(transport=tp, dt=1, tmax=2, calc=bad)
     with pytest.raises(SystemExit):
