@@ -220,12 +220,33 @@ class CellBatch(object):
             sh._fq_keepalive = fq
         return sh
 
+    def passive_species(self):
+        """indices of the species a steady solve takes out of the block system (same rule as reduce_passive in
+        csrc/pnp_capi.cu): no charge or migration off, no part in any homogeneous reaction, not read by a flux
+        equation.  Host-side mirror for reporting (bench roofline, tests); the library decides on its own."""
+        passive = [(int(self.z[k]) == 0 or not self.use_migration) for k in range(self.S)]
+        for (ed, pr, kf, kr) in self.reactions:
+            for k in list(ed) + list(pr):
+                passive[k] = False
+        for k in range(self.S):
+            if self.R and np.any(self.nu[k] != 0.0):
+                passive[k] = False
+        if self.flux_eq is not None:
+            for prog in self.flux_eq.programs:
+                for w in prog.code:
+                    if (w & 0xff) == 2:
+                        passive[w >> 8] = False
+        idx = [k for k in range(self.S) if passive[k]]
+        return idx if 0 < len(idx) < self.S else []
+
     def launch_order(self):
-        """cells sorted by predicted integration cost, expensive first (int32 permutation).  The cost of a cell
-        grows with the gradients its wall fluxes impose: sum_k |J_k| / D_k * L relative to the total bulk
-        concentration (measured on the C2 sweep: BDF steps 800 -> 1700 along this number).  Only the launch
-        order depends on it: with one cell per thread block the expensive cells start first and land on
-        different SMs."""
+        """cells sorted by predicted integration cost, expensive first (int32 permutation; longest processing time
+        first).  The cost of a cell grows with the gradients its wall fluxes impose: sum_k |J_k| / D_k * L relative
+        to the total bulk concentration (C2 sweep: 800 -> 1400 BDF steps along this number; the outliers with 1700
+        steps sit where the Tafel current saturates and are not predictable from the inputs).  Only the schedule
+        depends on it.  Measured on the 1024-cell C2 launch: -1.5 %; an SM-aware variant (expensive blocks placed on
+        the 40 SMs that get no second block -- block j and j+148 do share an SM) gained nothing because the
+        slowest cells are exactly those outliers."""
         S = self.S
         L = self.par[:, 3 * S + 5] * np.maximum(self.nx - 1, 1)
         if self.mesh_id is not None and self.mesh_xi is not None:

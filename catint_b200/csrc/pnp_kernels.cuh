@@ -893,6 +893,9 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             P.n_newton[cell] = nni;
             if (P.n_setups) P.n_setups[cell] = nsetups;
             if (prof_on) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                pc[4] = smid;                               // slot 4 (norms, fused into the sweeps long ago) reports the SM
                 pc[7] = clock64() - t_kernel0;
                 for (int k_ = 0; k_ < 8; ++k_) P.prof[cell * 8 + k_] = pc[k_];
             }

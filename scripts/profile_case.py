@@ -38,6 +38,13 @@ def main():
         tot = prof[:, 7].double().cpu().numpy(); print('total cycles min/mean/max %.3g %.3g %.3g' % (tot.min(), tot.mean(), tot.max()))
         j = int(tot.argmax()); pj = prof[j].cpu().numpy()
         print('slowest cell %d: steps %d newton %d setups %d cycles %s' % (j, stp[j], nw[j], sts[j], [int(v) for v in pj]))
+        sm = prof[:, 4].cpu().numpy()
+        per_sm = np.bincount(sm, minlength=148)
+        order = np.argsort(-tot)
+        print('cells per SM: min %d max %d; SMs with >4 cells: %d' % (per_sm.min(), per_sm.max(), int((per_sm > 4).sum())))
+        print('the 16 slowest cells sit on SMs holding', [int(per_sm[sm[j]]) for j in order[:16]], 'cells; launch slots of those cells:',
+              [int(np.where(batch.launch_order() == j)[0][0]) for j in order[:16]])
+        print('SM of launch slots 0,4,8,...,44:', [int(sm[batch.launch_order()[k]]) for k in range(0, 48, 4)], ' slots 592.. :', [int(sm[batch.launch_order()[k]]) for k in range(592, 640, 4)])
         pr = prof.double().mean(dim=0).cpu().numpy()
         names = ['factor', 'residual', 'forward', 'backward', 'norms', 'history', 'correction', 'total']
         print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})
