@@ -33,8 +33,17 @@ constexpr int LMAX = QMAX + 1;     // Nordsieck vectors zn[0..QMAX]
 constexpr double ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
 constexpr double ETAMX1 = 1e4, ETAMX2 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1, ETACF = 0.25, THRESH = 1.5;
 constexpr int MXNCF = 10, MXNEF = 7, MXNEF1 = 3, SMALL_NEF = 2, LONG_WAIT = 10;
-constexpr int MAXCOR = 3, MSBP = 8;       // VODE's default is 20; measured on C2: 8 cuts the BDF steps by 18 %
-constexpr double CRDOWN = 0.3, RDIV = 2.0, NLSCOEF = 0.1, DGMAX = 0.3;
+#ifndef CATINT_MSBP
+#define CATINT_MSBP 6
+#endif
+#ifndef CATINT_NLSCOEF
+#define CATINT_NLSCOEF 0.1
+#endif
+#ifndef CATINT_DGMAX
+#define CATINT_DGMAX 0.3
+#endif
+constexpr int MAXCOR = 3, MSBP = CATINT_MSBP;       // VODE default 20; measured on C2: 8 -> 18 % fewer steps; 6 is best once the 7x7 factorisation is cheap
+constexpr double CRDOWN = 0.3, RDIV = 2.0, NLSCOEF = CATINT_NLSCOEF, DGMAX = CATINT_DGMAX;
 
 struct SolveParams {
     DevTables tb;
