@@ -102,23 +102,36 @@ __device__ __forceinline__ double pivot_rcp(double a) {
 // the original row of every slot (4 bits each, uniform per half warp); a final shuffle hands every
 // lane its own column (skipped when no half warp swapped rows, the common case: the algebraic rows are
 // pre-scaled so that the diagonal is an acceptable pivot).  Returns false on a zero/non-finite pivot.
+// 64-bit shuffle from two explicit 32-bit ones (the compiler's own expansion of __shfl_sync(double) came with
+// register-pair swaps: three XORs per value in the elimination loop)
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    const int lo = __shfl_sync(FULL, __double2loint(v), src);
+    const int hi = __shfl_sync(FULL, __double2hiint(v), src);
+    return __hiloint2double(hi, lo);
+}
+
 template <int NB, bool ST>
 __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int l, int hbase) {
     static_assert(NB <= 15, "NB+1 columns per half warp");
-    bool ok = true;
-    bool swapped = false;
-    unsigned long long orig = 0xFEDCBA9876543210ull;
-    int mysrc = l;
+    bool bad = false;
+    unsigned long long plist = 0;                      // pivot slot of every step, 4 bits each (all zero: no swap)
 #pragma unroll 1
     for (int k = 0; k < NB; ++k) {
-        // magnitude keys: high word of |a| with the slot index in the low 4 bits
-        int best = (__double2hiint(A[0]) & 0x7ffffff0);
-        const int diag = best;
+        // reciprocal of the diagonal candidate, computed by every lane for its own column BEFORE the pivot
+        // decision: in the common case (no swap) the owner's value is simply broadcast with the column and
+        // the MUFU + Newton chain (~60 cycles) runs beside the pivot search instead of after the shuffles
+        double myinv = pivot_rcp(A[0]);
+        // magnitude keys: high word of |a| with the slot index in the low 4 bits; tree reduction
+        int key[NB];
+        key[0] = __double2hiint(A[0]) & 0x7ffffff0;
 #pragma unroll
-        for (int r = 1; r < NB; ++r) {
-            const int key = (r < NB - k) ? ((__double2hiint(A[r]) & 0x7ffffff0) | r) : 0;
-            best = max(best, key);
-        }
+        for (int r = 1; r < NB; ++r) key[r] = (r < NB - k) ? ((__double2hiint(A[r]) & 0x7ffffff0) | r) : 0;
+        const int diag = key[0];
+#pragma unroll
+        for (int w = 1; w < NB; w <<= 1)
+#pragma unroll
+            for (int r = 0; r + w < NB; r += 2 * w) key[r] = max(key[r], key[r + w]);
+        const int best = key[0];
         // keep the diagonal unless another entry is more than 8x larger (3 exponent steps)
         int p = best & 0xf;
         if (diag + (3 << 20) >= best) p = 0;
@@ -130,31 +143,40 @@ __device__ __forceinline__ bool gauss_jordan(double (&A)[NB], int l, int hbase) 
                 if (r == p) { const double t = A[r]; A[r] = a0; a0 = t; }
             }
             A[0] = a0;
-            const unsigned long long x = ((orig >> (4 * p)) ^ orig) & 0xfull;
-            orig ^= x | (x << (4 * p));
-            swapped = true;
+            myinv = pivot_rcp(a0);
+            plist |= (unsigned long long)p << (4 * k);
         }
-        const int pk = (int)(orig & 0xfull);           // original row of this step's pivot row
-        if (pk == l) mysrc = k;
-        orig = ((orig >> 4) & ~(0xfull << (4 * (NB - 1)))) | ((unsigned long long)pk << (4 * (NB - 1)));
         double col[NB];
 #pragma unroll
-        for (int r = 0; r < NB; ++r) col[r] = __shfl_sync(FULL, A[r], hbase + k);
-        const double ck = col[0];
-        const double inv = pivot_rcp(ck);
-        ok = ok && (ck != 0.0) && (fabs(inv) < 1e300);
+        for (int r = 0; r < NB; ++r) col[r] = shfl_f64(A[r], hbase + k);
+        const double inv = shfl_f64(myinv, hbase + k);
+        bad = bad || !(fabs(inv) < 1e300);             // zero / denormal / non-finite pivot
         const bool own = l == k;                       // the pivot column itself: continue with e_k in its place
         const double a0 = (own ? 1.0 : A[0]) * inv;
 #pragma unroll
         for (int r = 1; r < NB; ++r) A[r - 1] = fma(-col[r], a0, own ? 0.0 : A[r]);     // eliminate and rotate
         A[NB - 1] = a0;
     }
-    if (__any_sync(FULL, swapped)) {
+    if (__any_sync(FULL, plist != 0)) {
+        // rows were swapped in some half warp (rare: the algebraic rows are pre-scaled): replay the bookkeeping --
+        // `orig` tracks the original row of every slot -- to find which lane holds my column of the inverse
+        unsigned long long orig = 0xFEDCBA9876543210ull;
+        int mysrc = l;
+        for (int k = 0; k < NB; ++k) {
+            const int p = (int)((plist >> (4 * k)) & 0xfull);
+            if (p != 0) {
+                const unsigned long long x = ((orig >> (4 * p)) ^ orig) & 0xfull;
+                orig ^= x | (x << (4 * p));
+            }
+            const int pk = (int)(orig & 0xfull);       // original row of this step's pivot row
+            if (pk == l) mysrc = k;
+            orig = ((orig >> 4) & ~(0xfull << (4 * (NB - 1)))) | ((unsigned long long)pk << (4 * (NB - 1)));
+        }
         const int src = hbase + (l < NB ? mysrc : l);
 #pragma unroll
-        for (int r = 0; r < NB; ++r) A[r] = __shfl_sync(FULL, A[r], src);
+        for (int r = 0; r < NB; ++r) A[r] = shfl_f64(A[r], src);
     }
-    return ok;
+    return !bad;
 }
 
 // ---------------------------------------------------------------------------
