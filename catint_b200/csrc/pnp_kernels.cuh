@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
                 if (call_setup) {
                     CATINT_TIC;
                     bool ok;
-                    ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid);
+                    ok = factor_nodes<NB, ST, SMEM>(ws, so, inv_gamma, mid, prof_on ? P.prof + cell * 8 + 4 : nullptr);
                     CATINT_TOC(0);
                     ++nsetups;
                     have_factors = ok;
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
         for (int it = 0; it < P.polish_max_iter && !done; ++it) {
             // true Newton on the steady residual: inv_gamma = 0 removes the mass term
             bool ok;
-            ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid);
+            ok = factor_nodes<NB, ST, SMEM>(ws, so, 0.0, mid, nullptr);
             ++nsetups;
             if (!ok) break;
             residual_pass<NB, ST>(ws, 0.0);
@@ -902,11 +902,10 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             P.n_newton[cell] = nni;
             if (P.n_setups) P.n_setups[cell] = nsetups;
             if (prof_on) {
-                unsigned smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                pc[4] = smid;                               // slot 4 (norms, fused into the sweeps long ago) reports the SM
+                // slot 4 (norms, fused into the sweeps long ago) holds the assembly part of the factorisation,
+                // accumulated by factor_nodes itself
                 pc[7] = clock64() - t_kernel0;
-                for (int k_ = 0; k_ < 8; ++k_) P.prof[cell * 8 + k_] = pc[k_];
+                for (int k_ = 0; k_ < 8; ++k_) if (k_ != 4) P.prof[cell * 8 + k_] = pc[k_];
             }
         }
     }

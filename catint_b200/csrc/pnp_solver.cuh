@@ -684,7 +684,7 @@ struct SmemOffsets { unsigned scratch, sp, y, ring; };
 
 template <int NB, bool ST, bool SMEM>
 __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const SmemOffsets so, double inv_gamma,
-                                          int mid) {
+                                          int mid, long long* prof_assembly) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
     constexpr int REC = fac_rec<NB, ST>();
@@ -700,6 +700,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
     const bool mig = ws.tb->use_migration;
     const double* y = ws.y;
 
+    const long long t_asm = prof_assembly ? clock64() : 0;
     wall_flux_jacobian<NB, ST>(ws, y);            // flux equations: dJ/dy_0 for the wall block (no-op without them)
     // ---- assembly of all node records: [ A_D (raw, interior nodes) | l, a, ud, ua per row ] ----
     for (int item = lane; item < n * NB; item += 32) {
@@ -718,6 +719,7 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
         st_hint4(rec + NB * NBP + 4 * r, co, ws.keep);
     }
     __syncwarp();
+    if (prof_assembly && lane == 0) *prof_assembly += clock64() - t_asm;     // debug profile: cycles of the assembly
 
     // ---- elimination: top chain 0..mid in the lower half warp, bottom chain n-1..mid+1 in the upper ----
     const int grp = lane >> 4;

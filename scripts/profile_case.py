@@ -22,6 +22,7 @@ def main():
     if os.environ.get('CATINT_PHASES'):
         bk.lib.catint_pnp_debug_profile_buffer(prof.data_ptr())
     for rep in range(2):
+        prof.zero_()
         torch.cuda.synchronize(); t0 = time.time()
         bk.solve(db, [bench.T_END], mode=be.MODE_STEADY | (be.MODE_KEEP_ALL if os.environ.get('CATINT_KEEP_ALL') else 0), max_steps=max_steps, out=out)
         torch.cuda.synchronize(); dt = time.time() - t0
@@ -38,17 +39,10 @@ def main():
         tot = prof[:, 7].double().cpu().numpy(); print('total cycles min/mean/max %.3g %.3g %.3g' % (tot.min(), tot.mean(), tot.max()))
         j = int(tot.argmax()); pj = prof[j].cpu().numpy()
         print('slowest cell %d: steps %d newton %d setups %d cycles %s' % (j, stp[j], nw[j], sts[j], [int(v) for v in pj]))
-        sm = prof[:, 4].cpu().numpy()
-        per_sm = np.bincount(sm, minlength=148)
-        order = np.argsort(-tot)
-        print('cells per SM: min %d max %d; SMs with >4 cells: %d' % (per_sm.min(), per_sm.max(), int((per_sm > 4).sum())))
-        print('the 16 slowest cells sit on SMs holding', [int(per_sm[sm[j]]) for j in order[:16]], 'cells; launch slots of those cells:',
-              [int(np.where(batch.launch_order() == j)[0][0]) for j in order[:16]])
-        print('SM of launch slots 0,4,8,...,44:', [int(sm[batch.launch_order()[k]]) for k in range(0, 48, 4)], ' slots 592.. :', [int(sm[batch.launch_order()[k]]) for k in range(592, 640, 4)])
         pr = prof.double().mean(dim=0).cpu().numpy()
-        names = ['factor', 'residual', 'forward', 'backward', 'norms', 'history', 'correction', 'total']
+        names = ['factor', 'residual', 'forward', 'backward', 'assembly(in factor)', 'history', 'correction', 'total']
         print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})
-        print('per call: factor %.0f cyc, residual %.0f, forward %.0f, backward %.0f, norms %.0f (per newton), history %.0f, correction %.0f (per step)' % (pr[0] / (ns / n_cells), pr[1] / (nn / n_cells), pr[2] / (nn / n_cells), pr[3] / (nn / n_cells), pr[4] / (nn / n_cells), pr[5] / (st / n_cells), pr[6] / (st / n_cells)))
+        print('per call: factor %.0f cyc (assembly %.0f), residual %.0f, forward %.0f, backward %.0f (per newton), history %.0f, correction %.0f (per step)' % (pr[0] / (ns / n_cells), pr[4] / (ns / n_cells), pr[1] / (nn / n_cells), pr[2] / (nn / n_cells), pr[3] / (nn / n_cells), pr[5] / (st / n_cells), pr[6] / (st / n_cells)))
 
 if __name__ == '__main__':
     main()
