@@ -40,7 +40,7 @@ constexpr int RHS_ROUNDS = RHS_NODES / RHS_THREADS;
 constexpr int RHS_NP = RHS_NODES + 3;          // odd pitch of the transposed state (slot = node + 1)
 constexpr int RHS_MAXG = 16;                   // cells per group (tiny grids use fewer slots)
 #ifndef CATINT_RHS_MINB
-#define CATINT_RHS_MINB 2                      // resident blocks per SM the register allocation aims at
+#define CATINT_RHS_MINB 3                      // resident blocks per SM the register allocation aims at
 #endif
 
 // per-cell constants of the cells of a group (shared memory)
@@ -62,9 +62,9 @@ struct RhsProg {
 
 template <int S>
 __host__ __device__ inline size_t rhs_smem_bytes() {
-    size_t b = (sizeof(DevTables) + 15) & ~size_t(15);
+    size_t b = (sizeof(DevTables) + 15) & ~size_t(15);     // upper bound (the kernel copies tables_prefix_bytes)
     b += (sizeof(RhsProg) + 15) & ~size_t(15);
-    b += sizeof(RhsCell) * 2 * RHS_MAXG;            // double-buffered (the next group's cells are filled early)
+    b += sizeof(RhsCell) * RHS_MAXG;
     b += sizeof(double) * ((size_t)S * RHS_NP + 2 * (RHS_NODES + 4) + 2 * RHS_WARPS + 8);
     return b;
 }
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
     }
     size_t off = (sizeof(DevTables) + 15) & ~size_t(15);
     RhsProg* prog = reinterpret_cast<RhsProg*>(smem_raw + off);   off += (sizeof(RhsProg) + 15) & ~size_t(15);
-    RhsCell* cells_all = reinterpret_cast<RhsCell*>(smem_raw + off);  off += sizeof(RhsCell) * 2 * RHS_MAXG;
+    RhsCell* cells_all = reinterpret_cast<RhsCell*>(smem_raw + off);  off += sizeof(RhsCell) * RHS_MAXG;
     double* cs_ = reinterpret_cast<double*>(smem_raw + off);      // [S][RHS_NP] transposed state, slot = node + 1
     double* term = cs_ + (size_t)S * RHS_NP;                      // [RHS_NODES + 4] (F/eps)*sum z c * h_i per slot
     double* gs = term + RHS_NODES + 4;                            // [RHS_NODES + 4] g per slot
@@ -157,21 +157,10 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
             if (ce.xi) { const double h0 = mesh_h(ce, 0), h1 = mesh_h(ce, 1); w0 = 1.0 / (h0 + h1); ih0 = 1.0 / h0; }
             else { w0 = ce.u_ac; ih0 = 2.0 * ce.u_ac; }
             const double g1 = gs[slot + 1];
-            double Jw[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) Jw[s] = ce.J[s];
-            if (tb->fq.n_eq > 0) {
-                // flux equations (pnp_fluxeq.cuh): J = J_fixed + sum_e coef[.][e]*E_e(c(0), phi_wall)
-                for (int e = 0; e < tb->fq.n_eq; ++e) {
-                    const double E = fluxeq_eval(&tb->fq, e, ce.fpar, c0, ce.phi_wall, -1, S, nullptr);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) Jw[s] = fma(tb->fq.coef[s][e], E, Jw[s]);
-                }
-            }
 #pragma unroll
             for (int s = 0; s < S; ++s)                                                  // :902-909, inward flux
                 res[s] = (ce.D[s] * ((cs_[s * RHS_NP + slot + 2] - c0[s]) * w0
-                                     + ce.bF * tb->z[s] * cs_[s * RHS_NP + slot + 1] * g1) + Jw[s]) * ih0;
+                                     + ce.bF * tb->z[s] * cs_[s * RHS_NP + slot + 1] * g1) + ce.J[s]) * ih0;
         } else {
             double am, ap, ac;
             if (ce.xi) {
@@ -272,33 +261,18 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
 
     if constexpr (!LARGE) {
         // ------------------------------------------------------------------ groups of whole cells
-        // Software pipeline: while group g is scanned and computed, the node records of group g+1 are already
-        // in flight into registers and its cell constants are being filled into the other cell buffer, so
-        // the DRAM latency of one group hides behind the arithmetic of the previous one.
+        // (A software-pipelined variant -- node records of group g+1 in flight into registers while group g is
+        // computed -- was measured slower: 64 more live registers per thread spill at 128 registers / thread.)
+        RhsCell* cells = cells_all;
         int G = RHS_NODES / nxm;
         if (G > RHS_MAXG) G = RHS_MAXG;
         const long long n_groups = (P.n_cells + G - 1) / G;
-        double c0[RHS_ROUNDS][S], cn[RHS_ROUNDS][S];
-        int buf = 0;
-        auto prefetch = [&](long long grp, int b) {
+        for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
             const long long cell0 = grp * G;
             const int gc = (int)((P.n_cells - cell0) < G ? (P.n_cells - cell0) : G);
-            if (tid < gc) fill_cell(cells_all[b * RHS_MAXG + tid], cell0 + tid, tid * nxm);
-#pragma unroll
-            for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
-                const int j = tid + rd * RHS_THREADS;
-                const int cg = j / nxm;
-                // padding nodes (i >= nx[cell]) are fetched too (inside the cell's slice) and dropped later
-                if (cg < gc) fetch_node(P.c + ((size_t)cell0 * nxm + j) * S, cn[rd]);
-            }
-        };
-        long long grp = blockIdx.x;
-        if (grp < n_groups) prefetch(grp, buf);
-        for (; grp < n_groups; grp += gridDim.x) {
-            RhsCell* cells = cells_all + buf * RHS_MAXG;
-            const long long cell0 = grp * G;
-            const int gc = (int)((P.n_cells - cell0) < G ? (P.n_cells - cell0) : G);
-            __syncthreads();                       // cells[] of this group visible; everyone is done with the shared state
+            if (tid < gc) fill_cell(cells[tid], cell0 + tid, tid * nxm);
+            __syncthreads();
+            double c0[RHS_ROUNDS][S];
             int ci[RHS_ROUNDS], ii[RHS_ROUNDS];
 #pragma unroll
             for (int rd = 0; rd < RHS_ROUNDS; ++rd) {
@@ -307,12 +281,9 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                 const int i = j - cg * nxm;
                 const bool valid = cg < gc && i < cells[cg < gc ? cg : 0].n;
                 ci[rd] = valid ? cg : -1; ii[rd] = i;
-#pragma unroll
-                for (int s = 0; s < S; ++s) c0[rd][s] = cn[rd][s];
-                if (valid) publish_node(cells[cg], j + 1, i, c0[rd]);
+                if (valid) load_node(cells[cg], P.c + ((size_t)(cell0 + cg) * nxm + i) * S, j + 1, i, c0[rd]);
             }
             __syncthreads();
-            if (grp + gridDim.x < n_groups) prefetch(grp + gridDim.x, buf ^ 1);
             // g per cell: warp-per-cell suffix scan from the bulk (:753-759,793-796)
             for (int cg = warp; cg < gc; cg += RHS_WARPS) {
                 const RhsCell& ce = cells[cg];
@@ -320,12 +291,21 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                 if (n == 0) continue;
                 double* gc_ = gs + ce.first + 1;                    // g of this cell, indexed by node
                 const double* tc_ = term + ce.first + 1;
+                // four consecutive nodes per lane (serial partial sums) + one warp scan per 128 nodes: a 101-node
+                // cell needs one round of five shuffle steps instead of four rounds
                 double carry = 0.0;
-                for (int top = n - 2; top >= 1; top -= 32) {
-                    const int i = top - lane;
-                    const double t = warp_scan(i >= 1 ? tc_[i] : 0.0, lane);
-                    if (i >= 1) gc_[i] = mig ? ce.g_bulk + (carry + t) : 0.0;
-                    carry += __shfl_sync(FULL, t, 31);
+                for (int top = n - 2; top >= 1; top -= 128) {
+                    const int i0 = top - 4 * lane;
+                    double t[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) t[q] = (i0 - q >= 1) ? tc_[i0 - q] : 0.0;
+                    t[1] += t[0]; t[2] += t[1]; t[3] += t[2];
+                    const double incl = warp_scan(t[3], lane);
+                    const double base = carry + (incl - t[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (i0 - q >= 1) gc_[i0 - q] = mig ? ce.g_bulk + (base + t[q]) : 0.0;
+                    carry += __shfl_sync(FULL, incl, 31);
                 }
                 if (lane == 0) gc_[n - 1] = mig ? ce.g_bulk : 0.0;
                 __syncwarp();
@@ -345,7 +325,7 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                     node_rhs(cells[ci[rd]], c0[rd], j + 1, ii[rd], P.dcdt + ((size_t)(cell0 + ci[rd]) * nxm + ii[rd]) * S);
                 }
             }
-            buf ^= 1;
+            __syncthreads();
         }
     } else {
         // ------------------------------------------------------------------ tiles of one large cell
@@ -418,6 +398,30 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
     }
 }
 
+// Flux equations (pnp_fluxeq.cuh): the wall rows get ih0 * sum_e coef[.][e]*E_e(c(0), phi_wall) on top of the
+// fixed flux.  A separate one-thread-per-cell kernel after the streaming kernel: inside it, the call into the
+// expression interpreter cost every launch 15 % (register pressure around the call), with or without flux equations.
+__global__ void __launch_bounds__(128) pnp_rhs_fluxeq_kernel(RhsParams P) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= P.n_cells) return;
+    const DevTables& tb = P.tb;
+    const int S = tb.S, nxm = tb.nx_max;
+    const int n = P.nx[cell];
+    if (n < 4 || n > nxm) return;
+    const double* p = P.par + (size_t)cell * (3 * S + 8);
+    const int mid = P.mesh_id ? P.mesh_id[cell] : -1;
+    const double dx = p[3 * S + 5];
+    const double h0 = mid < 0 ? dx : dx * (P.mesh_xi[(size_t)mid * nxm + 1] - P.mesh_xi[(size_t)mid * nxm]);
+    const double ih0 = 1.0 / h0;
+    const double* c0 = P.c + (size_t)cell * nxm * S;
+    double* out = P.dcdt + (size_t)cell * nxm * S;
+    const double* fpar = tb.fpar ? tb.fpar + (size_t)cell * tb.fq.n_par : nullptr;
+    for (int e = 0; e < tb.fq.n_eq; ++e) {
+        const double E = fluxeq_eval(&tb.fq, e, fpar, c0, p[3 * S + 2], -1, S, nullptr) * ih0;
+        for (int s = 0; s < S; ++s) out[s] = fma(tb.fq.coef[s][e], E, out[s]);
+    }
+}
+
 template <int S>
 int launch_rhs(RhsParams& P, cudaStream_t st) {
     const size_t smem = rhs_smem_bytes<S>();
@@ -446,6 +450,7 @@ int launch_rhs(RhsParams& P, cudaStream_t st) {
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (large) pnp_rhs_kernel<S, true><<<grid, RHS_THREADS, smem, st>>>(P);
     else pnp_rhs_kernel<S, false><<<grid, RHS_THREADS, smem, st>>>(P);
+    if (P.tb.fq.n_eq > 0) pnp_rhs_fluxeq_kernel<<<(unsigned)((P.n_cells + 127) / 128), 128, 0, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 
