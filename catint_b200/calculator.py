@@ -165,7 +165,7 @@ class Calculator():
     def __init__(self, transport=None, dt=None, tmax=None, ntout=1, calc=None,
                  scale_pb_grid=None, tau_jacobi=1e-7, tau_scf=5e-5, mix_scf=0.5, mode='time-dependent',
                  rtol=1.49012e-8, atol=1.49012e-8, rate_mode='summed', device=None, max_steps=100000,
-                 poisson_bc='dirichlet', mesh=None):
+                 poisson_bc='dirichlet', mesh=None, continuation=None):
         """Reference keywords (calculator.py:55-56) plus backend options:
         rtol/atol  error tolerances of the BDF integrator (scipy odeint defaults)
         rate_mode  'summed' (default) or 'legacy_overwrite' 
@@ -173,6 +173,11 @@ class Calculator():
         mesh       optional normalised non-uniform node positions (see build_cell_batch)
         mode       'time-dependent': state at the output times of the time mesh
                    'stationary': integrate to tmax, then Newton-polish the steady residual
+        continuation  None (every cell starts from the bulk state, the reference's 'internal-reinit',
+                   transport.py:834-842) or an integer k >= 2 ('internal-cont' for a batch): every k-th cell of the
+                   sweep is solved cold, the cells in between start from the converged state of the nearest cold
+                   cell and are integrated over the same time span.  Stationary mode only; the warm cells reach
+                   the same steady state with a fraction of the steps (see Calculator.run_continuation).
         """
         self.mode = mode
         self.tau_scf = tau_scf
@@ -220,6 +225,10 @@ class Calculator():
         self.mesh = mesh
         self.device = device
         self.max_steps = max_steps
+        self.continuation = continuation
+        if continuation is not None and (int(continuation) < 2 or mode != 'stationary'):
+            self.tp.logger.error('| CI | -- | continuation needs an integer >= 2 and mode="stationary"')
+            sys.exit()
 
         # time mesh and output indices (calculator.py:105-138)
         if dt is not None:
@@ -381,7 +390,9 @@ class Calculator():
             batch.B, len(tp.descriptors[keys[0]]), len(tp.descriptors[keys[1]])))
         from . import distributed as _dist
         y0 = self.initial_state_from_folder(batch)
-        if y0 is None:
+        if y0 is None and self.continuation is not None:
+            res = self.run_continuation(batch)
+        elif y0 is None:
             res = _dist.solve_sharded(self, batch)
         else:
             res = _dist.solve_sharded(self, batch,
@@ -400,6 +411,53 @@ class Calculator():
         return res
 
     # ------------------------------------------------------------------
+    def run_continuation(self, batch):
+        """two waves over a sweep (the batch analogue of the reference's COMSOL option 'internal-cont',
+        transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
+        wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
+        nearest wave-1 neighbour, over the full time span (so a wrong starting guess costs steps, not accuracy).
+        Both waves are sharded like a plain run.  Returns the result dict of the whole batch."""
+        from . import distributed as _dist
+        k = int(self.continuation)
+        B = batch.B
+        cold = np.arange(0, B, k)
+        if cold[-1] != B - 1:
+            cold = np.append(cold, B - 1)
+        warm = np.setdiff1d(np.arange(B), cold)
+        r1 = _dist.solve_sharded(self, batch.select(cold))
+        if r1 is None:
+            return None
+        if len(warm) == 0:
+            return r1
+        nearest = cold[np.argmin(np.abs(warm[:, None] - cold[None, :]), axis=1)]
+        pos = {int(c): i for i, c in enumerate(cold)}
+        y0 = np.stack([r1['c'][-1, pos[int(c)]] for c in nearest])                     # [n_warm, nx_max, S]
+        ok = np.array([r1['status'][pos[int(c)]] == 0 for c in nearest])
+        for j in np.where(~ok)[0]:                                                     # failed neighbour: cold start
+            y0[j] = batch.par[warm[j], None, 0:batch.S]
+        sub = batch.select(warm)
+        sub.origin = np.arange(sub.B)                  # shards of `sub` index y0 by their position in `sub`
+        r2 = _dist.solve_sharded(self, sub, solve_fn=lambda sb: self.solve_batch_device(sb, y0=y0[sb.origin]))
+        res = {}
+        for key, v in r1.items():
+            if not hasattr(v, 'shape') or v.ndim == 0:
+                res[key] = v
+                continue
+            ax = 1 if key in ('c', 'phi', 'g') else 0
+            shape = list(v.shape)
+            shape[ax] = B
+            full = np.zeros(shape, dtype=v.dtype)
+            idx1 = [slice(None)] * v.ndim
+            idx2 = [slice(None)] * v.ndim
+            idx1[ax], idx2[ax] = cold, warm
+            full[tuple(idx1)] = v
+            full[tuple(idx2)] = r2[key]
+            res[key] = full
+        self.continuation_stats = {'cold_cells': len(cold), 'warm_cells': len(warm),
+                                   'cold_steps_mean': float(np.mean(r1['n_steps'])),
+                                   'warm_steps_mean': float(np.mean(r2['n_steps']))}
+        return res
+
     def scatter_results(self, batch, models, res):
         """fill tp.cout/potential/efield/total_charge (last cell, like the serial
         reference loop would leave them) and tp.alldata[i] for every cell.  Per-cell

@@ -492,3 +492,29 @@ def test_warm_start_from_results_folder(bk, resultsdir):
     cs = 93.7
     assert relerr(r2['c'][-1], r1['c'][-1], cs) < 1e-8
     assert r2['n_steps'].max() < 0.5 * r1['n_steps'].min()
+
+
+def test_continuation_reaches_the_same_states_with_fewer_steps(bk, resultsdir):
+    """Calculator(continuation=k): every k-th cell of the sweep cold, the others from the converged state of their
+    nearest cold neighbour (batch analogue of the reference's 'internal-cont', transport.py:834-842).  All cells
+    must end on the steady states of the plain run (same discrete root, 1e-6) and the warm cells must need
+    fewer than half the steps."""
+    from catint_b200 import workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import Calculator
+    kw = workloads.c2(n_potentials=48)
+    tp = Transport(resultsdir=resultsdir, model_name='plain', **kw)
+    tp.set_calculator('odeint')
+    plain = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary')
+    r0 = plain.run()
+    tp2 = Transport(resultsdir=resultsdir, model_name='cont', **workloads.c2(n_potentials=48))
+    tp2.set_calculator('odeint')
+    cont = Calculator(transport=tp2, dt=0.5, tmax=200, ntout=1, mode='stationary', continuation=4)
+    r1 = cont.run()
+    assert plain.stats['converged'] == 48 and cont.stats['converged'] == 48
+    cs = 93.7
+    assert relerr(r1['c'][-1], r0['c'][-1], cs) < RTOL_PROFILE
+    assert np.max(np.abs(r1['flux'] - r0['flux'])) < RTOL_PROFILE * np.max(np.abs(r0['flux']))
+    st = cont.continuation_stats
+    assert st['cold_cells'] == 13 and st['warm_cells'] == 35
+    assert st['warm_steps_mean'] < 0.5 * st['cold_steps_mean']
