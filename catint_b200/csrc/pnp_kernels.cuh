@@ -33,6 +33,9 @@ constexpr int LMAX = QMAX + 1;     // Nordsieck vectors zn[0..QMAX]
 constexpr double ADDON = 1e-6, BIAS1 = 6.0, BIAS2 = 6.0, BIAS3 = 10.0;
 constexpr double ETAMX1 = 1e4, ETAMX2 = 10.0, ETAMXF = 0.2, ETAMIN = 0.1, ETACF = 0.25, THRESH = 1.5;
 constexpr int MXNCF = 10, MXNEF = 7, MXNEF1 = 3, SMALL_NEF = 2, LONG_WAIT = 10;
+#ifndef CATINT_HIST_SPECIALIZE
+#define CATINT_HIST_SPECIALIZE 1       // order-specialised instances of the history / correction passes
+#endif
 #ifndef CATINT_MSBP
 #define CATINT_MSBP 6
 #endif
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             set_bdf<NB, ST>(B);
             const double rl1 = 1.0 / B.l[1];
             { CATINT_TIC;
-              if (!pend_undo && pend_dq == 0) {
+              if (CATINT_HIST_SPECIALIZE && !pend_undo && pend_dq == 0) {
                   switch (q_old) {
                       case 1: history_pass<NB, ST, 1>(ws, 1, 0, false, pend_eta, lc, A1c, rl1, true); break;
                       case 2: history_pass<NB, ST, 2>(ws, 2, 0, false, pend_eta, lc, A1c, rl1, true); break;
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             }
             if constexpr (STREAM) cp_wait<0>();
         };
-        switch (q) {
+        switch (CATINT_HIST_SPECIALIZE ? q : 0) {
             case 1: correction(std::integral_constant<int, 1>()); break;
             case 2: correction(std::integral_constant<int, 2>()); break;
             case 3: correction(std::integral_constant<int, 3>()); break;
