@@ -106,8 +106,26 @@ def unpack_results(gathered, n_cells, world_size, n_out, nx_max, S):
     return full
 
 
+_PINNED = {}
+
+
+def _to_host_pinned(t, key):
+    """device tensor -> numpy through a cached pinned staging buffer (pageable copies of the gathered results
+    cost several times the kernel at 8 GPUs); CPU tensors pass through"""
+    import torch
+    if t.device.type != 'cuda':
+        return t.numpy()
+    buf = _PINNED.get(key)
+    if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    buf.copy_(t, non_blocking=True)
+    return buf
+
+
 def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
-    """ONE all_gather of the packed per-rank results, then one copy to the host."""
+    """ONE all_gather of the packed per-rank results; the round-robin order (cell j -> rank j % N) is undone and
+    the fields are split ON THE DEVICE (a transpose and slices), then one copy per field into pinned host memory."""
     import torch
     import torch.distributed as dist
     per = (n_cells + world_size - 1) // world_size
@@ -118,8 +136,24 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
     packed = pack_results(local, per, n_out, nx_max, S, device=dev)
     out = torch.empty((world_size * per, packed.shape[1]), dtype=torch.float64, device=packed.device)
     dist.all_gather_into_tensor(out, packed)
-    host = out.cpu().numpy()
-    full = unpack_results(host, n_cells, world_size, n_out, nx_max, S)
+    width = out.shape[1]
+    # row r*per + i holds cell i*N + r: [N, per, w] -> [per, N, w] -> cells in order
+    ordered = out.reshape(world_size, per, width).transpose(0, 1).reshape(world_size * per, width)[:n_cells]
+    full, staged = {}, {}
+    off = 0
+    for name, shp in result_shapes(n_out, nx_max, S).items():
+        w = int(np.prod(shp)) if shp else 1
+        a = ordered[:, off:off + w].reshape((n_cells,) + shp)
+        off += w
+        if name in _INT_FIELDS:
+            a = torch.round(a).to(torch.int32)
+        a = a.movedim(0, _CELL_AXIS[name]).contiguous()
+        staged[name] = _to_host_pinned(a, name)
+    if out.device.type == 'cuda':
+        torch.cuda.current_stream(out.device).synchronize()
+    for name, h in staged.items():
+        # the staging buffers are reused by the next call: hand out copies (a straight host memcpy)
+        full[name] = np.array(h.numpy(), copy=True) if torch.is_tensor(h) else h
     full['gather_bytes'] = int(out.numel() * 8)
     return full
 
