@@ -45,7 +45,10 @@ constexpr int MXNCF = 10, MXNEF = 7, MXNEF1 = 3, SMALL_NEF = 2, LONG_WAIT = 10;
 #ifndef CATINT_DGMAX
 #define CATINT_DGMAX 0.3
 #endif
-constexpr int MAXCOR = 3, MSBP = CATINT_MSBP;       // VODE default 20; measured on C2: 8 -> 18 % fewer steps; 6 is best once the 7x7 factorisation is cheap
+#ifndef CATINT_MAXCOR
+#define CATINT_MAXCOR 3
+#endif
+constexpr int MAXCOR = CATINT_MAXCOR, MSBP = CATINT_MSBP;       // VODE default 20; measured on C2: 8 -> 18 % fewer steps; 6 is best once the 7x7 factorisation is cheap
 constexpr double CRDOWN = 0.3, RDIV = 2.0, NLSCOEF = CATINT_NLSCOEF, DGMAX = CATINT_DGMAX;
 
 struct SolveParams {

@@ -2,7 +2,10 @@
 /root/reference needed at run time -- the model arrays come from catint_b200's Transport,
 whose parity with the reference Transport is pinned by ref_*.npz).
 
-    OMP_NUM_THREADS=1 python tests/golden/make_sweep_golden.py
+    OMP_NUM_THREADS=1 python tests/golden/make_sweep_golden.py            # 8 cells  -> oracle_c2_sweep.npz
+    OMP_NUM_THREADS=1 python tests/golden/make_sweep_golden.py dense      # 40 more  -> oracle_c2_sweep_dense.npz
+                                                                          # (every 32nd cell + the band where the
+                                                                          # Tafel current saturates, cells 560-650)
 """
 import multiprocessing as mp
 import os
@@ -18,6 +21,7 @@ sys.path.insert(0, REPO)
 os.environ.setdefault('CATINT_QUIET', '1')
 
 CELLS = [0, 146, 292, 438, 585, 731, 877, 1023]
+DENSE = sorted(set(list(range(16, 1024, 32)) + list(range(560, 650, 11))) - set(CELLS))
 
 
 def oracle_system(batch, c, rate_mode='summed'):
@@ -54,9 +58,11 @@ def main():
     from catint_b200 import workloads
     tp = Transport(resultsdir=tempfile.mkdtemp(), **workloads.c2())
     batch, _ = build_cell_batch(tp)
+    dense = len(sys.argv) > 1 and sys.argv[1] == 'dense'
+    CELLS = DENSE if dense else globals()['CELLS']
     jobs = [(dict(z=batch.z, reactions=batch.reactions, nu=batch.nu, par=batch.par[c], nx=batch.nx[c]), c) for c in CELLS]
     with mp.Pool(min(len(jobs), os.cpu_count())) as pool:
-        res = pool.map(work, jobs)
+        res = pool.map(work, jobs, chunksize=1)
     out = dict(cells=np.array(CELLS), par=batch.par[CELLS])
     for c, cend, cn, vn, gn, nfe, wall, conv in res:
         out['c_end_%d' % c] = cend
@@ -64,7 +70,7 @@ def main():
         out['newton_potential_%d' % c] = vn
         out['newton_grad_%d' % c] = gn
         print('cell %4d nfe %d wall %.1fs newton %s K+(0)=%.6g' % (c, nfe, wall, conv, cn[0]))
-    np.savez_compressed(os.path.join(HERE, 'oracle_c2_sweep.npz'), **out)
+    np.savez_compressed(os.path.join(HERE, 'oracle_c2_sweep_dense.npz' if dense else 'oracle_c2_sweep.npz'), **out)
 
 
 if __name__ == '__main__':

@@ -158,6 +158,35 @@ def test_potential_sweep_cells_match_odeint(bk, resultsdir):
         assert relerr(got, go['c_end_%d' % c].reshape(S, n).T, cs, floor=1e-9) < RTOL_PROFILE, c
 
 
+def test_forty_more_sweep_cells_land_on_the_odeint_root(bk, resultsdir):
+    """Root selection over the WHOLE sweep: 40 further cells of the 1024-point C2 sweep (every 32nd cell and, more
+    densely, the band where the Tafel current saturates and the step counts scatter) against scipy odeint's
+    end state and its Newton root (tests/golden/make_sweep_golden.py dense)."""
+    from catint_b200 import backend as be, workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import build_cell_batch
+    go = load_golden('oracle_c2_sweep_dense.npz')
+    tp = Transport(resultsdir=resultsdir, **workloads.c2())
+    batch, _ = build_cell_batch(tp)
+    cells = [int(c) for c in go['cells']]
+    assert len(cells) == 40 and np.array_equal(batch.par[cells], go['par'])
+    sub = batch.select(cells)
+    out = bk.solve(bk.upload(sub), [200.0], mode=be.MODE_STEADY)
+    assert out['status'].tolist() == [0] * len(cells)
+    S, n = sub.S, sub.nx_max
+    cs = np.max(np.abs(sub.par[0, :S]))
+    worst = 0.0
+    for k, c in enumerate(cells):
+        got = out['c'][-1, k].cpu().numpy()
+        e1 = relerr(got, go['newton_c_%d' % c].reshape(S, n).T, cs)
+        e2 = relerr(got, go['c_end_%d' % c].reshape(S, n).T, cs, floor=1e-9)
+        assert e1 < RTOL_PROFILE and e2 < RTOL_PROFILE, (c, e1, e2)
+        worst = max(worst, e1)
+        psc = max(np.max(np.abs(go['newton_potential_%d' % c])), 1e-300)
+        assert np.max(np.abs(out['phi'][-1, k].cpu().numpy() - go['newton_potential_%d' % c])) < RTOL_PROFILE * psc, c
+    print('worst relative deviation from the odeint roots over 40 cells: %.2e' % worst)
+
+
 def test_ragged_and_mixed_batch(bk):
     """cells with 101 and 102 nodes, different bulk compositions and temperatures in one launch;
     every cell must equal its own single-cell solve bit for bit, padding must stay untouched."""
