@@ -940,16 +940,18 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
     double rhs = ws.zb[zo];
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
-    int rs = 0, is = RING_CHAIN - 1, tp = 0;             // ring slot read / refilled in this iteration, tt parity offset
+    int rs = 1, is = RING_CHAIN - 1, tp = 0;             // ring slot of the NEXT record / slot refilled in this iteration, tt parity offset
+    // my row of inv and my coupling coefficients travel one iteration ahead in registers: they are loaded right
+    // after the barrier that makes their record visible, so no shared-memory latency sits at the head of the
+    // next iteration's dependency chain (the loads reuse the registers row_dot has just read)
+    double2 m[H];
+#pragma unroll
+    for (int c = 0; c < H; ++c) m[c] = rowp[c * NB];
+    double2 cf = cop[0];
 #pragma unroll 1
     for (int k = 0; k < iters; ++k) {
         feed.issue(is);                                  // refills the slot of record k-1
         is = (is + 1) & (RING_CHAIN - 1);
-        double2 m[H];
-#pragma unroll
-        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
-        const double2 cf = cop[rs * SLOT];
-        rs = (rs + 1) & (RING_CHAIN - 1);
         const double t = fma(cf.y, zs, fma(cf.x, zprev, rhs));
         double* tt = tbuf + tp;
         tp ^= NBP;
@@ -961,6 +963,10 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
         if (k + 1 < count) zo += zstep;
         rhs = ws.zb[zo];
         const double z = row_dot<NB, ST>(m, tt);
+#pragma unroll
+        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
+        cf = cop[rs * SLOT];
+        rs = (rs + 1) & (RING_CHAIN - 1);
         if (rowlane && live) ws.zb[zo_now] = z;
         zprev = z;
         zs = __shfl_sync(FULL, z, gsrc);
@@ -1013,18 +1019,19 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
     double zcur = ws.zb[zo];                             // forward-eliminated value of the current node
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
-    int rs = 0, is = RING_CHAIN - 1, tp = 0;
+    int rs = 1, is = RING_CHAIN - 1, tp = 0;
+    double2 m[H];                                        // one iteration ahead in registers, see forward_solve
+#pragma unroll
+    for (int c = 0; c < H; ++c) m[c] = rowp[c * NB];
+    double2 cf = cop[0];
+    double wn = 0.0, z0n = 0.0;
+    if (wl) { wn = wp[0]; z0n = wp[NBP]; }
 #pragma unroll 1
     for (int k = 0; k < iters; ++k) {
         feed.issue(is);
         is = (is + 1) & (RING_CHAIN - 1);
-        double2 m[H];
-#pragma unroll
-        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
-        const double2 cf = cop[rs * SLOT];
-        double w = 0.0, z0 = 0.0;
-        if (wl) { w = wp[rs * 2 * SLOT]; z0 = wp[rs * 2 * SLOT + NBP]; }
-        rs = (rs + 1) & (RING_CHAIN - 1);
+        double w = wn;
+        const double z0 = z0n;
         double* tt = tbuf + tp;
         tp ^= NBP;
         if (rowlane) tt[r] = -fma(cf.x, dprev, cf.y * dg);
@@ -1037,6 +1044,11 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
         const double znext = ws.zb[zo];
         const double yold = ws.y[zo_now];
         double d = zcur - row_dot<NB, ST>(m, tt);
+#pragma unroll
+        for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
+        cf = cop[rs * SLOT];
+        if (wl) { wn = wp[rs * 2 * SLOT]; z0n = wp[rs * 2 * SLOT + NBP]; }
+        rs = (rs + 1) & (RING_CHAIN - 1);
         // wall end of the wall-side chain (warp-uniform test): node 1 couples through the dense W_1,
         // node 0 has the extra block V_0 towards node 2
         const int i0 = mid - 1 - k;
