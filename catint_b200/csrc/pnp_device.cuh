@@ -144,28 +144,6 @@ __device__ __forceinline__ double net_rate(const DevTables& tb, int r, const dou
     return f - b;
 }
 
-// scalars of a cell (every lane keeps a copy in registers)
-__device__ __forceinline__ void load_cell_scalars(const DevTables& tb, const double* par, const int* nx,
-                                                  const int* mesh_id, const double* mesh_xi, long long cell,
-                                                  CellScalars& cs) {
-    const int S = tb.S_full;
-    const double* p = par + (size_t)cell * (3 * S + 8);
-    cs.n = nx[cell];
-    const int mid = mesh_id ? mesh_id[cell] : -1;
-    cs.uniform = mid < 0;
-    cs.xi = mid < 0 ? nullptr : mesh_xi + (size_t)mid * tb.nx_max;
-    cs.fpar = (tb.fq.n_eq > 0 && tb.fpar) ? tb.fpar + (size_t)cell * tb.fq.n_par : nullptr;
-    cs.beta = p[3 * S + 0];
-    cs.eps = p[3 * S + 1];
-    cs.phi_wall = p[3 * S + 2];
-    cs.g_bulk = p[3 * S + 3];
-    cs.cstern = p[3 * S + 4];
-    cs.dx = p[3 * S + 5];
-    cs.u_am = 1.0 / (cs.dx * cs.dx);
-    cs.u_ac = 1.0 / (2.0 * cs.dx);
-    cs.u_sg = cs.eps / (cs.dx * UNIT_F);
-}
-
 // cell set-up shared by all kernels
 __device__ __forceinline__ void load_cell(const DevTables& tb, const double* par, const int* nx,
                                           const int* mesh_id, const double* mesh_xi, long long cell,

@@ -2,24 +2,24 @@
 //
 // One warp owns one cell.  The Newton matrix  A = Mass/gamma - dF/dy  is block
 // tridiagonal (+ one wall block).  It is FACTORED by a twisted block elimination (from both
-// ends towards the coupling node n/2) with threshold pivoting inside the NB x NB blocks, and
-// the factors are kept in global memory (L2) so that the modified-Newton iterations of the
-// following steps only run the cheap SOLVE sweeps (VODE/CVODE re-use policy):
+// ends towards the coupling node n/2, one end per half warp) with threshold pivoting inside the
+// NB x NB blocks, and the factors are kept in global memory (L2) so that the modified-Newton
+// iterations of the following steps only run the cheap SOLVE sweeps (VODE/CVODE re-use policy):
 //
 //   factor_nodes   phase 1, all lanes: assembly of every node's record [A_D | l,a,ud,ua] (one
 //                  (node, unknown) pair per lane at a time);
-//                  phase 2, sequential: records stream back through the cp.async ring; lane j owns
-//                  one column of [A_D' | I | u_g] (2*NB+1 <= 32 columns, NB registers per lane);
-//                  a rolled Gauss-Jordan turns it into [I | inv_i | W_i[:,g]]; inv_i = A_D'^{-1}
-//                  goes to global memory, the W columns (inv_i*A_U top-down, inv_i*A_L bottom-up)
-//                  are handed to the A_D lanes of the next node by warp shuffles for the Schur
-//                  update A_D' = A_D - A_L*W (resp. A_U*W^b).
+//                  phase 2, sequential: records stream back through the cp.async ring; in each half
+//                  warp lane l < NB owns column l of A_D' and ends with column l of inv_i = A_D'^{-1}
+//                  (in-place rolled Gauss-Jordan), lane NB carries the g column of the coupling block
+//                  (-> W[:,g]); inv_i goes to global memory as [16-byte chunk][row], the W columns
+//                  (inv_i*A_U top-down, inv_i*A_L bottom-up) are handed to the next node in registers /
+//                  by shuffles for the Schur update A_D' = A_D - A_L*W (resp. A_U*W^b).
 //   residual_pass  lane per node: rhs = F(y) - Mass*(y+psi)/gamma  (K1 arithmetic on the
 //                  shared-memory state)
 //   forward_solve  two chains, one per half warp, lane = row:  z_i = inv_i*(rhs_i - A_L z_{i-1})
 //   backward_solve same mapping:  d_i = z_i - inv_i*(A_U d_{i+1});  y += d; weighted max norms
 //
-// No tensor cores: the blocks are 9..13 wide and the chain over nodes is sequential.
+// No tensor cores: the blocks are 7..13 wide and the chain over nodes is sequential.
 #pragma once
 #include <cuda_pipeline.h>
 #include "pnp_device.cuh"
@@ -98,10 +98,10 @@ __device__ __forceinline__ double pivot_rcp(double a) {
 // pivots.  The pivot column is broadcast from lane k of the half warp by shuffles.  In place: when
 // the row that originally was row p becomes the pivot row of step k, column k of the left part turns
 // into a unit vector and column p of the (implicit) identity on the right stops being one; the latter
-// is stored in the former's place, i.e. lane k finishes with column p_k of the inverse.  `orig` tracks
-// the original row of every slot (4 bits each, uniform per half warp); a final shuffle hands every
-// lane its own column (skipped when no half warp swapped rows, the common case: the algebraic rows are
-// pre-scaled so that the diagonal is an acceptable pivot).  Returns false on a zero/non-finite pivot.
+// is stored in the former's place, i.e. lane k finishes with column p_k of the inverse.  The pivot slots
+// are only RECORDED in the loop (4 bits per step); when some half warp did swap rows (rare: the algebraic
+// rows are pre-scaled so that the diagonal is an acceptable pivot) the bookkeeping is replayed afterwards
+// and a final shuffle hands every lane its own column.  Returns false on a zero/non-finite pivot.
 // 64-bit shuffle from two explicit 32-bit ones (the compiler's own expansion of __shfl_sync(double) came with
 // register-pair swaps: three XORs per value in the elimination loop)
 __device__ __forceinline__ double shfl_f64(double v, int src) {
@@ -1133,31 +1133,6 @@ __device__ void solve_middle(WarpState<NB, ST>& ws, int m) {
         ws.zb[(size_t)m * NB + r] = s;
     }
     __syncwarp();
-}
-
-// ---------------------------------------------------------------------------
-// Weighted max norms of the Newton update (scale*zb) and of the accumulated correction
-// (y - zn0) over the error-controlled unknowns (concentrations of nodes 0..n-2).
-// wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
-template <int NB, bool ST>
-__device__ void newton_norms(const WarpState<NB, ST>& ws, double scale, bool want_acn, double& dnorm, double& anorm,
-                             int wmode, double prtol, double patol) {
-    constexpr int S = NB - 1 - (ST ? 1 : 0);
-    const int n = ws.cs.n;
-    double dmax = 0.0, amax = 0.0;
-    for (int idx = ws.lane; idx < ws.N; idx += 32) {
-        const int i = idx / NB, r = idx - i * NB;
-        if (r < S && i < n - 1) {
-            const double yv = ws.y[idx];
-            const double w = (wmode == 0) ? ws.ewt[idx] : 1.0 / (prtol * fabs(yv) + patol);
-            double ad = fabs(ws.zb[idx] * scale) * w;
-            if (!(ad <= 1e300)) ad = INFINITY;          // NaN/Inf must not be lost in fmax
-            dmax = fmax(dmax, ad);
-            if (want_acn) amax = fmax(amax, fabs(yv - ws.zn[idx]) * w);
-        }
-    }
-    dnorm = warp_max(dmax);
-    anorm = warp_max(amax);
 }
 
 }  // namespace catint
