@@ -756,6 +756,12 @@ __device__ __noinline__ bool factor_nodes(const WarpState<NB, ST> ws_in, const S
 // ---------------------------------------------------------------------------
 // rhs = F(y) - Mass*(y+psi)*inv_gamma for every unknown; one lane per node (mass term fused).
 // The g-row of interior nodes carries the same scale as in factor_sweep.
+#ifndef CATINT_RES_UNROLL
+#define CATINT_RES_UNROLL 1
+#endif
+constexpr int RES_UNROLL = CATINT_RES_UNROLL;     // unroll factor of the reaction loop in residual_pass (measured: 2 neutral,
+                                                  // 5 slows EVERY phase by ~5 % -- instruction-cache footprint)
+
 template <int NB, bool ST>
 __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
@@ -794,6 +800,7 @@ __device__ void residual_pass(WarpState<NB, ST>& ws, double inv_gamma) {
             F[r] = fma(-(c0 + ps[r]), inv_gamma, F[r]);
             rho = fma(ws.sp->qe[r], c0, rho);
         }
+#pragma unroll RES_UNROLL
         for (int rr = 0; rr < tb.R; ++rr) {
             // educt/product indices of one reaction as two packed words (one LDS each, uniform)
             const unsigned ew = *reinterpret_cast<const unsigned*>(tb.ed[rr]);
