@@ -39,6 +39,9 @@ constexpr int RHS_NODES = 512;                 // node slots per block iteration
 constexpr int RHS_ROUNDS = RHS_NODES / RHS_THREADS;
 constexpr int RHS_NP = RHS_NODES + 3;          // odd pitch of the transposed state (slot = node + 1)
 constexpr int RHS_MAXG = 16;                   // cells per group (tiny grids use fewer slots)
+#ifndef CATINT_RHS_CONST_TABLES
+#define CATINT_RHS_CONST_TABLES 1              // reaction tables read from the kernel parameters instead of shared memory
+#endif
 #ifndef CATINT_RHS_MINB
 #define CATINT_RHS_MINB 3                      // resident blocks per SM the register allocation aims at
 #endif
@@ -177,12 +180,25 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                 if (!ce.xi) d2 = (cp - 2.0 * c0[s] + cm) * am;                           // :890 (reciprocal hoisted)
                 else d2 = am * cm - (am + ap) * c0[s] + ap * cp;
                 const double dcg = (cp * gp - cm * gm) * ac;                             // :892
-                res[s] = ce.D[s] * (d2 + ce.bF * tb->z[s] * dcg);
+                res[s] = ce.D[s] * (d2 + ce.bF * (CATINT_RHS_CONST_TABLES ? P.tb.z[s] : tb->z[s]) * dcg);
             }
             // mass-action rates (:159-208): factors by pre-compiled byte offsets into the transposed state
             const unsigned char* mine = reinterpret_cast<const unsigned char*>(cs_ + slot);
 #pragma unroll 1
             for (int rr = 0; rr < R; ++rr) {
+#if CATINT_RHS_CONST_TABLES
+                // rate constants, stoichiometry and factor offsets straight from the kernel parameters (constant
+                // bank, warp-uniform index): no shared-memory wavefronts for data every lane reads alike
+                double f = P.tb.kf[rr], b = P.tb.kr[rr];
+                const int ne = P.tb.ned[rr], np = P.tb.npr[rr];
+#pragma unroll 1
+                for (int e = 0; e < ne; ++e) f *= *reinterpret_cast<const double*>(mine + (int)P.tb.ed[rr][e] * (RHS_NP * 8));
+#pragma unroll 1
+                for (int e = 0; e < np; ++e) b *= *reinterpret_cast<const double*>(mine + (int)P.tb.pr[rr][e] * (RHS_NP * 8));
+                const double net = f - b;
+#pragma unroll
+                for (int s = 0; s < S; ++s) res[s] = fma(P.tb.nu[rr][s], net, res[s]);        // :920-927
+#else
                 double f = tb->kf[rr], b = tb->kr[rr];
                 const int ne = prog->ne[rr], np = prog->np[rr];
                 const int* po = prog->off[rr];
@@ -198,6 +214,7 @@ __global__ void __launch_bounds__(RHS_THREADS, CATINT_RHS_MINB) pnp_rhs_kernel(R
                     res[s] = fma(nn.x, net, res[s]);
                     if (s + 1 < S) res[s + 1] = fma(nn.y, net, res[s + 1]);
                 }
+#endif
             }
         }
         if ((S % 2 == 0) && ((((size_t)o) & 15) == 0)) {
