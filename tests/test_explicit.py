@@ -214,3 +214,40 @@ def test_calculator_runs_the_fixed_step_calcs(bk, resultsdir):
     got = res['c'][-1, 2, :n].T
     assert np.max(np.abs(got - ref[-1][0])) <= 1e-6 * np.max(np.abs(ref[-1][0]))
     assert len(tp.cout) == len([i for i in tp.itout if i < tp.nt])
+
+
+@pytest.mark.gpu
+def test_entry_points_reject_what_they_do_not_handle(bk):
+    """error codes, not exits or silent fallbacks: the implicit kernels take the default pb_bound pair (and Stern),
+    the fixed-step steppers every pair but Stern and uniform meshes only, bad control values are EINVAL"""
+    import torch
+    from catint_b200 import backend as be
+    su = load_golden('ref_c1.npz')
+    S, n = len(su['z']), int(su['nx'])
+    c = to_dev(np.broadcast_to(su['c_bulk'][None, None, :], (1, n, S)))
+    batch = batch_with_pair(su, be.BC_DIRICHLET_BOTH)
+    db = bk.upload(batch)
+    with pytest.raises(RuntimeError, match='default Poisson boundary'):
+        bk.rhs(db, c)
+    with pytest.raises(RuntimeError, match='Poisson boundary must be the default pair or Stern'):
+        bk.solve(db, [1.0])
+    v, g, lp = bk.potential(db, c)                       # ... but the Poisson routine and the steppers take it
+    assert torch.isfinite(v).all()
+    out = bk.step(db, be.STEPPER_FTCS, 1e-11, 3, [2])
+    assert out['c'].shape == (1, 1, n, S) and torch.isfinite(out['c']).all()
+    with pytest.raises(RuntimeError, match='dt > 0'):
+        bk.step(db, be.STEPPER_FTCS, 0.0, 3, [2])
+    with pytest.raises(RuntimeError, match='unknown stepper'):
+        bk.step(db, 7, 1e-11, 3, [2])
+    stern = batch_with_pair(su, be.BC_DIRICHLET_BOTH)
+    stern.poisson_bc = be.BC_STERN_ROBIN
+    with pytest.raises(RuntimeError, match='not Stern'):
+        bk.step(bk.upload(stern), be.STEPPER_FTCS, 1e-11, 3, [2])
+    graded = batch_with_pair(su, 0)
+    graded.mesh_id = np.zeros(1, dtype=np.int32)
+    graded.mesh_xi = np.linspace(0.0, 1.0, n)[None, :]
+    with pytest.raises(RuntimeError, match='uniform mesh'):
+        bk.step(bk.upload(graded), be.STEPPER_CRANK_NICOLSON, 1e-11, 3, [2])
+    # outputs only at the listed steps; Crank-Nicolson counts its steps from 1 like the reference
+    out = bk.step(bk.upload(batch_with_pair(su, 0)), be.STEPPER_CRANK_NICOLSON, 1e-11, 4, [1, 3])
+    assert out['c'].shape[0] == 2 and not torch.equal(out['c'][0], out['c'][1])
