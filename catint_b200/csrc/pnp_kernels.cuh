@@ -374,7 +374,7 @@ __device__ void history_pass(WarpState<NB, ST>& ws, int q_old_rt, int dq_rt, boo
 // One linear solve with the stored factors + update of the iterate:  zb holds the rhs on entry and the
 // (unscaled) update on exit, y += scale*update; returns the weighted max norms of the scaled update
 // and of the accumulated correction (identical on both warps of a pair).
-template <int NB, bool ST>
+template <int NB, bool ST, bool GS>
 __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid,
                              double& del, double& acn, int wmode, double prtol, double patol,
                              long long* pc, bool prof_on) {
@@ -382,12 +382,12 @@ __device__ void newton_solve(WarpState<NB, ST>& ws, double scale, int mid,
     double dmax = 0.0, amax = 0.0;
     // twisted factors: both chains advance in the two halves of the warp
     long long t0 = prof_on ? clock64() : 0;
-    forward_solve<NB, ST>(ws, mid);
+    forward_solve<NB, ST, GS>(ws, mid);
     solve_middle<NB, ST>(ws, mid);
     if (prof_on) pc[2] += clock64() - t0;
     t0 = prof_on ? clock64() : 0;
     apply_node<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
-    backward_solve<NB, ST>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
+    backward_solve<NB, ST, GS>(ws, scale, mid, dmax, amax, wmode, prtol, patol);
     del = warp_max(dmax);
     acn = warp_max(amax);
     if (prof_on) pc[3] += clock64() - t0;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
                 for (int m = 0; m < MAXCOR; ++m) {
                     { CATINT_TIC; residual_pass<NB, ST>(ws, inv_gamma); CATINT_TOC(1); }
                     double del = 0.0, acn = 0.0;
-                    newton_solve<NB, ST>(ws, dscale, mid, del, acn, 0, 0.0, 0.0, pc, prof_on);
+                    newton_solve<NB, ST, !SMEM>(ws, dscale, mid, del, acn, 0, 0.0, 0.0, pc, prof_on);
                     ++nni;
                     if (!(del <= 1e300)) { bad = true; break; }
                     if (m > 0) crate = fmax(CRDOWN * crate, del / delp);
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             if (!ok) break;
             residual_pass<NB, ST>(ws, 0.0);
             double del = 0.0, acn = 0.0;
-            newton_solve<NB, ST>(ws, 1.0, mid, del, acn, 1, P.polish_rtol, patol, pc, false);
+            newton_solve<NB, ST, !SMEM>(ws, 1.0, mid, del, acn, 1, P.polish_rtol, patol, pc, false);
             ++nni;
             if (!(del <= 1e300)) break;
             // converged, or stagnating at the rounding floor of the linear solve with an update that is

@@ -847,16 +847,18 @@ struct SweepRing {
     static constexpr int REC = fac_rec<NB, ST>();
     static constexpr int CH = REC / 2;                    // 16-byte chunks per record
     static constexpr int R16 = (CH + 15) / 16;            // copy rounds of a half warp per record
-    static constexpr int SLOT = R16 * 32 + 2 * NBP;       // doubles per slot: record (padded) | weights | zn0
+    static constexpr int SLOT = R16 * 32 + 4 * NBP;       // doubles per slot: record (padded) | weights | zn0 | zb | y
     const double* src;                                    // my first chunk of the next record to copy
-    const double* wsrc; const double* zsrc;               // backward sweep: error weight and zn0 of my unknown
+    // per-lane side streams of my unknown: error weight and zn0 (backward sweep), and -- when the iterate and the
+    // rhs/update vector live in global memory (large grids) -- zb and y, so that no global load sits in the chain
+    const double* wsrc; const double* zsrc; const double* bsrc; const double* ysrc;
     unsigned dst, wdst;                                   // shared address of my first chunk / my weight in slot (0, grp)
     int rstride, zstep, left;                             // doubles between records / unknowns; records left to copy
     unsigned lastp;                                       // copy predicate of the last round
     unsigned long long pol;
-    bool wl;
+    bool wl, bl, yl;
     __device__ __forceinline__ void init(const WarpState<NB, ST>& ws, int first, int dir, int count, bool weights, int r,
-                                         bool rowlane) {
+                                         bool rowlane, bool stage_zb = false, bool stage_y = false) {
         const int l = ws.lane & 15, grp = ws.lane >> 4;
         src = ws.fac + (size_t)first * REC + 2 * l;
         rstride = dir * REC;
@@ -866,9 +868,13 @@ struct SweepRing {
         wdst = (unsigned)__cvta_generic_to_shared(ws.ring) + (unsigned)((grp * SLOT + R16 * 32 + l) * 8);
         lastp = (l + 16 * (R16 - 1) < CH) ? 1u : 0u;
         wl = weights && rowlane;
+        bl = stage_zb && rowlane;
+        yl = stage_y && rowlane;
         pol = ws.keep;
         wsrc = ws.ewt + (size_t)first * NB + r;
         zsrc = ws.zn + (size_t)first * NB + r;
+        bsrc = ws.zb + (size_t)first * NB + r;
+        ysrc = ws.y + (size_t)first * NB + r;
     }
     // copy the next record of my chain into ring slot `slot` (0..RING_CHAIN-1); past the end of the chain
     // the last record is copied again (never consumed by a live iteration)
@@ -879,14 +885,16 @@ struct SweepRing {
             if (q + 1 < R16) cp_async16_hint(d + 256u * q, src + 32 * q, pol);
             else cp_async16_if(d + 256u * q, src + 32 * q, lastp, pol);
         }
+        const unsigned dw = wdst + (unsigned)(slot * 2 * SLOT * 8);
         if (wl) {
-            const unsigned dw = wdst + (unsigned)(slot * 2 * SLOT * 8);
             cp_async8(dw, wsrc);
             cp_async8(dw + 8u * NBP, zsrc);
         }
+        if (bl) cp_async8(dw + 16u * NBP, bsrc);
+        if (yl) cp_async8(dw + 24u * NBP, ysrc);
         cp_commit();
         --left;
-        if (left > 0) { src += rstride; wsrc += zstep; zsrc += zstep; }
+        if (left > 0) { src += rstride; wsrc += zstep; zsrc += zstep; bsrc += zstep; ysrc += zstep; }
     }
 };
 
@@ -915,7 +923,7 @@ __device__ __forceinline__ double row_dot(const double2 (&m)[padded<NB, ST>() / 
 //   bulk side,  nodes n-1..mid+1 downwards:  z_i = inv_i*(rhs_i - A_U z_{i+1})
 // (the first node of a chain has no predecessor).  Lanes without a row and the shorter chain in its
 // missing last iteration run the same arithmetic on valid dummy operands and only skip the stores.
-template <int NB, bool ST>
+template <int NB, bool ST, bool GS>
 __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
     constexpr int NBP = padded<NB, ST>();
@@ -932,21 +940,22 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
     const int dir = grp ? -1 : 1;
     const int first = grp ? n - 1 : 0;
     SweepRing<NB, ST> feed;
-    feed.init(ws, first, dir, count, false, r, rowlane);
+    feed.init(ws, first, dir, count, false, r, rowlane, GS);
 #pragma unroll
     for (int p = 0; p < RING_CHAIN - 1; ++p) feed.issue(p);
     // my row of the record in slot (0, grp): chunk c at [c][r]; coupling coefficients (diagonal, g column)
     // A_L = -(diag l + a e_g^T) on the wall side, A_U = -(diag ud + ua e_g^T) on the bulk side
     const double2* rowp = reinterpret_cast<const double2*>(ws.ring + grp * SLOT) + r;
     const double2* cop = reinterpret_cast<const double2*>(ws.ring + grp * SLOT + NB * NBP + 4 * r + (grp ? 2 : 0));
+    const double* bp = ws.ring + grp * SLOT + SweepRing<NB, ST>::R16 * 32 + 2 * NBP + r;     // staged zb (GS)
     double* tbuf = ws.scratch + grp * 2 * NBP;           // [parity][NBP] per chain
     const int zstep = dir * NB;
     const int gsrc = (lane & 16) + S;                    // lane that owns the g component of my chain
     int zo = first * NB + r;                             // this lane's unknown of the current node
     double zprev = 0.0, zs = 0.0;                        // my row / the g row of the previous node (none at k = 0)
-    double rhs = ws.zb[zo];
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
+    double rhs = GS ? bp[0] : ws.zb[zo];
     int rs = 1, is = RING_CHAIN - 1, tp = 0;             // ring slot of the NEXT record / slot refilled in this iteration, tt parity offset
     // my row of inv and my coupling coefficients travel one iteration ahead in registers: they are loaded right
     // after the barrier that makes their record visible, so no shared-memory latency sits at the head of the
@@ -968,7 +977,7 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
         const bool live = k < count;
         const int zo_now = zo;
         if (k + 1 < count) zo += zstep;
-        rhs = ws.zb[zo];
+        rhs = GS ? bp[rs * 2 * SLOT] : ws.zb[zo];        // GS: my copy of zb of node k+1 landed with its record
         const double z = row_dot<NB, ST>(m, tt);
 #pragma unroll
         for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];
@@ -990,7 +999,7 @@ __device__ void forward_solve(WarpState<NB, ST>& ws, int mid) {
 // (concentrations of nodes 0..n-2), accumulated into dmax/amax (per lane, reduce afterwards):
 // the weight and zn0 of each unknown ride in the ring slot of their node (a lane reads back only what it
 // copied itself).  wmode 0: weights ws.ewt; wmode 1 (steady polish): w = 1/(prtol*|y|+patol).
-template <int NB, bool ST>
+template <int NB, bool ST, bool GS>
 __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
                                double& dmax, double& amax, int wmode, double prtol, double patol) {
     constexpr int S = NB - 1 - (ST ? 1 : 0);
@@ -1009,12 +1018,12 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
     const int first = grp ? mid + 1 : mid - 1;
     const bool wl = wmode == 0;
     SweepRing<NB, ST> feed;
-    feed.init(ws, first, dir, count, wl, r, rowlane);
+    feed.init(ws, first, dir, count, wl, r, rowlane, GS, GS);
 #pragma unroll
     for (int p = 0; p < RING_CHAIN - 1; ++p) feed.issue(p);
     const double2* rowp = reinterpret_cast<const double2*>(ws.ring + grp * SLOT) + r;
     const double2* cop = reinterpret_cast<const double2*>(ws.ring + grp * SLOT + NB * NBP + 4 * r + (grp ? 0 : 2));
-    const double* wp = ws.ring + grp * SLOT + WOFF + r;
+    const double* wp = ws.ring + grp * SLOT + WOFF + r;  // staged: +0 weight, +NBP zn0, +2 NBP zb, +3 NBP y
     double* tbuf = ws.scratch + grp * 2 * NBP;
     const int zstep = dir * NB;
     const int gsrc = (lane & 16) + S;
@@ -1023,9 +1032,10 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
     // final solution of the node before the chain (the coupling node): my row and its g row
     double dprev = ws.zb[zo - zstep];
     double dg = ws.zb[zo - zstep + (S - r)];
-    double zcur = ws.zb[zo];                             // forward-eliminated value of the current node
     cp_wait<RING_CHAIN - 2>();
     __syncwarp();                                        // record 0 is visible to every lane
+    double zcur = GS ? wp[2 * NBP] : ws.zb[zo];          // forward-eliminated value of the current node
+    double ynext = GS ? wp[3 * NBP] : 0.0;               // GS: iterate of the current node, staged with its record
     int rs = 1, is = RING_CHAIN - 1, tp = 0;
     double2 m[H];                                        // one iteration ahead in registers, see forward_solve
 #pragma unroll
@@ -1048,8 +1058,9 @@ __device__ void backward_solve(WarpState<NB, ST>& ws, double scale, int mid,
         const int i = first + dir * k;
         const int zo_now = zo;
         if (k + 1 < count) zo += zstep;
-        const double znext = ws.zb[zo];
-        const double yold = ws.y[zo_now];
+        const double znext = GS ? wp[rs * 2 * SLOT + 2 * NBP] : ws.zb[zo];
+        const double yold = GS ? ynext : ws.y[zo_now];
+        if (GS) ynext = wp[rs * 2 * SLOT + 3 * NBP];
         double d = zcur - row_dot<NB, ST>(m, tt);
 #pragma unroll
         for (int c = 0; c < H; ++c) m[c] = rowp[rs * SLOT + c * NB];

@@ -49,6 +49,10 @@ def main():
     db = bk.upload(batch)
     out = bk.alloc_outputs(db, len(t_out))
     ws, need = bk.workspace(db)
+    prof = None
+    if os.environ.get('CATINT_PHASES'):
+        prof = torch.zeros((batch.B, 8), dtype=torch.int64, device='cuda:0')
+        bk.lib.catint_pnp_debug_profile_buffer(prof.data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -73,6 +77,14 @@ def main():
             'fp64_TFs_8d': float((ns.sum() * n * (14.0 / 3.0 * b ** 3) + nn.sum() * n * 4.0 * b * b) / sec / 1e12),
             'fp64_TFs_8d_dense_per_newton': float(nn.sum() * flops_newton / sec / 1e12)}
     print(json.dumps(line), flush=True)
+    if prof is not None:
+        pr = prof.double().mean(dim=0).cpu().numpy()
+        names = ['factor', 'residual', 'forward', 'backward', 'assembly(in factor)', 'history', 'correction', 'total']
+        print('mean cycles per cell:', {k: '%.3g (%.1f%%)' % (v, 100 * v / pr[7]) for k, v in zip(names, pr)})
+        print('per call: factor %.0f (assembly %.0f), residual %.0f, forward %.0f, backward %.0f (per newton), history %.0f, '
+              'correction %.0f (per step); per node and sweep: fwd %.0f bwd %.0f cycles' % (
+                  pr[0] / ns.mean(), pr[4] / ns.mean(), pr[1] / nn.mean(), pr[2] / nn.mean(), pr[3] / nn.mean(),
+                  pr[5] / st.mean(), pr[6] / st.mean(), pr[2] / nn.mean() / (n / 2), pr[3] / nn.mean() / (n / 2)))
     if cfg.startswith('c5') or cfg == 'c3':
         bad = np.nonzero(status != 0)[0][:20]
         print('first failing cells', bad.tolist(), [int(s) for s in status[bad]])
