@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
             for (int j = 0; j < LMAX; ++j) lreg[j] = B.l[j];
             double* __restrict__ zn = ws.zn;
             double* __restrict__ ewt = ws.ewt;
-            constexpr int NARR = LMAX + 1;                           // zn[0..QMAX] and the weights
+            constexpr int NARR = LMAX + 1 + (SMEM ? 0 : 1);          // zn[0..QMAX], the weights (+ y when it lives in global memory)
             constexpr int SD = stream_depth<NB, ST, NARR>();
             constexpr bool STREAM = SD >= 3;
             const int nch = (N + vstride - 1) / vstride;
@@ -706,6 +706,7 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
                             else cp_async8_hint(d + 256u * j, zn + (size_t)j * N + ii, ws.stream);
                         }
                     cp_async8(d + 256u * LMAX, ewt + ii);
+                    if (!SMEM) cp_async8(d + 256u * (LMAX + 1), ws.y + ii);
                 }
                 cp_commit();
                 ++ichunk;
@@ -732,7 +733,9 @@ __global__ void __launch_bounds__(32 * BDF_WARPS, 8 / BDF_WARPS) pnp_bdf_kernel(
                             zj[j] = (j <= q || (j == QMAX && want_up)) ? zn[(size_t)j * N + ii] : 0.0;
                         w = ewt[ii];
                     }
-                    const double yv = ws.y[ii];
+                    double yv;
+                    if constexpr (SMEM || !STREAM) yv = ws.y[ii];
+                    else yv = sring[rslot * NARR * 32 + (LMAX + 1) * 32];
                     const int i = ii / NB, r = ii - i * NB;
                     const bool mass = r < S && i < n - 1;
                     const double ac = yv - zj[0];
