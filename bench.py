@@ -377,7 +377,9 @@ def run_gpu(args):
         return r
 
     def e2e_step():
-        return D.solve_sharded(calc, gbatch, solve_fn=solve_fn, device=dev)
+        # the gathered results go to the host of rank 0 (the rank that saves, Transport.save); every rank takes
+        # part in the device-side gather
+        return D.solve_sharded(calc, gbatch, solve_fn=solve_fn, device=dev, root_only=True)
 
     e2e_steps = max(1, min(args.steps, 3))
     res = e2e_step()                                                   # warm
@@ -386,10 +388,12 @@ def run_gpu(args):
     e2e_conv = 0
     for _ in range(e2e_steps):
         res = e2e_step()
-        e2e_conv += int(np.sum(res['status'] == 0))                    # whole job (gathered on every rank)
+        if res is not None:
+            e2e_conv += int(np.sum(res['status'] == 0))                # whole job (gathered on rank 0)
     sync_all()
     e2e_s = time.perf_counter() - t0
-    d2h_local = int(res.get('gather_bytes', 0)) or sum(int(v.nbytes) for k, v in res.items() if hasattr(v, 'nbytes'))
+    d2h_local = 0 if res is None else (int(res.get('gather_bytes', 0)) or
+                                       sum(int(v.nbytes) for k, v in res.items() if hasattr(v, 'nbytes')))
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -461,7 +465,8 @@ def run_gpu(args):
                     'd2h_bytes_per_step': int(d2h_all), 'steps': e2e_steps,
                     'path': 'Calculator.solve_batch_device + distributed.solve_sharded: H2D (pinned) -> solve -> '
                             + ('one packed NCCL all_gather_into_tensor on the devices -> ' if world > 1 else '')
-                            + 'D2H of all results; wall clock, barrier on both sides, max over ranks'},
+                            + 'D2H of all results' + (' on rank 0' if world > 1 else '')
+                            + '; wall clock, barrier on both sides, max over ranks'},
             'gpu_launches': launches * args.gpus,
             'converged_cells_per_step': n_conv_all,
             'roofline': roofline,

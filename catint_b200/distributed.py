@@ -123,9 +123,12 @@ def _to_host_pinned(t, key):
     return buf
 
 
-def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
+def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, root_only=False):
     """ONE all_gather of the packed per-rank results; the round-robin order (cell j -> rank j % N) is undone and
-    the fields are split ON THE DEVICE (a transpose and slices), then one copy per field into pinned host memory."""
+    the fields are split ON THE DEVICE (a transpose and slices), then one copy per field into pinned host memory.
+    root_only: only rank 0 copies the gathered results to its host (the others return None) -- what a driver
+    that saves on rank 0 needs; the default hands every rank the complete result like the reference's
+    reduce_dict_mpi + sync_mpi (catint_io.py:154-178)."""
     import torch
     import torch.distributed as dist
     per = (n_cells + world_size - 1) // world_size
@@ -136,6 +139,8 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
     packed = pack_results(local, per, n_out, nx_max, S, device=dev)
     out = torch.empty((world_size * per, packed.shape[1]), dtype=torch.float64, device=packed.device)
     dist.all_gather_into_tensor(out, packed)
+    if root_only and dist.get_rank() != 0:
+        return None
     width = out.shape[1]
     # row r*per + i holds cell i*N + r: [N, per, w] -> [per, N, w] -> cells in order
     ordered = out.reshape(world_size, per, width).transpose(0, 1).reshape(world_size * per, width)[:n_cells]
@@ -158,7 +163,7 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None):
     return full
 
 
-def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None):
+def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None, root_only=False):
     """Solve ``batch`` with the cells split over all ranks; every rank returns
     the complete, ordered result dict (numpy).  ``solve_fn(sub_batch) -> dict`` of
     torch tensors (device) or numpy arrays defaults to the CUDA path
@@ -185,8 +190,9 @@ def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None):
     else:
         local = solve_fn(batch.select(idx))
         extra = {k: v for k, v in local.items() if k not in _CELL_AXIS}
-    full = gather_results(local, batch.B, ws, n_out, batch.nx_max, batch.S, device=device)
-    full.update(extra)
+    full = gather_results(local, batch.B, ws, n_out, batch.nx_max, batch.S, device=device, root_only=root_only)
+    if full is not None:
+        full.update(extra)
     return full
 
 

@@ -35,7 +35,7 @@ def make_batch(B=7):
     return batch
 
 
-def _worker(rank, world, port, q, n_cells=7):
+def _worker(rank, world, port, q, n_cells=7, root_only=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -46,18 +46,21 @@ def _worker(rank, world, port, q, n_cells=7):
         def solve(sub):
             calls.append(sub.B)
             return fake_solve(sub)
-        full = D.solve_sharded(None, batch, solve_fn=solve, n_out=2)
-        full['solve_calls'] = np.array(calls)
-        q.put((rank, {k: v for k, v in full.items()}))
+        full = D.solve_sharded(None, batch, solve_fn=solve, n_out=2, root_only=root_only)
+        if full is None:
+            q.put((rank, None))
+        else:
+            full['solve_calls'] = np.array(calls)
+            q.put((rank, {k: v for k, v in full.items()}))
     finally:
         dist.destroy_process_group()
 
 
-def _run_ranks(world, n_cells):
+def _run_ranks(world, n_cells, root_only=False):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_cells)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_cells, root_only)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=120) for _ in range(world))
@@ -139,3 +142,12 @@ def test_results_folder_is_created_once_and_saved_by_rank_zero(tmp_path):
     files = got[1][3]
     assert 'transport_id000.log' in files and 'transport_id001.log' in files
     assert sum(1 for f in files if f.startswith('alldata')) == 1
+
+
+def test_root_only_gather_hands_the_results_to_rank_zero():
+    """root_only=True: every rank joins the gather, only rank 0 copies the complete result to its host"""
+    got = _run_ranks(2, 7, root_only=True)
+    want = fake_solve(make_batch())
+    assert got[1] is None
+    for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'):
+        assert np.array_equal(got[0][k], want[k]), k
