@@ -294,9 +294,10 @@ class Calculator():
         db = backend.upload(batch, pinned=pinned)
         if self.calc in FD_STEP_CALCS:
             return self._step_batch_device(backend, db, y0)
-        if batch.poisson_bc not in (_be.BC_DIRICHLET_WALL_NEUMANN_BULK, _be.BC_STERN_ROBIN):
-            self.tp.logger.error('| CI | -- | the implicit integrator takes the default pb_bound pair (wall potential + '
-                                 'bulk gradient) or the Stern boundary; the other pairs run with calc=FTCS / '
+        if batch.poisson_bc not in (_be.BC_DIRICHLET_WALL_NEUMANN_BULK, _be.BC_STERN_ROBIN,
+                                    _be.BC_DIRICHLET_BULK_NEUMANN_BULK):
+            self.tp.logger.error('| CI | -- | the implicit integrator takes the pb_bound pairs with a bulk gradient (wall '
+                                 'or bulk potential) or the Stern boundary; the other pairs run with calc=FTCS / '
                                  'Crank-Nicolson')
             sys.exit()
         mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT

@@ -323,9 +323,16 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
     int rc = check_common(sh, cells, n_cells);
     if (rc) return rc;
     if (sh->nx_max < CATINT_PNP_MIN_NODES) return fail(CATINT_PNP_EINVAL, "nx_max must be >= CATINT_PNP_MIN_NODES");
-    if (sh->poisson_bc != CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK && sh->poisson_bc != CATINT_PNP_BC_STERN_ROBIN)
-        return fail(CATINT_PNP_EINVAL, "catint_pnp_solve_batch: Poisson boundary must be the default pair or Stern "
-                                       "(the other pb_bound pairs run in catint_pnp_step_batch)");
+    // the bulk/bulk pair has the field of the default pair (backward sum from the bulk gradient); only its potential
+    // is integrated from the bulk end: same kernel, potential rewritten from g_out afterwards
+    const bool bulk_pair = sh->poisson_bc == CATINT_PNP_BC_DIRICHLET_BULK_NEUMANN_BULK;
+    if (sh->poisson_bc != CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK && sh->poisson_bc != CATINT_PNP_BC_STERN_ROBIN && !bulk_pair)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_solve_batch: Poisson boundary must be the default pair, the bulk/bulk "
+                                       "pair or Stern (the other pb_bound pairs run in catint_pnp_step_batch)");
+    if (bulk_pair && phi_out && !g_out)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_solve_batch: the bulk/bulk pair derives phi_out from g_out; pass both");
+    if (bulk_pair && sh->flux_eq && sh->flux_eq->n_eq > 0)
+        return fail(CATINT_PNP_EINVAL, "catint_pnp_solve_batch: flux equations read the wall potential; not with the bulk/bulk pair");
     if (!ctl || !ctl->t_out || ctl->n_out < 1) return fail(CATINT_PNP_EINVAL, "control / t_out missing");
     if (!c_out || !status || !n_steps || !n_newton) return fail(CATINT_PNP_EINVAL, "output pointers are NULL");
     if (!(ctl->rtol >= 0.0) || !(ctl->atol > 0.0)) return fail(CATINT_PNP_EINVAL, "need rtol >= 0 and atol > 0");
@@ -372,6 +379,13 @@ extern "C" int catint_pnp_solve_batch(const CatintPnpShared* sh, const CatintPnp
         DISPATCH_NB(nb, launch_bdf, false, P, st);
     }
     if (rc == CATINT_PNP_ECUDA) return fail(rc, "pnp_bdf_kernel launch failed");
+    if (rc == CATINT_PNP_OK && bulk_pair && phi_out) {
+        BulkPotentialParams Q;
+        Q.par = cells->par; Q.nx = cells->nx; Q.mesh_id = cells->mesh_id; Q.mesh_xi = cells->mesh_xi;
+        Q.g = g_out; Q.v = phi_out; Q.n_cells = n_cells; Q.rows = (long long)ctl->n_out * n_cells;
+        Q.S = sh->S; Q.nx_max = sh->nx_max;
+        if (launch_bulk_potential(Q, st) != 0) return fail(CATINT_PNP_ECUDA, "pnp_bulk_potential_kernel launch failed");
+    }
     return rc;
 }
 

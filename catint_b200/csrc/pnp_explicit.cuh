@@ -369,6 +369,54 @@ inline int launch_explicit(ExplicitParams& P, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
 }
 
+// Potential of the pair "potential and gradient in the bulk" (calculator_old.py:795-797) from a gradient the implicit
+// integrator has written: the dynamics of that pair are those of the default pair (the field is the backward sum from
+// the bulk gradient either way, :787-790), only the potential is integrated from the other end:
+//   v[n-1] = phi_bulk,  v[i] = v[i+1] - g[i]*(x_{i+1}-x_i)  (i = n-2..1),  v[0] = v[1] + (v[1]-v[2])*h_0/h_1.
+// One warp per (output time, cell) row of g_out / phi_out.
+struct BulkPotentialParams {
+    const double* par; const int* nx; const int* mesh_id; const double* mesh_xi;
+    const double* g; double* v;          // [rows][nx_max], rows = n_out * n_cells, cell = row % n_cells
+    long long n_cells, rows;
+    int S, nx_max;
+};
+
+__global__ void __launch_bounds__(128) pnp_bulk_potential_kernel(BulkPotentialParams P) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 4 + warp;
+    if (row >= P.rows) return;
+    const long long cell = row % P.n_cells;
+    const double* p = P.par + (size_t)cell * (3 * P.S + 8);
+    const int n = P.nx[cell];
+    if (n < 4 || n > P.nx_max) return;
+    const double dx = p[3 * P.S + 5], phi_bulk = p[3 * P.S + 6];
+    const int mid = P.mesh_id ? P.mesh_id[cell] : -1;
+    const double* xi = mid < 0 ? nullptr : P.mesh_xi + (size_t)mid * P.nx_max;
+    const double* g = P.g + (size_t)row * P.nx_max;
+    double* v = P.v + (size_t)row * P.nx_max;
+    double carry = phi_bulk;
+    for (int top = n - 2; top >= 1; top -= 32) {
+        const int i = top - lane;
+        double t = 0.0;
+        if (i >= 1) t = g[i] * (xi ? dx * (xi[i + 1] - xi[i]) : dx);
+        const double s = wscan(t, lane);
+        if (i >= 1) v[i] = carry - s;
+        carry -= __shfl_sync(FULL, s, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        v[n - 1] = phi_bulk;
+        const double ratio = xi ? (xi[1] - xi[0]) / (xi[2] - xi[1]) : 1.0;
+        v[0] = v[1] + (v[1] - v[2]) * ratio;
+    }
+}
+
+inline int launch_bulk_potential(BulkPotentialParams& P, cudaStream_t st) {
+    const unsigned grid = (unsigned)((P.rows + 3) / 4);
+    pnp_bulk_potential_kernel<<<grid, 128, 0, st>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : CATINT_PNP_ECUDA;
+}
+
 inline int launch_potential(PotentialParams& P, cudaStream_t st) {
     int dev = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return CATINT_PNP_ECUDA;

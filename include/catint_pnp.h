@@ -66,7 +66,9 @@ enum {
 /* Poisson boundary conditions = the reference's pb_bound combinations (catint/calculator_old.py:776-803; exactly one
    gradient and one potential, or both potentials).  0 is the reference default (catint/transport.py:1278-1322) and,
    with 1 (Stern/Robin wall, phi carried as an unknown; extension), what K1-K3 handle; 2-5 are available in
-   catint_pnp_potential_batch and in the fixed-step steppers of catint_pnp_step_batch.                          */
+   catint_pnp_potential_batch and in the fixed-step steppers of catint_pnp_step_batch.  catint_pnp_solve_batch also
+   takes 5: its field is the default pair's (backward sum from the bulk gradient, :787-790), the potential is
+   integrated from the bulk end (:795-797) out of g_out (pass g_out with phi_out; no flux equations).          */
 enum { CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_BULK = 0, CATINT_PNP_BC_STERN_ROBIN = 1,
        CATINT_PNP_BC_DIRICHLET_BOTH = 2,               /* potential at wall and bulk                           */
        CATINT_PNP_BC_DIRICHLET_WALL_NEUMANN_WALL = 3,  /* potential and gradient at the wall                   */

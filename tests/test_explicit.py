@@ -229,7 +229,7 @@ def test_entry_points_reject_what_they_do_not_handle(bk):
     db = bk.upload(batch)
     with pytest.raises(RuntimeError, match='default Poisson boundary'):
         bk.rhs(db, c)
-    with pytest.raises(RuntimeError, match='Poisson boundary must be the default pair or Stern'):
+    with pytest.raises(RuntimeError, match='Poisson boundary must be the default pair, the bulk/bulk pair or Stern'):
         bk.solve(db, [1.0])
     v, g, lp = bk.potential(db, c)                       # ... but the Poisson routine and the steppers take it
     assert torch.isfinite(v).all()
@@ -251,3 +251,55 @@ def test_entry_points_reject_what_they_do_not_handle(bk):
     # outputs only at the listed steps; Crank-Nicolson counts its steps from 1 like the reference
     out = bk.step(bk.upload(batch_with_pair(su, 0)), be.STEPPER_CRANK_NICOLSON, 1e-11, 4, [1, 3])
     assert out['c'].shape[0] == 2 and not torch.equal(out['c'][0], out['c'][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('graded', [False, True])
+def test_implicit_integrator_takes_the_bulk_bulk_pair(bk, graded):
+    """pb_bound = potential and gradient in the bulk (calculator_old.py:787-790 + :795-797): the field is the default
+    pair's backward sum, so concentrations and gradient of catint_pnp_solve_batch must equal the default-pair run bit
+    for bit; the potential must be the restatement's backward sum of that gradient (on the graded mesh: the same
+    recursion with h_i = x_{i+1}-x_i)."""
+    from catint_b200 import backend as be
+    from oracle.explicit_oracle import potential_and_gradient
+    su = load_golden('ref_c1.npz')
+    S, n = len(su['z']), int(su['nx'])
+    pair = dict(potential=dict(wall=None, bulk=0.013), gradient=dict(wall=None, bulk=float(su['g_bulk'])))
+    res = {}
+    for code in (be.BC_DIRICHLET_WALL_NEUMANN_BULK, be.BC_DIRICHLET_BULK_NEUMANN_BULK):
+        batch = batch_from_setup(su, B=2)
+        batch.par[1, S:2 * S] *= 0.5
+        batch.poisson_bc = code
+        batch.par[:, 3 * S + 3] = pair['gradient']['bulk']
+        if code == be.BC_DIRICHLET_BULK_NEUMANN_BULK:
+            batch.par[:, 3 * S + 2] = 0.0
+            batch.par[:, 3 * S + 6] = pair['potential']['bulk']
+        if graded:
+            xi = np.linspace(0.0, 1.0, n) ** 1.5
+            batch.mesh_id = np.zeros(2, dtype=np.int32)
+            batch.mesh_xi = xi[None, :]
+            batch.par[:, 3 * S + 5] = float(su['dx']) * (n - 1)
+        out = bk.solve(bk.upload(batch), [1e-3, 10.0], mode=be.MODE_TRANSIENT)
+        assert out['status'].tolist() == [0, 0]
+        res[code] = {k: out[k].cpu().numpy() for k in ('c', 'g', 'phi')}
+    a, b = res[be.BC_DIRICHLET_WALL_NEUMANN_BULK], res[be.BC_DIRICHLET_BULK_NEUMANN_BULK]
+    assert np.array_equal(a['c'], b['c']) and np.array_equal(a['g'], b['g'])
+    for k in range(2):
+        for cell in range(2):
+            g = b['g'][k, cell, :n]
+            v = b['phi'][k, cell, :n]
+            if not graded:
+                C = b['c'][k, cell, :n].T
+                v2, g2, _ = potential_and_gradient(C, float(su['dx']), su['z'] * UNIT_F, float(su['eps']), pair)
+                scale = np.max(np.abs(g2)) * float(su['dx']) * n + np.max(np.abs(v2))
+                # the integrator carries g as an unknown solved to the Newton tolerance, the restatement sums the charge
+                assert np.max(np.abs(g - g2)) <= 1e-6 * np.max(np.abs(g2))
+                assert np.max(np.abs(v - v2)) <= 1e-6 * scale
+            x = (batch.mesh_xi[0] * batch.par[cell, 3 * S + 5]) if graded else np.arange(n) * float(su['dx'])
+            want = np.zeros(n)
+            want[n - 1] = pair['potential']['bulk']
+            for i in range(n - 2, 0, -1):
+                want[i] = want[i + 1] - g[i] * (x[i + 1] - x[i])
+            want[0] = want[1] + (want[1] - want[2]) * (x[1] - x[0]) / (x[2] - x[1])
+            assert np.max(np.abs(v - want)) <= 1e-13 * (np.max(np.abs(want)) + np.sum(np.abs(g[1:n - 1] * np.diff(x)[1:])))
+    assert not np.array_equal(a['phi'], b['phi'])
