@@ -217,6 +217,12 @@ class Calculator():
             self.tp.logger.error('| CI | -- | Lax-Friedrichs terms belong to the fixed-step steppers (FTCS--LF, '
                                  'Crank-Nicolson--LF)')
             sys.exit()
+        if scale_pb_grid is not None:
+            # calculator_old.py:684-712, :805-813: 'linear' divides dx by the option string (TypeError upstream), 'log'
+            # integrates a logarithmic grid with the uniform dx -- neither is a result to reproduce; never ignore it
+            self.tp.logger.error('| CI | -- | scale_pb_grid is not available (the reference option cannot run / integrates '
+                                 'the log grid with the uniform dx); pass mesh= for a graded grid')
+            sys.exit()
         self.scale_pb_grid = scale_pb_grid
         self.tau_jacobi = tau_jacobi
         self.rtol, self.atol = rtol, atol
@@ -302,7 +308,9 @@ class Calculator():
             sys.exit()
         mode = _be.MODE_STEADY if self.mode == 'stationary' else _be.MODE_TRANSIENT
         y0_dev = None
-        if y0 is not None:
+        if torch.is_tensor(y0):
+            y0_dev = y0.to(device=backend.device, dtype=torch.float64).contiguous()
+        elif y0 is not None:
             y0_dev = torch.as_tensor(np.ascontiguousarray(y0, dtype=np.float64)).to(backend.device)
         out = backend.solve(db, self.output_times(), mode=mode, rtol=self.rtol, atol=self.atol,
                             max_steps=self.max_steps, y0=y0_dev)
@@ -412,52 +420,65 @@ class Calculator():
         return res
 
     # ------------------------------------------------------------------
-    def run_continuation(self, batch):
+    def run_continuation(self, batch, root_only=False):
         """two waves over a sweep (the batch analogue of the reference's COMSOL option 'internal-cont',
         transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
         wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
         nearest wave-1 neighbour, over the full time span (so a wrong starting guess costs steps, not accuracy).
-        Both waves are sharded like a plain run.  Returns the result dict of the whole batch."""
+        Both waves are sharded like a plain run.  The results of wave 1 stay on the devices: every rank builds the
+        initial states of its wave-2 cells there (an index_select of the gathered wave-1 states), the two waves
+        are merged there, and ONE device->host copy brings the whole batch to the host (root_only: of rank 0
+        only; the other ranks return None).  Returns the result dict of the whole batch."""
+        import torch
         from . import distributed as _dist
         k = int(self.continuation)
-        B = batch.B
+        B, S = batch.B, batch.S
         cold = np.arange(0, B, k)
         if cold[-1] != B - 1:
             cold = np.append(cold, B - 1)
         warm = np.setdiff1d(np.arange(B), cold)
-        r1 = _dist.solve_sharded(self, batch.select(cold))
-        if r1 is None:
-            return None
+
+        def as_tensors(r):
+            return {key: (torch.as_tensor(v) if isinstance(v, np.ndarray) else v) for key, v in r.items()}
+
+        r1 = as_tensors(_dist.solve_sharded(self, batch.select(cold), to_host=False))
+        dev = r1['c'].device
         if len(warm) == 0:
-            return r1
-        nearest = cold[np.argmin(np.abs(warm[:, None] - cold[None, :]), axis=1)]
-        pos = {int(c): i for i, c in enumerate(cold)}
-        y0 = np.stack([r1['c'][-1, pos[int(c)]] for c in nearest])                     # [n_warm, nx_max, S]
-        ok = np.array([r1['status'][pos[int(c)]] == 0 for c in nearest])
-        for j in np.where(~ok)[0]:                                                     # failed neighbour: cold start
-            y0[j] = batch.par[warm[j], None, 0:batch.S]
+            return _dist.results_to_host(r1, root_only=root_only)
+        # position (in wave 1) of the nearest cold neighbour of every warm cell
+        nearest = np.searchsorted(cold, warm)                       # cold[nearest-1] < warm < cold[nearest]
+        nearest = np.where(warm - cold[nearest - 1] <= cold[nearest] - warm, nearest - 1, nearest)
+        near_t = torch.as_tensor(nearest, device=dev)
+        c1 = r1['c'][-1]                                            # [n_cold, nx_max, S]
+        ok = (r1['status'] == 0).index_select(0, near_t)            # failed neighbour: cold start from the bulk state
+        bulk = torch.as_tensor(np.ascontiguousarray(batch.par[warm, 0:S])).to(dev)
+
+        def warm_start(sb):
+            o = torch.as_tensor(np.asarray(sb.origin), device=dev)
+            src = c1.index_select(0, near_t.index_select(0, o))
+            y0 = torch.where(ok.index_select(0, o)[:, None, None], src, bulk.index_select(0, o)[:, None, :])
+            return self.solve_batch_device(sb, y0=y0.contiguous())
+
         sub = batch.select(warm)
-        sub.origin = np.arange(sub.B)                  # shards of `sub` index y0 by their position in `sub`
-        r2 = _dist.solve_sharded(self, sub, solve_fn=lambda sb: self.solve_batch_device(sb, y0=y0[sb.origin]))
+        sub.origin = np.arange(sub.B)                  # shards of `sub` index the warm list by their position in `sub`
+        r2 = as_tensors(_dist.solve_sharded(self, sub, solve_fn=warm_start, to_host=False))
+        cold_t, warm_t = torch.as_tensor(cold, device=dev), torch.as_tensor(warm, device=dev)
         res = {}
         for key, v in r1.items():
-            if not hasattr(v, 'shape') or v.ndim == 0:
-                res[key] = v
+            if not torch.is_tensor(v) or v.ndim == 0:
+                res[key] = v + r2[key] if key in ('h2d_bytes', 'gather_bytes') and key in r2 else v
                 continue
             ax = 1 if key in ('c', 'phi', 'g') else 0
             shape = list(v.shape)
             shape[ax] = B
-            full = np.zeros(shape, dtype=v.dtype)
-            idx1 = [slice(None)] * v.ndim
-            idx2 = [slice(None)] * v.ndim
-            idx1[ax], idx2[ax] = cold, warm
-            full[tuple(idx1)] = v
-            full[tuple(idx2)] = r2[key]
+            full = torch.empty(shape, dtype=v.dtype, device=dev)
+            full.index_copy_(ax, cold_t, v)
+            full.index_copy_(ax, warm_t, r2[key].to(dev))
             res[key] = full
         self.continuation_stats = {'cold_cells': len(cold), 'warm_cells': len(warm),
-                                   'cold_steps_mean': float(np.mean(r1['n_steps'])),
-                                   'warm_steps_mean': float(np.mean(r2['n_steps']))}
-        return res
+                                   'cold_steps_mean': float(r1['n_steps'].double().mean()),
+                                   'warm_steps_mean': float(r2['n_steps'].double().mean())}
+        return _dist.results_to_host(res, root_only=root_only)
 
     def scatter_results(self, batch, models, res):
         """fill tp.cout/potential/efield/total_charge (last cell, like the serial

@@ -123,12 +123,14 @@ def _to_host_pinned(t, key):
     return buf
 
 
-def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, root_only=False):
+def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, root_only=False, to_host=True):
     """ONE all_gather of the packed per-rank results; the round-robin order (cell j -> rank j % N) is undone and
     the fields are split ON THE DEVICE (a transpose and slices), then one copy per field into pinned host memory.
     root_only: only rank 0 copies the gathered results to its host (the others return None) -- what a driver
     that saves on rank 0 needs; the default hands every rank the complete result like the reference's
-    reduce_dict_mpi + sync_mpi (catint_io.py:154-178)."""
+    reduce_dict_mpi + sync_mpi (catint_io.py:154-178).  to_host=False: every rank keeps the ordered fields as
+    tensors on the gather's device (the next wave of a continuation run reads its initial states from them; no host
+    round trip)."""
     import torch
     import torch.distributed as dist
     per = (n_cells + world_size - 1) // world_size
@@ -139,7 +141,7 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, ro
     packed = pack_results(local, per, n_out, nx_max, S, device=dev)
     out = torch.empty((world_size * per, packed.shape[1]), dtype=torch.float64, device=packed.device)
     dist.all_gather_into_tensor(out, packed)
-    if root_only and dist.get_rank() != 0:
+    if root_only and to_host and dist.get_rank() != 0:
         return None
     width = out.shape[1]
     # row r*per + i holds cell i*N + r: [N, per, w] -> [per, N, w] -> cells in order
@@ -153,7 +155,13 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, ro
         if name in _INT_FIELDS:
             a = torch.round(a).to(torch.int32)
         a = a.movedim(0, _CELL_AXIS[name]).contiguous()
+        if not to_host:
+            full[name] = a
+            continue
         staged[name] = _to_host_pinned(a, name)
+    if not to_host:
+        full['gather_bytes'] = int(out.numel() * 8)
+        return full
     if out.device.type == 'cuda':
         torch.cuda.current_stream(out.device).synchronize()
     for name, h in staged.items():
@@ -163,19 +171,22 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, ro
     return full
 
 
-def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None, root_only=False):
+def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None, root_only=False, to_host=True):
     """Solve ``batch`` with the cells split over all ranks; every rank returns
     the complete, ordered result dict (numpy).  ``solve_fn(sub_batch) -> dict`` of
     torch tensors (device) or numpy arrays defaults to the CUDA path
     ``calc.solve_batch_device`` (tests of the host logic inject their own
     function; there is no CPU solver in the product).  A rank whose shard is
     empty (fewer cells than ranks) skips the solve and still joins the gather,
-    like the reference's ``itask % size != rank: continue``."""
+    like the reference's ``itask % size != rank: continue``.  ``to_host=False``: the ordered result stays on
+    the device of every rank (dict of torch tensors), see ``results_to_host``."""
     rank, ws = world()
     if ws > 1 and not group_ready():
         raise RuntimeError('catint_b200: WORLD_SIZE=%d but torch.distributed is not initialised; call '
                            'torch.distributed.init_process_group first (one process per GPU)' % ws)
     if ws == 1:
+        if not to_host:
+            return (solve_fn or calc.solve_batch_device)(batch)
         if solve_fn is None:
             return calc.solve_batch(batch)
         return _to_host(solve_fn(batch))
@@ -190,9 +201,32 @@ def solve_sharded(calc, batch, solve_fn=None, device=None, n_out=None, root_only
     else:
         local = solve_fn(batch.select(idx))
         extra = {k: v for k, v in local.items() if k not in _CELL_AXIS}
-    full = gather_results(local, batch.B, ws, n_out, batch.nx_max, batch.S, device=device, root_only=root_only)
+    full = gather_results(local, batch.B, ws, n_out, batch.nx_max, batch.S, device=device, root_only=root_only,
+                          to_host=to_host)
     if full is not None:
         full.update(extra)
+    return full
+
+
+def results_to_host(res, root_only=False):
+    """ordered result dict of device tensors (solve_sharded(..., to_host=False)) -> numpy, through the pinned
+    staging buffers of the gather; root_only: ranks other than 0 return None"""
+    import torch
+    if root_only and world()[0] != 0:
+        return None
+    staged, full = {}, {}
+    dev = None
+    for k, v in res.items():
+        if torch.is_tensor(v):
+            staged[k] = _to_host_pinned(v.contiguous(), k)
+            if v.device.type == 'cuda':
+                dev = v.device
+        else:
+            full[k] = v
+    if dev is not None:
+        torch.cuda.current_stream(dev).synchronize()
+    for k, h in staged.items():
+        full[k] = np.array(h.numpy(), copy=True) if torch.is_tensor(h) else h
     return full
 
 

@@ -1,0 +1,51 @@
+"""C2 potential sweep, plain run against Calculator(continuation=k) (the batch analogue of the reference's
+'internal-cont', /root/reference/catint/transport.py:834-842), both through the host-buffer path
+(distributed.solve_sharded: H2D of the parameters, solve, D2H of the results):
+    python scripts/continuation_bench.py [k] [n_cells ...]
+Prints for every sweep size the wall time of both modes, the step counts, and how many cells of the continuation
+run deviate from the plain run's steady state by more than 1e-6 (same discrete root or not)."""
+import os, sys, time, tempfile
+HERE = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, os.path.dirname(HERE))
+os.environ.setdefault('CATINT_QUIET', '1')
+import numpy as np
+import torch
+from catint_b200 import workloads, distributed as D
+from catint_b200.transport import Transport
+from catint_b200.calculator import Calculator, build_cell_batch
+
+
+def main():
+    k = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    sizes = [int(a) for a in sys.argv[2:]] or [1024, 8192]
+    for n in sizes:
+        tp = Transport(resultsdir=tempfile.mkdtemp(prefix='catint_cont_'), model_name='cont', **workloads.c2(n_potentials=n))
+        tp.set_calculator('odeint')
+        batch, _ = build_cell_batch(tp)
+        plain = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', device='cuda:0')
+        cont = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', device='cuda:0', continuation=k)
+        res = {}
+        modes = (('plain', lambda: D.solve_sharded(plain, batch)), ('cont', lambda: cont.run_continuation(batch)))
+        if os.environ.get('CONT_NO_PLAIN'):
+            modes = modes[1:]
+        for name, fn in modes:
+            fn()                                             # warm-up (allocations, first launch)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            res[name] = r
+            print('%5d cells %-5s: %.4f s = %8.1f cells/s, converged %d, steps mean %.0f max %d'
+                  % (n, name, dt, n / dt, int(np.sum(r['status'] == 0)), r['n_steps'].mean(), r['n_steps'].max()))
+        st = getattr(cont, 'continuation_stats', None)
+        if st:
+            print('      ', {kk: (round(v, 1) if isinstance(v, float) else v) for kk, v in st.items()})
+        if 'plain' not in res:
+            continue
+        a, b = res['plain']['c'][-1], res['cont']['c'][-1]
+        scale = np.max(np.abs(a), axis=(1, 2), keepdims=True)
+        dev = np.max(np.abs(a - b) / scale, axis=(1, 2))
+        print('%5d cells: continuation vs plain steady states, worst relative deviation %.2e, cells beyond 1e-6: %d'
+              % (n, dev.max(), int(np.sum(dev > 1e-6))))
+
+
+if __name__ == '__main__':
+    main()

@@ -151,3 +151,77 @@ def test_root_only_gather_hands_the_results_to_rank_zero():
     assert got[1] is None
     for k in ('c', 'phi', 'g', 'flux', 'status', 'n_steps', 'n_newton', 'n_setups'):
         assert np.array_equal(got[0][k], want[k]), k
+
+
+# ---- continuation (two waves) over two ranks: plumbing with a stand-in solve ---------------------------------
+def _fake_device_solve(sub, y0=None):
+    """stand-in for Calculator.solve_batch_device (CPU tensors): the 'steady state' is a function of the cell's
+    fluxes; the result also records where the cell started from (c of output 0 = y0, bulk state when none)"""
+    r = fake_solve(sub)
+    B, n, S = sub.B, sub.nx_max, sub.S
+    r['c'] = r['c'][:2].copy()
+    start = np.broadcast_to(sub.par[:, None, 0:S], (B, n, S)) if y0 is None else y0.numpy()
+    r['c'][0] = start
+    r['status'] = np.zeros(B, dtype=np.int32)
+    r['status'][sub.par[:, 3 * S + 4] < 0] = 2           # cells flagged by a negative Stern capacitance "fail"
+    return {k: torch.as_tensor(np.ascontiguousarray(v)) for k, v in r.items()}
+
+
+def _continuation_worker(rank, world, port, q, n_cells, k, root_only):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    if world > 1:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from catint_b200.calculator import Calculator
+        batch = make_batch(n_cells)
+        S = batch.S
+        batch.par[k, 3 * S + 4] = -1.0                   # the second cold cell fails: its neighbours start cold
+        calc = Calculator.__new__(Calculator)            # plumbing only: no Transport, no device
+        calc.continuation = k
+        calc.solve_batch_device = _fake_device_solve
+        calc.output_times = lambda: [1.0, 2.0]
+        res = calc.run_continuation(batch, root_only=root_only)
+        q.put((rank, None if res is None else dict(res, stats=calc.continuation_stats)))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,root_only', [(1, False), (2, False), (2, True)])
+def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_only):
+    n_cells, k = 23, 4
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_continuation_worker, args=(r, world, port, q, n_cells, k, root_only)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    batch = make_batch(n_cells)
+    S, n = batch.S, batch.nx_max
+    want = fake_solve(batch)
+    cold = sorted(set(range(0, n_cells, k)) | {n_cells - 1})
+    for rank in range(world):
+        res = got[rank]
+        if root_only and rank != 0:
+            assert res is None
+            continue
+        assert res['stats']['cold_cells'] == len(cold) and res['stats']['warm_cells'] == n_cells - len(cold)
+        # final states and per-cell fields: those of a plain run, in cell order
+        assert np.array_equal(res['c'][1], want['c'][1]) and np.array_equal(res['flux'], want['flux'])
+        assert np.array_equal(res['n_steps'], want['n_steps']) and res['status'].dtype == np.int32
+        for cell in range(n_cells):
+            start = res['c'][0, cell]
+            bulk = np.broadcast_to(batch.par[cell, None, 0:S], (n, S))
+            if cell in cold:
+                assert np.array_equal(start, bulk)
+                continue
+            near = min(cold, key=lambda c: (abs(c - cell), c))
+            if near == k:                                # failed neighbour -> bulk state
+                assert np.array_equal(start, bulk)
+            else:
+                assert np.array_equal(start, want['c'][1, near]), (cell, near)

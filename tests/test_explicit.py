@@ -110,6 +110,8 @@ def test_calculator_accepts_the_fixed_step_calcs(resultsdir):
         assert c.calc == name.split('--')[0] and c.use_lax_friedrich == lf
     with pytest.raises(SystemExit):
         Calculator(transport=tp, dt=1e-11, tmax=1e-9, ntout=4, calc='odeint--LF')
+    with pytest.raises(SystemExit):                       # never silently ignored
+        Calculator(transport=tp, dt=1e-11, tmax=1e-9, ntout=4, calc='odeint', scale_pb_grid='log')
 
 
 # ---------------------------------------------------------------- device ----------------------------------
@@ -275,11 +277,12 @@ def test_implicit_integrator_takes_the_bulk_bulk_pair(bk, graded):
             batch.par[:, 3 * S + 2] = 0.0
             batch.par[:, 3 * S + 6] = pair['potential']['bulk']
         if graded:
-            xi = np.linspace(0.0, 1.0, n) ** 1.5
+            sx = np.linspace(0.0, 1.0, n)
+            xi = sx + 0.02 * np.sin(np.pi * sx) ** 2          # spacings within +-6 % of the uniform ones
             batch.mesh_id = np.zeros(2, dtype=np.int32)
             batch.mesh_xi = xi[None, :]
             batch.par[:, 3 * S + 5] = float(su['dx']) * (n - 1)
-        out = bk.solve(bk.upload(batch), [1e-3, 10.0], mode=be.MODE_TRANSIENT)
+        out = bk.solve(bk.upload(batch), [1e-7, 1e-6] if graded else [1e-3, 10.0], mode=be.MODE_TRANSIENT)
         assert out['status'].tolist() == [0, 0]
         res[code] = {k: out[k].cpu().numpy() for k in ('c', 'g', 'phi')}
     a, b = res[be.BC_DIRICHLET_WALL_NEUMANN_BULK], res[be.BC_DIRICHLET_BULK_NEUMANN_BULK]
