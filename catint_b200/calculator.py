@@ -16,6 +16,7 @@ the result containers the reference's tools read (tp.cout, tp.potential,
 tp.efield, tp.total_charge, tp.alldata[i][...]; conventions of
 /root/reference/catint/comsol_reader.py:186-300).
 """
+import os
 import sys
 import time
 
@@ -441,7 +442,18 @@ class Calculator():
         def as_tensors(r):
             return {key: (torch.as_tensor(v) if isinstance(v, np.ndarray) else v) for key, v in r.items()}
 
+        timing = os.environ.get('CATINT_CONT_TIMING')         # debug: synchronised wall time of the four stages
+        marks = []
+
+        def mark(name):
+            if timing:
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark('start')
         r1 = as_tensors(_dist.solve_sharded(self, batch.select(cold), to_host=False))
+        mark('wave1')
         dev = r1['c'].device
         if len(warm) == 0:
             return _dist.results_to_host(r1, root_only=root_only)
@@ -462,6 +474,7 @@ class Calculator():
         sub = batch.select(warm)
         sub.origin = np.arange(sub.B)                  # shards of `sub` index the warm list by their position in `sub`
         r2 = as_tensors(_dist.solve_sharded(self, sub, solve_fn=warm_start, to_host=False))
+        mark('wave2')
         cold_t, warm_t = torch.as_tensor(cold, device=dev), torch.as_tensor(warm, device=dev)
         res = {}
         for key, v in r1.items():
@@ -478,7 +491,12 @@ class Calculator():
         self.continuation_stats = {'cold_cells': len(cold), 'warm_cells': len(warm),
                                    'cold_steps_mean': float(r1['n_steps'].double().mean()),
                                    'warm_steps_mean': float(r2['n_steps'].double().mean())}
-        return _dist.results_to_host(res, root_only=root_only)
+        mark('merge')
+        host = _dist.results_to_host(res, root_only=root_only)
+        mark('to_host')
+        if timing:
+            self.continuation_timing = {b[0]: b[1] - a[1] for a, b in zip(marks[:-1], marks[1:])}
+        return host
 
     def scatter_results(self, batch, models, res):
         """fill tp.cout/potential/efield/total_charge (last cell, like the serial

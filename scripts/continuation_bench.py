@@ -35,6 +35,8 @@ def main():
             res[name] = r
             print('%5d cells %-5s: %.4f s = %8.1f cells/s, converged %d, steps mean %.0f max %d'
                   % (n, name, dt, n / dt, int(np.sum(r['status'] == 0)), r['n_steps'].mean(), r['n_steps'].max()))
+        if getattr(cont, 'continuation_timing', None):
+            print('       stages [s]:', {a: round(b, 4) for a, b in cont.continuation_timing.items()})
         st = getattr(cont, 'continuation_stats', None)
         if st:
             print('      ', {kk: (round(v, 1) if isinstance(v, float) else v) for kk, v in st.items()})
