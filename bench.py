@@ -328,6 +328,7 @@ def continuation_block(bk, dev, world, rank, sync_all, reps=2):
     sync_all()
     t0 = time.perf_counter()
     for _ in range(reps):
+        res = None                                       # drop the previous result: its pinned block is recycled
         res = calc.run_continuation(gb, root_only=True)
     sync_all()
     dt = (time.perf_counter() - t0) / reps
@@ -425,6 +426,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     e2e_conv = 0
     for _ in range(e2e_steps):
+        res = None                                       # drop the previous result: its pinned block is recycled
         res = e2e_step()
         if res is not None:
             e2e_conv += int(np.sum(res['status'] == 0))                # whole job (gathered on rank 0)

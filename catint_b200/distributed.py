@@ -106,19 +106,16 @@ def unpack_results(gathered, n_cells, world_size, n_out, nx_max, S):
     return full
 
 
-_PINNED = {}
-
-
-def _to_host_pinned(t, key):
-    """device tensor -> numpy through a cached pinned staging buffer (pageable copies of the gathered results
-    cost several times the kernel at 8 GPUs); CPU tensors pass through"""
+def _to_host_pinned(t, key=None):
+    """device tensor -> a FRESH pinned host tensor (asynchronous copy on the current stream; the caller synchronises
+    and hands out its numpy view).  Pageable copies of the gathered results cost several times the kernel at 8
+    GPUs, and copying a reused staging buffer into a new numpy array costs as much again (first-touch page faults:
+    ~3 GB/s).  torch's caching host allocator recycles the pinned block once the caller has dropped the previous
+    result, so a loop of solves pays the page-locking once.  CPU tensors pass through."""
     import torch
     if t.device.type != 'cuda':
-        return t.numpy()
-    buf = _PINNED.get(key)
-    if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        _PINNED[key] = buf
+        return t
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     buf.copy_(t, non_blocking=True)
     return buf
 
@@ -165,8 +162,7 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, ro
     if out.device.type == 'cuda':
         torch.cuda.current_stream(out.device).synchronize()
     for name, h in staged.items():
-        # the staging buffers are reused by the next call: hand out copies (a straight host memcpy)
-        full[name] = np.array(h.numpy(), copy=True) if torch.is_tensor(h) else h
+        full[name] = h.numpy()                        # view of this call's own pinned block (kept alive by the array)
     full['gather_bytes'] = int(out.numel() * 8)
     return full
 
@@ -226,7 +222,7 @@ def results_to_host(res, root_only=False):
     if dev is not None:
         torch.cuda.current_stream(dev).synchronize()
     for k, h in staged.items():
-        full[k] = np.array(h.numpy(), copy=True) if torch.is_tensor(h) else h
+        full[k] = h.numpy()
     return full
 
 

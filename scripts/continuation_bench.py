@@ -28,7 +28,8 @@ def main():
         if os.environ.get('CONT_NO_PLAIN'):
             modes = modes[1:]
         for name, fn in modes:
-            fn()                                             # warm-up (allocations, first launch)
+            r = fn()                                         # warm-up (allocations, first launch)
+            del r
             torch.cuda.synchronize(); t0 = time.perf_counter()
             r = fn()
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
