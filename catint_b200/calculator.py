@@ -490,7 +490,9 @@ class Calculator():
             res[key] = full
         self.continuation_stats = {'cold_cells': len(cold), 'warm_cells': len(warm),
                                    'cold_steps_mean': float(r1['n_steps'].double().mean()),
-                                   'warm_steps_mean': float(r2['n_steps'].double().mean())}
+                                   'warm_steps_mean': float(r2['n_steps'].double().mean()),
+                                   'warm_newton_mean': float(r2['n_newton'].double().mean()),
+                                   'warm_setups_mean': float(r2['n_setups'].double().mean())}
         mark('merge')
         host = _dist.results_to_host(res, root_only=root_only)
         mark('to_host')

@@ -27,6 +27,17 @@ def main():
     print('rank %d/%d: sharded == single-rank: %s, converged %d/%d, CO2(0) first/last %.6f %.6f' % (
         rank, world, ok, int((res['status'] == 0).sum()), batch.B,
         tp.alldata[0]['species']['CO2']['surface_concentration'], tp.alldata[-1]['species']['CO2']['surface_concentration']), flush=True)
+    # continuation run (two sharded waves, wave 1 gathered and kept on the devices): the plain run's steady states
+    cont = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', device='cuda:%d' % local, continuation=4)
+    rc = cont.run_continuation(batch)
+    scale = np.max(np.abs(ref['c'][-1]), axis=(1, 2), keepdims=True)
+    devn = float(np.max(np.abs(rc['c'][-1] - ref['c'][-1]) / scale))
+    okc = devn < 1e-6 and bool(np.all(rc['status'] == 0)) and rc['status'].dtype == ref['status'].dtype \
+        and float(np.max(np.abs(rc['flux'] - ref['flux']))) < 1e-6 * float(np.max(np.abs(ref['flux'])))
+    st = cont.continuation_stats
+    print('rank %d/%d: continuation == plain: %s (worst deviation %.1e, cold %d cells %.0f steps, warm %d cells %.0f steps)'
+          % (rank, world, okc, devn, st['cold_cells'], st['cold_steps_mean'], st['warm_cells'], st['warm_steps_mean']), flush=True)
+    ok = ok and okc
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -1,7 +1,8 @@
 """Two-GPU test of the sharded driver (skipped on a one-GPU box): Calculator.run() under torch.distributed
 with NCCL -- cells sharded round-robin, one packed all_gather on the devices -- must give every rank the
 complete, ordered result, bit for bit equal to the single-rank solve of the same batch
-(/root/reference/catint/calculator.py:209-212, catint_io.py:154-178 is what it replaces)."""
+(/root/reference/catint/calculator.py:209-212, catint_io.py:154-178 is what it replaces); the two-wave continuation
+run over the same two ranks must end on the same steady states (1e-6)."""
 import os
 import subprocess
 import sys
@@ -25,3 +26,4 @@ def test_sharded_run_equals_single_rank_on_two_gpus():
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:]
     assert p.stdout.count('sharded == single-rank: True') == 2, p.stdout[-3000:]
+    assert p.stdout.count('continuation == plain: True') == 2, p.stdout[-3000:]
