@@ -292,7 +292,7 @@ class Calculator():
             ts = [float(self.tp.tmax)]
         return ts
 
-    def solve_batch_device(self, batch, backend=None, pinned=None, y0=None):
+    def solve_batch_device(self, batch, backend=None, pinned=None, y0=None, max_steps=None):
         """host CellBatch -> result dict of DEVICE tensors (plus the host->device byte count): upload of the
         cell parameters and the solve.  The sharded driver gathers these on the device."""
         import torch
@@ -314,7 +314,7 @@ class Calculator():
         elif y0 is not None:
             y0_dev = torch.as_tensor(np.ascontiguousarray(y0, dtype=np.float64)).to(backend.device)
         out = backend.solve(db, self.output_times(), mode=mode, rtol=self.rtol, atol=self.atol,
-                            max_steps=self.max_steps, y0=y0_dev)
+                            max_steps=self.max_steps if max_steps is None else int(max_steps), y0=y0_dev)
         out = dict(out)
         out['h2d_bytes'] = db.h2d_bytes + (0 if y0 is None else int(y0_dev.numel() * 8))
         return out
@@ -426,7 +426,9 @@ class Calculator():
         transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
         wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
         nearest wave-1 neighbour, over the full time span (so a wrong starting guess costs steps, not accuracy).
-        Both waves are sharded like a plain run.  The results of wave 1 stay on the devices: every rank builds the
+        A warm cell may take at most 3x the steps of the slowest converged cold cell; warm cells that fail (or hit that
+        cap) are solved again from the bulk state (wave 3), so a cell that converges in a plain run converges here.
+        All waves are sharded like a plain run.  The results of wave 1 stay on the devices: every rank builds the
         initial states of its wave-2 cells there (an index_select of the gathered wave-1 states), the two waves
         are merged there, and ONE device->host copy brings the whole batch to the host (root_only: of rank 0
         only; the other ranks return None).  Returns the result dict of the whole batch."""
@@ -465,16 +467,32 @@ class Calculator():
         ok = (r1['status'] == 0).index_select(0, near_t)            # failed neighbour: cold start from the bulk state
         bulk = torch.as_tensor(np.ascontiguousarray(batch.par[warm, 0:S])).to(dev)
 
+        conv1 = r1['status'] == 0
+        cold_max = int(torch.where(conv1, r1['n_steps'], torch.zeros_like(r1['n_steps'])).max()) if len(cold) else 0
+        warm_cap = int(min(self.max_steps, max(1000, 3 * cold_max)))
+        if getattr(self, 'continuation_warm_cap', None):              # test / tuning knob: explicit cap of the warm wave
+            warm_cap = int(self.continuation_warm_cap)
+
         def warm_start(sb):
             o = torch.as_tensor(np.asarray(sb.origin), device=dev)
             src = c1.index_select(0, near_t.index_select(0, o))
             y0 = torch.where(ok.index_select(0, o)[:, None, None], src, bulk.index_select(0, o)[:, None, :])
-            return self.solve_batch_device(sb, y0=y0.contiguous())
+            return self.solve_batch_device(sb, y0=y0.contiguous(), max_steps=warm_cap)
 
         sub = batch.select(warm)
         sub.origin = np.arange(sub.B)                  # shards of `sub` index the warm list by their position in `sub`
         r2 = as_tensors(_dist.solve_sharded(self, sub, solve_fn=warm_start, to_host=False))
         mark('wave2')
+        # wave 3: warm-started cells that did not converge start again from the bulk state (every rank holds the same
+        # gathered wave-2 status, so every rank takes the same decision)
+        rerun = torch.nonzero((r2['status'] != 0) & ok.to(r2['status'].device)).flatten()
+        n_rerun = int(rerun.numel())
+        if n_rerun:
+            r3 = as_tensors(_dist.solve_sharded(self, batch.select(warm[rerun.cpu().numpy()]), to_host=False))
+            for key, v in r2.items():
+                if torch.is_tensor(v) and v.ndim > 0 and key in r3:
+                    v.index_copy_(1 if key in ('c', 'phi', 'g') else 0, rerun.to(v.device), r3[key].to(v.device))
+        mark('wave3')
         cold_t, warm_t = torch.as_tensor(cold, device=dev), torch.as_tensor(warm, device=dev)
         res = {}
         for key, v in r1.items():
@@ -492,7 +510,8 @@ class Calculator():
                                    'cold_steps_mean': float(r1['n_steps'].double().mean()),
                                    'warm_steps_mean': float(r2['n_steps'].double().mean()),
                                    'warm_newton_mean': float(r2['n_newton'].double().mean()),
-                                   'warm_setups_mean': float(r2['n_setups'].double().mean())}
+                                   'warm_setups_mean': float(r2['n_setups'].double().mean()),
+                                   'warm_step_cap': warm_cap, 'rerun_cold_cells': n_rerun}
         mark('merge')
         host = _dist.results_to_host(res, root_only=root_only)
         mark('to_host')

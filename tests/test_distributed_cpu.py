@@ -154,7 +154,7 @@ def test_root_only_gather_hands_the_results_to_rank_zero():
 
 
 # ---- continuation (two waves) over two ranks: plumbing with a stand-in solve ---------------------------------
-def _fake_device_solve(sub, y0=None):
+def _fake_device_solve(sub, y0=None, max_steps=None):
     """stand-in for Calculator.solve_batch_device (CPU tensors): the 'steady state' is a function of the cell's
     fluxes; the result also records where the cell started from (c of output 0 = y0, bulk state when none)"""
     r = fake_solve(sub)
@@ -163,7 +163,10 @@ def _fake_device_solve(sub, y0=None):
     start = np.broadcast_to(sub.par[:, None, 0:S], (B, n, S)) if y0 is None else y0.numpy()
     r['c'][0] = start
     r['status'] = np.zeros(B, dtype=np.int32)
-    r['status'][sub.par[:, 3 * S + 4] < 0] = 2           # cells flagged by a negative Stern capacitance "fail"
+    r['status'][sub.par[:, 3 * S + 4] == -1.0] = 2       # cells flagged by a Stern capacitance of -1 "fail"
+    if y0 is not None:                                   # ... flagged -2: fail when warm-started, converge from the bulk state
+        r['status'][sub.par[:, 3 * S + 4] == -2.0] = 3
+        assert max_steps == max(1000, 3 * int(sub.nx_max))          # cap = 3 x the slowest cold cell (fake n_steps = nx)
     return {k: torch.as_tensor(np.ascontiguousarray(v)) for k, v in r.items()}
 
 
@@ -177,8 +180,10 @@ def _continuation_worker(rank, world, port, q, n_cells, k, root_only):
         batch = make_batch(n_cells)
         S = batch.S
         batch.par[k, 3 * S + 4] = -1.0                   # the second cold cell fails: its neighbours start cold
+        batch.par[10, 3 * S + 4] = -2.0                  # warm cell 10 fails from its neighbour's state: solved again cold
         calc = Calculator.__new__(Calculator)            # plumbing only: no Transport, no device
         calc.continuation = k
+        calc.max_steps = 100000
         calc.solve_batch_device = _fake_device_solve
         calc.output_times = lambda: [1.0, 2.0]
         res = calc.run_continuation(batch, root_only=root_only)
@@ -214,6 +219,8 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
         # final states and per-cell fields: those of a plain run, in cell order
         assert np.array_equal(res['c'][1], want['c'][1]) and np.array_equal(res['flux'], want['flux'])
         assert np.array_equal(res['n_steps'], want['n_steps']) and res['status'].dtype == np.int32
+        assert res['stats']['rerun_cold_cells'] == 1 and res['status'][10] == 0 and res['status'][k] == 2
+        assert np.count_nonzero(res['status']) == 1
         for cell in range(n_cells):
             start = res['c'][0, cell]
             bulk = np.broadcast_to(batch.par[cell, None, 0:S], (n, S))
@@ -221,7 +228,7 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
                 assert np.array_equal(start, bulk)
                 continue
             near = min(cold, key=lambda c: (abs(c - cell), c))
-            if near == k:                                # failed neighbour -> bulk state
+            if near == k or cell == 10:                  # failed neighbour / re-run after a failed warm start -> bulk state
                 assert np.array_equal(start, bulk)
             else:
                 assert np.array_equal(start, want['c'][1, near]), (cell, near)

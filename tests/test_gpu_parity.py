@@ -547,3 +547,25 @@ def test_continuation_reaches_the_same_states_with_fewer_steps(bk, resultsdir):
     st = cont.continuation_stats
     assert st['cold_cells'] == 13 and st['warm_cells'] == 35
     assert st['warm_steps_mean'] < 0.5 * st['cold_steps_mean']
+
+
+def test_continuation_solves_failed_warm_cells_again_from_the_bulk_state(bk, resultsdir):
+    """a warm-started cell that does not converge (here: every one, the warm wave is capped at 5 steps) is solved
+    again cold, so the continuation run can only fail where a plain run fails: all cells converge, the states are
+    the plain run's, and the step counts of the re-run cells are those of cold cells"""
+    from catint_b200 import workloads
+    from catint_b200.transport import Transport
+    from catint_b200.calculator import Calculator, build_cell_batch
+    tp = Transport(resultsdir=resultsdir, model_name='rerun', **workloads.c2(n_potentials=24))
+    tp.set_calculator('odeint')
+    batch, _ = build_cell_batch(tp)
+    plain = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary').solve_batch(batch)
+    cont = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', continuation=4)
+    cont.continuation_warm_cap = 5
+    r = cont.run_continuation(batch)
+    st = cont.continuation_stats
+    assert st['cold_cells'] == 7 and st['warm_cells'] == 17 and st['rerun_cold_cells'] == 17
+    assert np.all(r['status'] == 0) and np.all(plain['status'] == 0)
+    assert np.array_equal(r['n_steps'], plain['n_steps'])          # every cell ended up integrated from the bulk state
+    assert relerr(r['c'][-1], plain['c'][-1], 93.7) < 1e-10
+    assert np.array_equal(r['flux'], plain['flux'])
