@@ -156,6 +156,29 @@ def build_cell_batch(tp, rate_mode='summed', points=None, poisson_bc='dirichlet'
     return batch, models
 
 
+def continuation_plan(n_cells, k, row_length=None):
+    """cold / warm split of a sweep for Calculator(continuation=k) and, for every warm cell, the position (in the
+    cold list) of its nearest cold neighbour.  The cells of a 2D descriptor grid are numbered row by row (inner
+    descriptor fastest, calculator.py:196-212): with ``row_length`` the plan is made per row -- every k-th cell of
+    a row and its last cell are cold, and a warm cell only looks for neighbours in its own row, never across the
+    row end, where the flattened neighbour is the other end of the inner descriptor's range."""
+    L = int(row_length) if row_length else int(n_cells)
+    if L <= 0 or n_cells % L != 0:
+        L = int(n_cells)
+    in_row = np.arange(0, L, k)
+    if in_row[-1] != L - 1:
+        in_row = np.append(in_row, L - 1)
+    rows = n_cells // L
+    cold = (np.arange(rows)[:, None] * L + in_row[None, :]).ravel()
+    warm = np.setdiff1d(np.arange(n_cells), cold)
+    if len(warm) == 0:
+        return cold, warm, np.zeros(0, dtype=np.int64)
+    wr, wi = warm // L, warm % L
+    j = np.searchsorted(in_row, wi)                                  # in_row[j-1] < wi < in_row[j]
+    j = np.where(wi - in_row[j - 1] <= in_row[j] - wi, j - 1, j)     # ties: the lower neighbour
+    return cold, warm, wr * len(in_row) + j
+
+
 def shard_indices(n_cells, rank, world_size):
     """round-robin cell -> rank map (calculator.py:209-212: itask % size == rank)"""
     return np.arange(rank, n_cells, world_size)
@@ -401,7 +424,8 @@ class Calculator():
         from . import distributed as _dist
         y0 = self.initial_state_from_folder(batch)
         if y0 is None and self.continuation is not None:
-            res = self.run_continuation(batch)
+            n1, n2 = len(tp.descriptors[keys[0]]), len(tp.descriptors[keys[1]])
+            res = self.run_continuation(batch, row_length=n2 if (n1 > 1 and n2 > 1) else None)
         elif y0 is None:
             res = _dist.solve_sharded(self, batch)
         else:
@@ -421,7 +445,7 @@ class Calculator():
         return res
 
     # ------------------------------------------------------------------
-    def run_continuation(self, batch, root_only=False):
+    def run_continuation(self, batch, root_only=False, row_length=None):
         """two waves over a sweep (the batch analogue of the reference's COMSOL option 'internal-cont',
         transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
         wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
@@ -436,10 +460,7 @@ class Calculator():
         from . import distributed as _dist
         k = int(self.continuation)
         B, S = batch.B, batch.S
-        cold = np.arange(0, B, k)
-        if cold[-1] != B - 1:
-            cold = np.append(cold, B - 1)
-        warm = np.setdiff1d(np.arange(B), cold)
+        cold, warm, nearest = continuation_plan(B, k, row_length)
 
         def as_tensors(r):
             return {key: (torch.as_tensor(v) if isinstance(v, np.ndarray) else v) for key, v in r.items()}
@@ -459,10 +480,7 @@ class Calculator():
         dev = r1['c'].device
         if len(warm) == 0:
             return _dist.results_to_host(r1, root_only=root_only)
-        # position (in wave 1) of the nearest cold neighbour of every warm cell
-        nearest = np.searchsorted(cold, warm)                       # cold[nearest-1] < warm < cold[nearest]
-        nearest = np.where(warm - cold[nearest - 1] <= cold[nearest] - warm, nearest - 1, nearest)
-        near_t = torch.as_tensor(nearest, device=dev)
+        near_t = torch.as_tensor(nearest, device=dev)    # position (in wave 1) of every warm cell's nearest cold neighbour
         c1 = r1['c'][-1]                                            # [n_cold, nx_max, S]
         ok = (r1['status'] == 0).index_select(0, near_t)            # failed neighbour: cold start from the bulk state
         bulk = torch.as_tensor(np.ascontiguousarray(batch.par[warm, 0:S])).to(dev)

@@ -132,3 +132,27 @@ def test_run_without_gpu_fails_loudly(resultsdir):
     calc = Calculator(transport=tp, dt=0.1, tmax=1.0)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         calc.run()
+
+
+def test_continuation_plan_splits_rows_and_finds_the_nearest_cold_cell():
+    """Calculator(continuation=k): every k-th cell and the last one cold; on a 2D descriptor grid per row of the inner
+    descriptor, neighbours never across a row end"""
+    from catint_b200.calculator import continuation_plan
+    cold, warm, near = continuation_plan(23, 4)
+    assert list(cold) == [0, 4, 8, 12, 16, 20, 22] and len(warm) == 16
+    for w, p in zip(warm, near):
+        d = np.abs(cold - w)
+        assert d[p] == d.min() and (p == 0 or d[p - 1] > d[p])           # nearest; ties go to the lower neighbour
+    # 3 rows of 10 cells
+    cold, warm, near = continuation_plan(30, 4, row_length=10)
+    assert list(cold) == [0, 4, 8, 9, 10, 14, 18, 19, 20, 24, 28, 29]
+    assert sorted(list(cold) + list(warm)) == list(range(30))
+    for w, p in zip(warm, near):
+        assert cold[p] // 10 == w // 10                                  # same row
+        same_row = cold[cold // 10 == w // 10]
+        assert abs(cold[p] - w) == np.min(np.abs(same_row - w))
+    # degenerate inputs fall back to one row; k larger than the sweep: first and last cell cold
+    assert list(continuation_plan(7, 4, row_length=3)[0]) == [0, 4, 6]
+    cold, warm, near = continuation_plan(5, 16)
+    assert list(cold) == [0, 4] and list(near) == [0, 0, 1]
+    assert len(continuation_plan(2, 2)[1]) == 0
