@@ -15,6 +15,8 @@ between steps, max over ranks); e2e = the same through Calculator.solve_batch
 with host buffers (H2D of the parameters, solve, D2H of all results per step);
 roofline of the dominant kernel (pnp_bdf_kernel); cpu_baseline = the oracle
 (scipy odeint on the restated RHS) on the host cores.
+continuation = the opt-in Calculator(continuation=k) mode on ONE sweep of 16384*N
+cells, end to end with host buffers (reported beside the headline, never as it).
 
 --impl reference: the reference's CPU path (oracle port; the reference's own FD
 integrator is orphaned Python 2 and cannot run) as a
