@@ -156,3 +156,21 @@ def test_continuation_plan_splits_rows_and_finds_the_nearest_cold_cell():
     cold, warm, near = continuation_plan(5, 16)
     assert list(cold) == [0, 4] and list(near) == [0, 0, 1]
     assert len(continuation_plan(2, 2)[1]) == 0
+
+
+def test_auto_continuation_only_where_it_pays(resultsdir):
+    from catint_b200 import workloads
+    from catint_b200.calculator import auto_continuation_k, Calculator
+    from catint_b200.transport import Transport
+    assert auto_continuation_k(1024) is None and auto_continuation_k(4095) is None        # a plain run is as fast
+    assert auto_continuation_k(16384) == 16 and auto_continuation_k(65536) == 64           # one resident cold wave
+    assert auto_continuation_k(16384, world_size=8) is None and auto_continuation_k(131072, world_size=8) == 16
+    assert auto_continuation_k(65536, row_length=256) is None                               # 2D grid: measured slower
+    tp = Transport(resultsdir=resultsdir, **workloads.c1())
+    tp.set_calculator('odeint')
+    assert Calculator(transport=tp, dt=0.5, tmax=200, mode='stationary', continuation='auto').continuation == 'auto'
+    for bad in ('always', 1):
+        with pytest.raises(SystemExit):
+            Calculator(transport=tp, dt=0.5, tmax=200, mode='stationary', continuation=bad)
+    with pytest.raises(SystemExit):
+        Calculator(transport=tp, dt=0.5, tmax=200, continuation='auto')                    # stationary mode only
