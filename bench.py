@@ -439,7 +439,10 @@ def run_gpu(args):
 
     cont = None
     if not args.no_continuation:
-        cont = continuation_block(bk, dev, world, rank, sync_all)
+        try:
+            cont = continuation_block(bk, dev, world, rank, sync_all)
+        except Exception as e:                              # the side block must never cost the headline line
+            cont = {'error': '%s: %s' % (type(e).__name__, e)}
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)

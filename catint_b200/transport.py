@@ -19,6 +19,7 @@ Design differences (deliberate, B200 batch backend):
 """
 import collections
 import copy
+import functools
 import logging
 import math
 import os
@@ -109,19 +110,31 @@ class _Fatal(object):
 # ----------------------------------------------------------------------
 # parsing helpers
 # ----------------------------------------------------------------------
-def reaction_species(string):
-    """species tokens of a reaction string, in order of appearance, as the
-    reference discovers them (transport.py:553-555,582-586)."""
+@functools.lru_cache(maxsize=4096)
+def _reaction_species(string):
     out = []
     for side in string.split('->'):
         for term in side.split(' + '):
             out.append(_SPECIES_TOKEN.findall(term.strip())[0])
-    return out
+    return tuple(out)
+
+
+def reaction_species(string):
+    """species tokens of a reaction string, in order of appearance, as the
+    reference discovers them (transport.py:553-555,582-586).  (Parsed once per string: a sweep re-derives
+    the model for every cell.)"""
+    return list(_reaction_species(string))
 
 
 def parse_reaction(string):
     """'A + 2 B <-> C' -> ([[A,B,B],[C]], nel) (transport.py:1098-1132);
     nel = number of electrons if an 'n e-' term is present else None."""
+    sides, nel = _parse_reaction(string)
+    return [list(names) for names in sides], nel
+
+
+@functools.lru_cache(maxsize=4096)
+def _parse_reaction(string):
     if '<->' in string:
         sides = sum([part.split('->') for part in string.split('<->')], [])
     else:
@@ -140,8 +153,8 @@ def parse_reaction(string):
             else:
                 mult = int(m_n[0])
                 names.extend([term[len(str(mult)) + 1:].strip()] * mult)
-        parsed.append(names)
-    return parsed, nel
+        parsed.append(tuple(names))
+    return tuple(parsed), nel
 
 
 def charge_from_symbol(symbol):
@@ -249,16 +262,39 @@ def _solve_bulk_equilibria(species, unknowns, eq_names, library, constraints, el
                     out.append(constraints[con] + total)
         return tuple(out)
 
-    sol, _, ier, msg = fsolve(residuals, (1,) * len(unknowns), full_output=True)
+    # A sweep re-derives the model for every cell and most descriptors (phiM, fluxes, boundary thickness) leave the
+    # bulk composition alone: the solve is a deterministic function of the values below, so it is done once per
+    # distinct set of them (the cached numbers are the ones fsolve returned: bit-identical results).
+    key = (tuple(unknowns), tuple((tuple(e), tuple(p), K) for e, p, K in eqs),
+           tuple((sp, species[sp].get('bulk_concentration', None), species[sp].get('charge', None))
+                 for sp in species),
+           None if constraints is None else tuple(sorted(constraints.items())),
+           tuple(electrolyte_species), tuple(exclude))
+    try:
+        hit = _BULK_CACHE.get(key)
+    except TypeError:                     # an unhashable entry (array-valued input): no caching
+        key, hit = None, None
+    if hit is None:
+        sol, _, ier, msg = fsolve(residuals, (1,) * len(unknowns), full_output=True)
+        hit = (tuple(np.atleast_1d(sol)), ier, msg)
+        if key is not None:
+            if len(_BULK_CACHE) >= 8192:
+                _BULK_CACHE.clear()
+            _BULK_CACHE[key] = hit
+    sol, ier, msg = hit
     if ier != 1:
         logger.warning('| CI | -- | bulk buffer equilibria did not converge ({}); the reference would silently '
                        'continue with these values (SURVEY C-8)'.format(msg.replace('\n', ' ')))
     return dict(zip(unknowns, sol))
 
 
+_BULK_CACHE = {}
+
+
 def derive_model(species_in, electrode_reactions_in, electrolyte_reactions_in, system_in, pb_bound_in,
-                 nx_in, logger, tables, quiet=False, flux_env=None):
-    """dicts -> DerivedModel.  Pure: inputs are deep-copied.  Follows the
+                 nx_in, logger, tables, quiet=False, flux_env=None, owned=False):
+    """dicts -> DerivedModel.  Pure: inputs are deep-copied (owned=True: species_in / system_in already are the
+    caller's private copies -- derive_for -- and are used as they are).  Follows the
     order of operations of the reference constructor (transport.py:183-509),
     which matters (e.g. the bulk_pH override happens after charge neutrality)."""
     fatal = _Fatal(logger)
@@ -277,9 +313,9 @@ def derive_model(species_in, electrode_reactions_in, electrolyte_reactions_in, s
             for key in species_in[sp]:
                 if key not in SPECIES_KEYS and key not in _SPECIES_DERIVED_KEYS:
                     fatal('No such key "' + key + '" in species list. Quitting here.')
-        species = copy.deepcopy(species_in)
+        species = species_in if owned else copy.deepcopy(species_in)
     species = collections.OrderedDict(species)
-    system = _prepare_system(copy.deepcopy(system_in), fatal)
+    system = _prepare_system(system_in if owned else copy.deepcopy(system_in), fatal)
     exclude = system['exclude species']
     for es in exclude:
         species.pop(es, None)
@@ -875,7 +911,7 @@ class Transport(object):
                         species[sp][key] = float(species[sp][key](view))
         return derive_model(species, self._inputs['electrode_reactions'], self._inputs['electrolyte_reactions'],
                             system, self._inputs['pb_bound'], self._inputs['nx'], self.logger, self._tables,
-                            quiet=_quiet, flux_env=self._flux_env)
+                            quiet=_quiet, flux_env=self._flux_env, owned=True)
 
     # ------------------------------------------------------------------
     def initialize_descriptors(self, descriptors):
