@@ -472,7 +472,8 @@ class Calculator():
         transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
         wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
         nearest wave-1 neighbour, over the full time span (so a wrong starting guess costs steps, not accuracy).
-        A warm cell may take at most 3x the steps of the slowest converged cold cell; warm cells that fail (or hit that
+        Only cells with the SAME bulk composition as their neighbour are warm-started (the others start from their
+        own bulk state in wave 2).  A warm cell may take at most 3x the steps of the slowest converged cold cell; warm cells that fail (or hit that
         cap) are solved again from the bulk state (wave 3), so a cell that converges in a plain run converges here.
         All waves are sharded like a plain run.  The results of wave 1 stay on the devices: every rank builds the
         initial states of its wave-2 cells there (an index_select of the gathered wave-1 states), the two waves
@@ -505,6 +506,12 @@ class Calculator():
         near_t = torch.as_tensor(nearest, device=dev)    # position (in wave 1) of every warm cell's nearest cold neighbour
         c1 = r1['c'][-1]                                            # [n_cold, nx_max, S]
         ok = (r1['status'] == 0).index_select(0, near_t)            # failed neighbour: cold start from the bulk state
+        # ... and so does a cell whose neighbour has another bulk composition (a sweep over bulk_pH or a bulk
+        # concentration): from such a state the integration may end on another root of the discrete system than the
+        # cold run selects (CPU prototype on C4, profiles/r2/continuation_axis_probe.txt: 4 % off, or a blow-up).
+        cb_w, cb_n = batch.par[warm, 0:S], batch.par[cold[nearest], 0:S]
+        same_bulk = np.all(np.abs(cb_w - cb_n) <= 1e-12 * np.abs(cb_n), axis=1)
+        ok = ok & torch.as_tensor(same_bulk, device=dev)
         bulk = torch.as_tensor(np.ascontiguousarray(batch.par[warm, 0:S])).to(dev)
 
         conv1 = r1['status'] == 0
@@ -551,7 +558,8 @@ class Calculator():
                                    'warm_steps_mean': float(r2['n_steps'].double().mean()),
                                    'warm_newton_mean': float(r2['n_newton'].double().mean()),
                                    'warm_setups_mean': float(r2['n_setups'].double().mean()),
-                                   'warm_step_cap': warm_cap, 'rerun_cold_cells': n_rerun}
+                                   'warm_step_cap': warm_cap, 'rerun_cold_cells': n_rerun,
+                                   'warm_started_cells': int(ok.sum())}
         mark('merge')
         host = _dist.results_to_host(res, root_only=root_only)
         mark('to_host')

@@ -181,6 +181,7 @@ def _continuation_worker(rank, world, port, q, n_cells, k, root_only):
         S = batch.S
         batch.par[k, 3 * S + 4] = -1.0                   # the second cold cell fails: its neighbours start cold
         batch.par[10, 3 * S + 4] = -2.0                  # warm cell 10 fails from its neighbour's state: solved again cold
+        batch.par[18, 0] *= 1.5                          # warm cell 18 has another bulk composition than its neighbour
         calc = Calculator.__new__(Calculator)            # plumbing only: no Transport, no device
         calc.continuation = k
         calc.max_steps = 100000
@@ -208,6 +209,7 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
         assert p.exitcode == 0
     batch = make_batch(n_cells)
     S, n = batch.S, batch.nx_max
+    batch.par[18, 0] *= 1.5
     want = fake_solve(batch)
     cold = sorted(set(range(0, n_cells, k)) | {n_cells - 1})
     for rank in range(world):
@@ -228,7 +230,7 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
                 assert np.array_equal(start, bulk)
                 continue
             near = min(cold, key=lambda c: (abs(c - cell), c))
-            if near == k or cell == 10:                  # failed neighbour / re-run after a failed warm start -> bulk state
+            if near == k or cell in (10, 18):            # failed neighbour / re-run after a failed warm start / other bulk
                 assert np.array_equal(start, bulk)
             else:
                 assert np.array_equal(start, want['c'][1, near]), (cell, near)
