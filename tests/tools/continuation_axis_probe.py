@@ -1,10 +1,10 @@
 """CPU probe (oracle BDF, the algorithmic prototype of the CUDA integrator: same step/order control): how many BDF
 steps does a C4 cell need from the bulk state, from the converged state of a neighbour along the bulk-pH axis, and
 from one along the boundary-layer axis?  Decides the continuation axis of 2D sweeps (Calculator.run_continuation).
-    OMP_NUM_THREADS=1 python scripts/continuation_axis_probe.py [i_pH] [i_L] [offsets ...]
-Test infrastructure (uses oracle/); not part of the product path."""
+    OMP_NUM_THREADS=1 python tests/tools/continuation_axis_probe.py [i_pH] [i_L] [offsets ...]
+Test infrastructure (lives under tests/ because it uses oracle/); not part of the product path."""
 import os, sys, tempfile, time
-HERE = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, os.path.dirname(HERE))
+HERE = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 os.environ.setdefault('CATINT_QUIET', '1')
 import numpy as np
 from catint_b200 import workloads

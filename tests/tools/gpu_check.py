@@ -3,7 +3,7 @@ import os, sys, time
 import numpy as np
 import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from catint_b200 import backend as be
 from oracle.fixtures import system_from_setup, parse_rx
 from oracle.pnp_local import LocalForm
@@ -25,7 +25,7 @@ def batch_from_setup(su, B=1, rate_mode='summed', fluxes=None):
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else 'c1'
-    su = dict(np.load(os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'ref_%s.npz' % name)))
+    su = dict(np.load(os.path.join(os.path.dirname(HERE), 'golden', 'ref_%s.npz' % name)))
     S, n = len(su['z']), int(su['nx'])
     bk = be.PnpBackend('cuda:0')
     batch = batch_from_setup(su, B=4)
@@ -66,7 +66,7 @@ def main():
         print('K3 mode %d: %.3fs status %s steps %s newton %s' % (mode, dt, out['status'].tolist(), out['n_steps'].tolist(), out['n_newton'].tolist()))
         cfin = out['c'][-1, 0].cpu().numpy()
         print('   surface c:', cfin[0])
-        gp = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'oracle_%s_summed.npz' % name)
+        gp = os.path.join(os.path.dirname(HERE), 'golden', 'oracle_%s_summed.npz' % name)
         if os.path.exists(gp):
             go = dict(np.load(gp))
             key = 'newton_c' if mode == be.MODE_STEADY else 'c_end'
