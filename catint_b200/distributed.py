@@ -106,6 +106,16 @@ def unpack_results(gathered, n_cells, world_size, n_out, nx_max, S):
     return full
 
 
+# Result arrays are numpy views of page-locked blocks (see _to_host_pinned).  A caller that keeps MANY results alive
+# holds that much page-locked memory; CATINT_PINNED_RESULTS=0 hands out pageable copies instead (one more host copy).
+PINNED_RESULTS = os.environ.get('CATINT_PINNED_RESULTS', '1') != '0'
+
+
+def _as_result(h):
+    a = h.numpy()
+    return a if PINNED_RESULTS else np.array(a, copy=True)
+
+
 def _to_host_pinned(t, key=None):
     """device tensor -> a FRESH pinned host tensor (asynchronous copy on the current stream; the caller synchronises
     and hands out its numpy view).  Pageable copies of the gathered results cost several times the kernel at 8
@@ -162,7 +172,7 @@ def gather_results(local, n_cells, world_size, n_out, nx_max, S, device=None, ro
     if out.device.type == 'cuda':
         torch.cuda.current_stream(out.device).synchronize()
     for name, h in staged.items():
-        full[name] = h.numpy()                        # view of this call's own pinned block (kept alive by the array)
+        full[name] = _as_result(h)                    # view of this call's own pinned block (kept alive by the array)
     full['gather_bytes'] = int(out.numel() * 8)
     return full
 
@@ -222,7 +232,7 @@ def results_to_host(res, root_only=False):
     if dev is not None:
         torch.cuda.current_stream(dev).synchronize()
     for k, h in staged.items():
-        full[k] = h.numpy()
+        full[k] = _as_result(h)
     return full
 
 
