@@ -174,3 +174,16 @@ def test_auto_continuation_only_where_it_pays(resultsdir):
             Calculator(transport=tp, dt=0.5, tmax=200, mode='stationary', continuation=bad)
     with pytest.raises(SystemExit):
         Calculator(transport=tp, dt=0.5, tmax=200, continuation='auto')                    # stationary mode only
+
+
+def test_continuation_brackets_interpolation_weights():
+    from catint_b200.calculator import continuation_plan, continuation_brackets
+    cold, warm, _ = continuation_plan(30, 4, row_length=10)
+    left, right, w = continuation_brackets(cold, warm, row_length=10)
+    for cell, l, r, wt in zip(warm, left, right, w):
+        assert cold[l] < cell < cold[r] and cold[l] // 10 == cell // 10 == cold[r] // 10
+        assert not np.any((cold > cold[l]) & (cold < cold[r]))                  # adjacent cold cells
+        assert wt == (cell - cold[l]) / float(cold[r] - cold[l]) and 0.0 < wt < 1.0
+    cold, warm, _ = continuation_plan(23, 4)
+    left, right, w = continuation_brackets(cold, warm)
+    assert list(cold[left][-1:]) == [20] and list(cold[right][-1:]) == [22] and w[-1] == 0.5
