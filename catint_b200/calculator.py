@@ -525,6 +525,7 @@ class Calculator():
         # cold run selects (CPU prototype on C4, profiles/r2/continuation_axis_probe.txt: 4 % off, or a blow-up).
         cb_w, cb_n = batch.par[warm, 0:S], batch.par[cold[nearest], 0:S]
         same_bulk = np.all(np.abs(cb_w - cb_n) <= 1e-12 * np.abs(cb_n), axis=1)
+        same_bulk &= batch.nx[warm] == batch.nx[cold[nearest]]     # ragged grids: a state only fits a cell of its node count
         ok = ok & torch.as_tensor(same_bulk, device=dev)
         bulk = torch.as_tensor(np.ascontiguousarray(batch.par[warm, 0:S])).to(dev)
 
@@ -548,6 +549,7 @@ class Calculator():
             for side in (left, right):
                 cb_s = batch.par[cold[side], 0:S]
                 same2 &= np.all(np.abs(cb_w - cb_s) <= 1e-12 * np.abs(cb_s), axis=1)
+                same2 &= batch.nx[warm] == batch.nx[cold[side]]
             ok2 = conv1.index_select(0, left_t) & conv1.index_select(0, right_t) & torch.as_tensor(same2, device=dev)
         else:
             ok2 = torch.zeros_like(ok)

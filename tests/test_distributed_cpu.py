@@ -231,17 +231,21 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
                 continue
             near = min(cold, key=lambda c: (abs(c - cell), c))
             left, right = max(c for c in cold if c < cell), min(c for c in cold if c > cell)
+            nxc = batch.nx
+            both = k not in (left, right) and nxc[left] == nxc[cell] == nxc[right]
             if cell in (10, 18):                         # re-run after a failed warm start / other bulk composition
                 assert np.array_equal(start, bulk)
-            elif k not in (left, right):                 # both bracketing cold cells converged: interpolated state
+            elif both:                                   # both bracketing cold cells converged, same node count
                 w = (cell - left) / float(right - left)
                 mix = torch.lerp(torch.as_tensor(want['c'][1, left]), torch.as_tensor(want['c'][1, right]),
                                  torch.tensor(w, dtype=torch.float64)).numpy()
                 assert np.array_equal(start, mix), (cell, left, right)
-            elif near == k:                              # failed nearest neighbour -> bulk state
+            elif near == k or nxc[near] != nxc[cell]:    # failed nearest neighbour / other node count -> bulk state
                 assert np.array_equal(start, bulk)
-            else:                                        # one bracket failed, the nearest one is fine: its state
+            else:                                        # only the nearest one fits: its state
                 assert np.array_equal(start, want['c'][1, near]), (cell, near)
         assert res['stats']['interpolated_starts'] == sum(
             1 for cell in range(n_cells) if cell not in cold and cell != 18
-            and k not in (max(c for c in cold if c < cell), min(c for c in cold if c > cell)))
+            and k not in (max(c for c in cold if c < cell), min(c for c in cold if c > cell))
+            and batch.nx[max(c for c in cold if c < cell)] == batch.nx[cell] == batch.nx[min(c for c in cold if c > cell)])
+        assert 0 < res['stats']['interpolated_starts'] < res['stats']['warm_started_cells']
