@@ -561,7 +561,7 @@ class Calculator():
             if interp:
                 a = c1.index_select(0, left_t.index_select(0, o))
                 b = c1.index_select(0, right_t.index_select(0, o))
-                mix = torch.lerp(a, b, w_t.index_select(0, o)[:, None, None])
+                mix = a + (b - a) * w_t.index_select(0, o)[:, None, None]
                 src = torch.where(ok2.index_select(0, o)[:, None, None], mix, src)
             y0 = torch.where(ok.index_select(0, o)[:, None, None], src, bulk.index_select(0, o)[:, None, :])
             return self.solve_batch_device(sb, y0=y0.contiguous(), max_steps=warm_cap)

@@ -237,8 +237,7 @@ def test_continuation_waves_start_from_the_nearest_cold_neighbour(world, root_on
                 assert np.array_equal(start, bulk)
             elif both:                                   # both bracketing cold cells converged, same node count
                 w = (cell - left) / float(right - left)
-                mix = torch.lerp(torch.as_tensor(want['c'][1, left]), torch.as_tensor(want['c'][1, right]),
-                                 torch.tensor(w, dtype=torch.float64)).numpy()
+                mix = want['c'][1, left] + (want['c'][1, right] - want['c'][1, left]) * w
                 assert np.array_equal(start, mix), (cell, left, right)
             elif near == k or nxc[near] != nxc[cell]:    # failed nearest neighbour / other node count -> bulk state
                 assert np.array_equal(start, bulk)
