@@ -483,15 +483,19 @@ class Calculator():
     def run_continuation(self, batch, root_only=False, row_length=None, k=None):
         """two waves over a sweep (the batch analogue of the reference's COMSOL option 'internal-cont',
         transport.py:834-842: "the solution of the previous parameter set is used to initialize the next"):
-        wave 1 solves every k-th cell from the bulk state, wave 2 the others from the converged state of their
-        nearest wave-1 neighbour, over the full time span (so a wrong starting guess costs steps, not accuracy).
-        Only cells with the SAME bulk composition as their neighbour are warm-started (the others start from their
-        own bulk state in wave 2).  A warm cell may take at most 3x the steps of the slowest converged cold cell; warm cells that fail (or hit that
-        cap) are solved again from the bulk state (wave 3), so a cell that converges in a plain run converges here.
+        wave 1 solves every k-th cell from the bulk state, wave 2 the others from a state built out of the
+        converged wave-1 states, over the full time span (so a poor starting guess costs steps, not accuracy).
+        Starting state of a warm cell: the linear interpolation, along the sweep, of the two cold cells that
+        bracket it; if one of them failed, the state of the nearest one; else the cell's own bulk state.  Only
+        cold cells with the warm cell's bulk composition and node count are used (from another composition the
+        integration may end on another root of the discrete system).  A warm cell may take at most
+        3x the steps of the slowest converged cold cell; warm cells that fail (or hit that cap) are solved again
+        from the bulk state (wave 3), so a cell that converges in a plain run converges here.
         All waves are sharded like a plain run.  The results of wave 1 stay on the devices: every rank builds the
-        initial states of its wave-2 cells there (an index_select of the gathered wave-1 states), the two waves
-        are merged there, and ONE device->host copy brings the whole batch to the host (root_only: of rank 0
-        only; the other ranks return None).  Returns the result dict of the whole batch."""
+        initial states of its wave-2 cells there (index_select of the gathered wave-1 states), the waves are
+        merged there, and ONE device->host copy brings the whole batch to the host (root_only: of rank 0 only;
+        the other ranks return None).  row_length: cells per row of a 2D descriptor grid (the plan is made per
+        row); k overrides self.continuation.  Returns the result dict of the whole batch."""
         import torch
         from . import distributed as _dist
         k = int(self.continuation if k is None else k)
