@@ -187,3 +187,41 @@ def test_continuation_brackets_interpolation_weights():
     cold, warm, _ = continuation_plan(23, 4)
     left, right, w = continuation_brackets(cold, warm)
     assert list(cold[left][-1:]) == [20] and list(cold[right][-1:]) == [22] and w[-1] == 0.5
+
+
+def test_run_with_continuation_end_to_end_on_a_stand_in_solver(resultsdir):
+    """Calculator.run() with continuation: descriptor grid -> plan -> waves -> result containers, with the device solve
+    replaced by a stand-in (plumbing only; the product has no CPU solver)."""
+    import torch
+    tp = Transport(resultsdir=resultsdir, model_name='cont', **workloads.c2(n_potentials=12))
+    tp.set_calculator('odeint')
+    calc = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', continuation=4)
+    calls = []
+
+    def stand_in(sub, backend=None, pinned=None, y0=None, max_steps=None):
+        B, n, S = sub.B, sub.nx_max, sub.S
+        calls.append((B, y0 is not None))
+        c = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(sub.par[:, None, 0:S], (B, n, S)))).clone()[None]
+        if y0 is not None:
+            assert tuple(y0.shape) == (B, n, S) and y0.dtype == torch.float64
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64)
+        i32 = lambda v: torch.full((B,), v, dtype=torch.int32)
+        return {'c': c, 'phi': z(1, B, n), 'g': z(1, B, n), 'flux': torch.as_tensor(sub.par[:, S:2 * S].copy()),
+                'status': i32(0), 'n_steps': i32(7 if y0 is not None else 70), 'n_newton': i32(9), 'n_setups': i32(3),
+                'h2d_bytes': 1}
+
+    calc.solve_batch_device = stand_in
+    res = calc.run()
+    assert calls == [(4, False), (8, True)]                       # cells 0,4,8,11 cold; the other 8 warm
+    assert calc.stats['converged'] == 12 and res['c'].shape == (1, 12, tp.nx, len(tp.species))
+    assert list(res['n_steps']) == [70, 7, 7, 7, 70, 7, 7, 7, 70, 7, 7, 70]
+    st = calc.continuation_stats
+    assert st['cold_cells'] == 4 and st['warm_cells'] == 8 and st['interpolated_starts'] == 8 and st['rerun_cold_cells'] == 0
+    assert len(tp.alldata) == 12 and 'surface_concentration' in tp.alldata[5]['species']['CO2']
+    # 'auto' on a sweep this small is a plain run
+    calc2 = Calculator(transport=tp, dt=0.5, tmax=200, ntout=1, mode='stationary', continuation='auto')
+    calls.clear()
+    calc2.solve_batch_device = stand_in
+    calc2.solve_batch = lambda batch, **kw: {k: (v.numpy() if hasattr(v, 'numpy') else v) for k, v in stand_in(batch).items()}
+    calc2.run()
+    assert calls == [(12, False)]
